@@ -1,0 +1,487 @@
+/*
+ * epx_api.cu — session state and the C ABI of libepx.so (include/epx.h).
+ *
+ * Host work done here is integer bookkeeping only (CSR validation, unique-probe slots, work items,
+ * the Kolmogorov-Smirnov p-value lookup table, which depends on the group size alone); every
+ * statistic of the path is computed by the kernels in epx_kernels.cu. There is no CPU fallback.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "epx_internal.h"
+#include "epx_math.h"
+
+using namespace epx;
+
+namespace {
+
+int fail(char *err, size_t errlen, int code, const char *fmt, ...)
+{
+    if (err && errlen) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(err, errlen, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define EPX_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(err, errlen, e_ == cudaErrorMemoryAllocation ? EPX_ENOMEM : EPX_ECUDA, "%s: %s", \
+                        #call, cudaGetErrorString(e_));                                                  \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0; /* elements */
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+struct epx_session {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    /* methylation, probe-major */
+    DevBuf<double> meth_own;
+    const double *meth = nullptr;
+    int64_t P = 0, n_meth = 0, ld = 0;
+    /* expression */
+    DevBuf<double> expr;
+    int64_t G = 0, n = 0;
+    /* index */
+    DevBuf<int32_t> probe_idx, pair_slot, uniq_probe;
+    DevBuf<Item> items;
+    int64_t Np = 0, U = 0, n_items = 0, G_index = -1;
+    /* per-gene and per-probe intermediates */
+    DevBuf<uint16_t> perm, ord;
+    DevBuf<uint8_t> lab8;
+    DevBuf<double> xc, gene_aux, lut;
+    DevBuf<int32_t> nuniq, scal; /* scal: counts[3], ref_gene, status */
+    int64_t ldl = 0, ldx = 0, ldo = 0;
+    int lut_m = -1;
+    /* results */
+    DevBuf<double> pair, pair_stat, gene;
+    DevBuf<uint16_t> pair_na, gene_na;
+    DevBuf<int32_t> pair_dnum, gene_dnum;
+    /* timing */
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool ran = false;
+    int launches = 0;
+    void *staging = nullptr; /* pinned */
+    size_t staging_bytes = 0;
+};
+
+extern "C" {
+
+int epx_abi_version(void) { return EPX_ABI_VERSION; }
+
+int epx_device_count(int *count, char *err, size_t errlen)
+{
+    if (!count) return fail(err, errlen, EPX_EINVAL, "count is NULL");
+    EPX_CUDA(cudaGetDeviceCount(count));
+    return EPX_OK;
+}
+
+int epx_device_info(int device, char *name, size_t namelen, int *sm_count, int64_t *mem_bytes, char *err,
+                    size_t errlen)
+{
+    cudaDeviceProp prop;
+    EPX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name && namelen) snprintf(name, namelen, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = (int64_t)prop.totalGlobalMem;
+    return EPX_OK;
+}
+
+void epx_options_default(epx_options *opt)
+{
+    if (!opt) return;
+    memset(opt, 0, sizeof(*opt));
+    opt->struct_size = (int32_t)sizeof(*opt);
+    opt->data_linear = 1;
+    opt->test_expr_t = 1;
+    opt->test_meth_t = 0;
+}
+
+int epx_host_alloc(void **ptr, size_t bytes, char *err, size_t errlen)
+{
+    if (!ptr) return fail(err, errlen, EPX_EINVAL, "ptr is NULL");
+    EPX_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return EPX_OK;
+}
+
+void epx_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
+{
+    if (!out) return fail(err, errlen, EPX_EINVAL, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    EPX_CUDA(cudaGetDeviceCount(&count));
+    if (count <= 0) return fail(err, errlen, EPX_ECUDA, "no CUDA device: libepx has no CPU fallback");
+    if (device < 0 || device >= count) return fail(err, errlen, EPX_EINVAL, "device %d out of range [0,%d)", device, count);
+    EPX_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EPX_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(err, errlen, EPX_ECUDA, "device %d is sm_%d%d; libepx is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    EPX_CUDA(kernels_init());
+    epx_session *s = new (std::nothrow) epx_session();
+    if (!s) return fail(err, errlen, EPX_ENOMEM, "out of host memory");
+    s->device = device;
+    s->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = s->scal.reserve(8);
+    if (e != cudaSuccess) {
+        epx_session_destroy(s);
+        return fail(err, errlen, EPX_ECUDA, "session setup: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return EPX_OK;
+}
+
+void epx_session_destroy(epx_session *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    s->meth_own.release(); s->expr.release(); s->probe_idx.release(); s->pair_slot.release();
+    s->uniq_probe.release(); s->items.release(); s->perm.release(); s->ord.release(); s->lab8.release();
+    s->xc.release(); s->gene_aux.release(); s->lut.release(); s->nuniq.release(); s->scal.release();
+    s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
+    s->pair_dnum.release(); s->gene_dnum.release();
+    for (int i = 0; i < 6; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->staging) cudaFreeHost(s->staging);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int check_samples(epx_session *s, int64_t n, char *err, size_t errlen)
+{
+    if (n < 3) return fail(err, errlen, EPX_EINVAL, "need at least 3 samples, got %lld", (long long)n);
+    if (n > 16384) return fail(err, errlen, EPX_EINVAL, "n_samples %lld exceeds the supported maximum 16384", (long long)n);
+    (void)s;
+    return EPX_OK;
+}
+
+int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t n_probes, int64_t n_samples,
+                                     int64_t ld, char *err, size_t errlen)
+{
+    if (!s || !rows || n_probes < 1 || ld < n_samples) return fail(err, errlen, EPX_EINVAL, "bad methylation arguments");
+    int rc = check_samples(s, n_samples, err, errlen);
+    if (rc) return rc;
+    EPX_CUDA(cudaSetDevice(s->device));
+    const int64_t dld = round_up(n_samples, 4); /* 32-byte aligned rows */
+    EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
+    EPX_CUDA(cudaMemcpy2DAsync(s->meth_own.p, (size_t)dld * 8, rows, (size_t)ld * 8, (size_t)n_samples * 8,
+                               (size_t)n_probes, cudaMemcpyHostToDevice, s->stream));
+    EPX_CUDA(cudaStreamSynchronize(s->stream));
+    s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
+    s->G_index = -1; /* slots refer to the previous matrix */
+    return EPX_OK;
+}
+
+int epx_session_set_methylation_cols(epx_session *s, const double *const *cols, int64_t n_samples, int64_t n_probes,
+                                     char *err, size_t errlen)
+{
+    if (!s || !cols || n_probes < 1) return fail(err, errlen, EPX_EINVAL, "bad methylation arguments");
+    int rc = check_samples(s, n_samples, err, errlen);
+    if (rc) return rc;
+    EPX_CUDA(cudaSetDevice(s->device));
+    const int64_t dld = round_up(n_samples, 4);
+    EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
+    /* stage a chunk of sample columns on the device, transpose into probe-major rows */
+    int chunk = (int)((int64_t)(256ll << 20) / (n_probes * 8));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_samples) chunk = (int)n_samples;
+    DevBuf<double> stage;
+    EPX_CUDA(stage.reserve((size_t)chunk * (size_t)n_probes));
+    for (int64_t s0 = 0; s0 < n_samples; s0 += chunk) {
+        const int ns = (int)((n_samples - s0) < chunk ? (n_samples - s0) : chunk);
+        for (int j = 0; j < ns; j++) {
+            if (!cols[s0 + j]) { stage.release(); return fail(err, errlen, EPX_EINVAL, "column %lld is NULL", (long long)(s0 + j)); }
+            cudaError_t e = cudaMemcpyAsync(stage.p + (size_t)j * n_probes, cols[s0 + j], (size_t)n_probes * 8,
+                                            cudaMemcpyHostToDevice, s->stream);
+            if (e != cudaSuccess) { stage.release(); return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e)); }
+        }
+        cudaError_t e = launch_transpose_cols(stage.p, s->meth_own.p, n_probes, ns, s0, dld, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) { stage.release(); return fail(err, errlen, EPX_ECUDA, "transpose: %s", cudaGetErrorString(e)); }
+    }
+    stage.release();
+    s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
+    s->G_index = -1;
+    return EPX_OK;
+}
+
+int epx_session_set_methylation_device(epx_session *s, const double *d_rows, int64_t n_probes, int64_t n_samples,
+                                       int64_t ld, char *err, size_t errlen)
+{
+    if (!s || !d_rows || n_probes < 1 || ld < n_samples) return fail(err, errlen, EPX_EINVAL, "bad methylation arguments");
+    int rc = check_samples(s, n_samples, err, errlen);
+    if (rc) return rc;
+    s->meth_own.release();
+    s->meth = d_rows; s->P = n_probes; s->n_meth = n_samples; s->ld = ld;
+    s->G_index = -1;
+    return EPX_OK;
+}
+
+int epx_session_set_expression(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples, int is_device,
+                               char *err, size_t errlen)
+{
+    if (!s || !expr || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad expression arguments");
+    int rc = check_samples(s, n_samples, err, errlen);
+    if (rc) return rc;
+    EPX_CUDA(cudaSetDevice(s->device));
+    EPX_CUDA(s->expr.reserve((size_t)(n_genes * n_samples)));
+    EPX_CUDA(cudaMemcpyAsync(s->expr.p, expr, (size_t)(n_genes * n_samples) * 8,
+                             is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream));
+    EPX_CUDA(cudaStreamSynchronize(s->stream));
+    s->G = n_genes; s->n = n_samples;
+    return EPX_OK;
+}
+
+int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
+                          char *err, size_t errlen)
+{
+    if (!s || !row_ptr || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad index arguments");
+    if (!s->meth) return fail(err, errlen, EPX_ESTATE, "set the methylation matrix before the index");
+    if (row_ptr[0] != 0) return fail(err, errlen, EPX_EINVAL, "row_ptr[0] must be 0");
+    const int64_t Np = row_ptr[n_genes];
+    if (Np < 0 || Np > 0x7fffffff) return fail(err, errlen, EPX_EINVAL, "pair count %lld out of range", (long long)Np);
+    if (Np > 0 && !probe_idx) return fail(err, errlen, EPX_EINVAL, "probe_idx is NULL");
+    EPX_CUDA(cudaSetDevice(s->device));
+
+    std::vector<int32_t> slot_of((size_t)s->P, -1), pair_slot((size_t)Np), uniq;
+    std::vector<Item> items;
+    for (int64_t g = 0; g < n_genes; g++) {
+        const int64_t b = row_ptr[g], e = row_ptr[g + 1];
+        if (e < b || e > Np) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)g);
+        for (int64_t j = b; j < e; j++) {
+            const int32_t pi = probe_idx[j];
+            if (pi >= s->P) return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d >= n_probes %lld", (long long)j, pi, (long long)s->P);
+            if (pi < 0) { pair_slot[(size_t)j] = -1; continue; }
+            if (slot_of[(size_t)pi] < 0) { slot_of[(size_t)pi] = (int32_t)uniq.size(); uniq.push_back(pi); }
+            pair_slot[(size_t)j] = slot_of[(size_t)pi];
+        }
+        for (int64_t j = b; j < e; j += ITEM_PAIRS) {
+            Item it;
+            it.gene = (int32_t)g; it.begin = (int32_t)j;
+            it.count = (int32_t)((e - j) < ITEM_PAIRS ? (e - j) : ITEM_PAIRS); it.pad = 0;
+            items.push_back(it);
+        }
+    }
+    EPX_CUDA(s->probe_idx.reserve((size_t)Np));
+    EPX_CUDA(s->pair_slot.reserve((size_t)Np));
+    EPX_CUDA(s->uniq_probe.reserve(uniq.size()));
+    EPX_CUDA(s->items.reserve(items.size()));
+    if (Np) {
+        EPX_CUDA(cudaMemcpyAsync(s->probe_idx.p, probe_idx, (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(cudaMemcpyAsync(s->pair_slot.p, pair_slot.data(), (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (!uniq.empty())
+        EPX_CUDA(cudaMemcpyAsync(s->uniq_probe.p, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    if (!items.empty())
+        EPX_CUDA(cudaMemcpyAsync(s->items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, s->stream));
+    EPX_CUDA(cudaStreamSynchronize(s->stream)); /* the vectors die with this scope */
+    s->Np = Np; s->U = (int64_t)uniq.size(); s->n_items = (int64_t)items.size(); s->G_index = n_genes;
+    return EPX_OK;
+}
+
+/* KS p-value lookup for two groups of equal size m: index d = max|cA - cB|, numerator d*m */
+static int build_ks_lut(epx_session *s, int m, cudaStream_t st, char *err, size_t errlen)
+{
+    if (s->lut_m == m) return EPX_OK;
+    std::vector<double> lut((size_t)2 * (m + 1)), u((size_t)m + 2);
+    const bool exact_ok = (double)m * (double)m < 10000.0;
+    for (int d = 0; d <= m; d++) {
+        const double dnum = (double)d * (double)m;
+        lut[(size_t)d] = exact_ok ? epx_ks_p_exact(dnum, m, m, u.data()) : EPX_NAN;
+        lut[(size_t)(m + 1 + d)] = epx_ks_p_asym(dnum, (double)m, (double)m);
+    }
+    EPX_CUDA(s->lut.reserve(lut.size()));
+    EPX_CUDA(cudaMemcpyAsync(s->lut.p, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice, st));
+    EPX_CUDA(cudaStreamSynchronize(st));
+    s->lut_m = m;
+    return EPX_OK;
+}
+
+int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, char *err, size_t errlen)
+{
+    if (!s) return fail(err, errlen, EPX_EINVAL, "session is NULL");
+    epx_options opt;
+    epx_options_default(&opt);
+    if (opt_in) {
+        size_t sz = opt_in->struct_size > 0 && (size_t)opt_in->struct_size < sizeof(opt) ? (size_t)opt_in->struct_size : sizeof(opt);
+        memcpy(&opt, opt_in, sz);
+    }
+    if (!s->meth || !s->expr.p) return fail(err, errlen, EPX_ESTATE, "methylation and expression must be set before run");
+    if (s->G_index != s->G) return fail(err, errlen, EPX_ESTATE, "index covers %lld genes, expression has %lld", (long long)s->G_index, (long long)s->G);
+    if (s->n_meth != s->n) return fail(err, errlen, EPX_EINVAL, "sample counts differ: expression %lld, methylation %lld", (long long)s->n, (long long)s->n_meth);
+    const int n = (int)s->n;
+    if (opt.strict_n3 && n % 3 != 0)
+        return fail(err, errlen, EPX_ESTRICT, "arguments imply differing number of rows: %d, %d", n, 3 * (n / 3));
+    if (n > MAX_WARP_SAMPLES && s->Np > 0)
+        return fail(err, errlen, EPX_EINVAL, "n_samples %d > %d is not supported by the pair kernel yet", n, MAX_WARP_SAMPLES);
+    EPX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const int m = n / 3;
+    const int64_t G = s->G, Np = s->Np;
+
+    s->ldl = round_up(n, 16); s->ldx = round_up(n, 2); s->ldo = round_up(n, 16);
+    EPX_CUDA(s->perm.reserve((size_t)(G * n)));
+    EPX_CUDA(s->lab8.reserve((size_t)(G * s->ldl)));
+    EPX_CUDA(s->xc.reserve((size_t)(G * s->ldx)));
+    EPX_CUDA(s->gene_aux.reserve((size_t)(G * 2)));
+    EPX_CUDA(s->nuniq.reserve((size_t)G));
+    EPX_CUDA(s->ord.reserve((size_t)(s->U * s->ldo)));
+    EPX_CUDA(s->gene.reserve((size_t)(G * GENE_COLS)));
+    EPX_CUDA(s->gene_na.reserve((size_t)G));
+    EPX_CUDA(s->gene_dnum.reserve((size_t)(G * 3)));
+    EPX_CUDA(s->pair.reserve((size_t)(Np * PAIR_COLS)));
+    EPX_CUDA(s->pair_na.reserve((size_t)Np));
+    EPX_CUDA(s->pair_stat.reserve((size_t)(Np * 3)));
+    EPX_CUDA(s->pair_dnum.reserve((size_t)(Np * 3)));
+    int rc = build_ks_lut(s, m, st, err, errlen);
+    if (rc) return rc;
+
+    GeneParams gp;
+    gp.expr = s->expr.p; gp.n = n; gp.G = (int)G; gp.npad = next_pow2(n); gp.m = m;
+    gp.perm = s->perm.p; gp.lab8 = s->lab8.p; gp.ldl = s->ldl; gp.xc = s->xc.p; gp.ldx = s->ldx;
+    gp.gene_aux = s->gene_aux.p; gp.nuniq = s->nuniq.p;
+
+    GeneTestParams tp;
+    tp.expr = s->expr.p; tp.perm = s->perm.p; tp.n = n; tp.G = (int)G; tp.nuniq = s->nuniq.p;
+    tp.counts = s->scal.p; tp.ref_gene = s->scal.p + 3; tp.status = s->scal.p + 4;
+    tp.test_t = opt.test_expr_t; tp.data_linear = opt.data_linear; tp.fc_from_means = opt.fc_from_means;
+    tp.gene = s->gene.p; tp.gene_na = s->gene_na.p; tp.gene_dnum = s->gene_dnum.p;
+
+    RankParams rp;
+    rp.meth = s->meth; rp.ld = s->ld; rp.uniq_probe = s->uniq_probe.p; rp.U = s->U; rp.n = n; rp.npad = next_pow2(n);
+    rp.ord = s->ord.p; rp.ldo = s->ldo;
+
+    PairParams pp;
+    pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;
+    pp.pair_slot = s->pair_slot.p; pp.xc = s->xc.p; pp.ldx = s->ldx; pp.lab8 = s->lab8.p; pp.ldl = s->ldl;
+    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items;
+    pp.n = n; pp.m = m; pp.test_t = opt.test_meth_t;
+    pp.exact_ok = ((double)m * (double)m < 10000.0) ? 1 : 0;
+    pp.lut_exact = s->lut.p; pp.lut_asym = s->lut.p + (m + 1);
+    pp.pair = s->pair.p; pp.pair_na = s->pair_na.p; pp.pair_stat = s->pair_stat.p; pp.pair_dnum = s->pair_dnum.p;
+
+    s->launches = 0;
+    EPX_CUDA(cudaEventRecord(s->ev[0], st));
+    EPX_CUDA(launch_gene_sort(gp, st)); s->launches++;
+    EPX_CUDA(cudaEventRecord(s->ev[1], st));
+    EPX_CUDA(launch_pick_reference(tp, st)); s->launches++;
+    EPX_CUDA(launch_gene_tests(tp, st)); s->launches++;
+    EPX_CUDA(cudaEventRecord(s->ev[2], st));
+    if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, st)); s->launches++; }
+    EPX_CUDA(cudaEventRecord(s->ev[3], st));
+    if (s->n_items > 0) { EPX_CUDA(launch_pair_stats(pp, s->sm_count, st)); s->launches++; }
+    EPX_CUDA(cudaEventRecord(s->ev[4], st));
+    s->ran = true;
+    return EPX_OK;
+}
+
+int epx_session_fetch(epx_session *s, epx_result *out, void *stream, char *err, size_t errlen)
+{
+    if (!s || !out) return fail(err, errlen, EPX_EINVAL, "NULL argument");
+    if (!s->ran) return fail(err, errlen, EPX_ESTATE, "fetch before run");
+    EPX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    int32_t scal[5];
+    EPX_CUDA(cudaMemcpyAsync(scal, s->scal.p, sizeof(scal), cudaMemcpyDeviceToHost, st));
+    const size_t Np = (size_t)s->Np, G = (size_t)s->G, n = (size_t)s->n;
+    if (out->pair && Np) EPX_CUDA(cudaMemcpyAsync(out->pair, s->pair.p, Np * PAIR_COLS * 8, cudaMemcpyDeviceToHost, st));
+    if (out->pair_na && Np) EPX_CUDA(cudaMemcpyAsync(out->pair_na, s->pair_na.p, Np * 2, cudaMemcpyDeviceToHost, st));
+    if (out->pair_stat && Np) EPX_CUDA(cudaMemcpyAsync(out->pair_stat, s->pair_stat.p, Np * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (out->pair_ks_dnum && Np) EPX_CUDA(cudaMemcpyAsync(out->pair_ks_dnum, s->pair_dnum.p, Np * 3 * 4, cudaMemcpyDeviceToHost, st));
+    if (out->gene) EPX_CUDA(cudaMemcpyAsync(out->gene, s->gene.p, G * GENE_COLS * 8, cudaMemcpyDeviceToHost, st));
+    if (out->gene_na) EPX_CUDA(cudaMemcpyAsync(out->gene_na, s->gene_na.p, G * 2, cudaMemcpyDeviceToHost, st));
+    if (out->gene_ks_dnum) EPX_CUDA(cudaMemcpyAsync(out->gene_ks_dnum, s->gene_dnum.p, G * 3 * 4, cudaMemcpyDeviceToHost, st));
+    if (out->perm) EPX_CUDA(cudaMemcpyAsync(out->perm, s->perm.p, G * n * 2, cudaMemcpyDeviceToHost, st));
+    EPX_CUDA(cudaStreamSynchronize(st));
+    out->counts[0] = scal[0]; out->counts[1] = scal[1]; out->counts[2] = scal[2];
+    out->ref_gene = scal[3];
+    if (scal[4] == ST_BREAKS_NOT_UNIQUE)
+        return fail(err, errlen, EPX_EBREAKS, "bin.var on reference gene %d: 'breaks' are not unique", scal[3]);
+    return EPX_OK;
+}
+
+int epx_session_timing(epx_session *s, epx_timing *out, char *err, size_t errlen)
+{
+    if (!s || !out) return fail(err, errlen, EPX_EINVAL, "NULL argument");
+    if (!s->ran) return fail(err, errlen, EPX_ESTATE, "timing before run");
+    EPX_CUDA(cudaSetDevice(s->device));
+    EPX_CUDA(cudaEventSynchronize(s->ev[4]));
+    memset(out, 0, sizeof(*out));
+    EPX_CUDA(cudaEventElapsedTime(&out->total_ms, s->ev[0], s->ev[4]));
+    EPX_CUDA(cudaEventElapsedTime(&out->gene_sort_ms, s->ev[0], s->ev[1]));
+    EPX_CUDA(cudaEventElapsedTime(&out->gene_tests_ms, s->ev[1], s->ev[2]));
+    EPX_CUDA(cudaEventElapsedTime(&out->probe_rank_ms, s->ev[2], s->ev[3]));
+    EPX_CUDA(cudaEventElapsedTime(&out->pair_stats_ms, s->ev[3], s->ev[4]));
+    out->n_pairs = s->Np; out->n_unique_probes = s->U; out->n_genes = s->G; out->n_samples = s->n;
+    out->algorithmic_bytes = s->Np * (8 * s->n + 88) + s->G * (10 * s->n + 48);
+    out->kernel_launches = s->launches;
+    return EPX_OK;
+}
+
+int epx_session_result_device_ptr(epx_session *s, int which, void **ptr, int64_t *bytes, char *err, size_t errlen)
+{
+    if (!s || !ptr) return fail(err, errlen, EPX_EINVAL, "NULL argument");
+    if (!s->ran) return fail(err, errlen, EPX_ESTATE, "no results yet");
+    const int64_t Np = s->Np, G = s->G, n = s->n;
+    void *p = nullptr; int64_t b = 0;
+    switch (which) {
+    case 0: p = s->pair.p; b = Np * PAIR_COLS * 8; break;
+    case 1: p = s->pair_na.p; b = Np * 2; break;
+    case 2: p = s->pair_stat.p; b = Np * 24; break;
+    case 3: p = s->pair_dnum.p; b = Np * 12; break;
+    case 4: p = s->gene.p; b = G * GENE_COLS * 8; break;
+    case 5: p = s->gene_na.p; b = G * 2; break;
+    case 6: p = s->gene_dnum.p; b = G * 12; break;
+    case 7: p = s->perm.p; b = G * n * 2; break;
+    default: return fail(err, errlen, EPX_EINVAL, "unknown table %d", which);
+    }
+    *ptr = p;
+    if (bytes) *bytes = b;
+    return EPX_OK;
+}
+
+int epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples, const int64_t *row_ptr,
+                const int32_t *probe_idx, const epx_options *opt, epx_result *out, char *err, size_t errlen)
+{
+    int rc = epx_session_set_expression(s, expr, n_genes, n_samples, 0, err, errlen);
+    if (rc) return rc;
+    rc = epx_session_set_index(s, row_ptr, probe_idx, n_genes, err, errlen);
+    if (rc) return rc;
+    rc = epx_session_run(s, opt, nullptr, err, errlen);
+    if (rc) return rc;
+    return epx_session_fetch(s, out, nullptr, err, errlen);
+}
+
+} /* extern "C" */

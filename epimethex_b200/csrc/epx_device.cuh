@@ -1,0 +1,73 @@
+/*
+ * epx_device.cuh — device helpers shared by the libepx kernels (sm_100a).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "epx_math.h"
+
+namespace epx {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+/* order-preserving map double -> uint64 (ascending); -0.0 and +0.0 map to the same key, as R's
+ * comparisons treat them (R/EpimethexAnalysis.R:117-122 order()/sort()). Inputs carry no NaN. */
+__device__ __forceinline__ unsigned long long key_of(double v)
+{
+    v = v + 0.0;
+    long long b = __double_as_longlong(v);
+    unsigned long long u = (unsigned long long)b;
+    return (b < 0) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(FULL, v); }
+
+/* sum over the whole block; every thread gets the result. red: >= 33 doubles of shared memory */
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads(); /* protect red[] from a previous use */
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+/* In-place ascending bitonic sort of npad (power of two) (key, idx) records in shared memory, ordered
+ * by key then idx. All threads of the block must call. */
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long *keys, unsigned short *idx, int npad)
+{
+    const int half = npad >> 1;
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < half; t += blockDim.x) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int p = i | j;
+                bool up = ((i & k) == 0);
+                unsigned long long ki = keys[i], kp = keys[p];
+                unsigned short ii = idx[i], ip = idx[p];
+                bool gt = (ki > kp) || (ki == kp && ii > ip);
+                if (gt == up) {
+                    keys[i] = kp; keys[p] = ki;
+                    idx[i] = ip; idx[p] = ii;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+} // namespace epx

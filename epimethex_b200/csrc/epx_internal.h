@@ -1,0 +1,100 @@
+/*
+ * epx_internal.h — kernel launch interface between epx_api.cu (session, C ABI) and epx_kernels.cu.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/epx.h"
+
+namespace epx {
+
+/* work item of the pair kernel: a run of consecutive pairs of one gene */
+struct Item {
+    int32_t gene;
+    int32_t begin;  /* first pair (index into probe_idx) */
+    int32_t count;
+    int32_t pad;
+};
+
+constexpr int PAIR_COLS = 11;
+constexpr int GENE_COLS = 15;
+constexpr int ITEM_PAIRS = 16;       /* pairs per work item */
+constexpr int MAX_WARP_SAMPLES = 1024; /* warp-per-pair kernel: n <= 32 lanes * 32 elements */
+
+/* device status word (d_status) */
+enum { ST_OK = 0, ST_BREAKS_NOT_UNIQUE = 1 };
+
+struct GeneParams {
+    const double *expr;     /* [G][n] */
+    int n, G, npad, m;
+    uint16_t *perm;         /* [G][n] */
+    uint8_t *lab8;          /* [G][ldl]  methylation-side label of each SAMPLE: rank/m, 3 = unlabelled */
+    int64_t ldl;
+    double *xc;             /* [G][ldx]  x - mean(x), original sample order */
+    int64_t ldx;
+    double *gene_aux;       /* [G][2]    {sum (x-mean)^2, mean} */
+    int32_t *nuniq;         /* [G] */
+};
+
+struct GeneTestParams {
+    const double *expr;
+    const uint16_t *perm;
+    int n, G;
+    const int32_t *nuniq;
+    int32_t *counts;        /* [3] nUP, nM, nD */
+    int32_t *ref_gene;
+    int32_t *status;
+    int test_t, data_linear, fc_from_means;
+    double *gene;           /* [G][15] */
+    uint16_t *gene_na;
+    int32_t *gene_dnum;     /* [G][3] */
+};
+
+struct RankParams {
+    const double *meth;
+    int64_t ld;
+    const int32_t *uniq_probe; /* [U] */
+    int64_t U;
+    int n, npad;
+    uint16_t *ord;          /* [U][ldo]: sample index of the k-th smallest value | 0x8000 when equal to the next */
+    int64_t ldo;
+};
+
+struct PairParams {
+    const double *meth;
+    int64_t ld;
+    const uint16_t *ord;
+    int64_t ldo;
+    const int32_t *probe_idx;
+    const int32_t *pair_slot;
+    const double *xc;
+    int64_t ldx;
+    const uint8_t *lab8;
+    int64_t ldl;
+    const uint16_t *perm;
+    const double *gene_aux;
+    const Item *items;
+    int n_items;
+    int n, m;
+    int test_t;
+    int exact_ok;           /* m*m < 10000: exact KS p-value unless the two groups hold ties */
+    const double *lut_exact; /* [m+1] p-value for max|cA-cB| = d */
+    const double *lut_asym;  /* [m+1] */
+    double *pair;           /* [Np][11] */
+    uint16_t *pair_na;
+    double *pair_stat;      /* [Np][3] */
+    int32_t *pair_dnum;     /* [Np][3] */
+};
+
+cudaError_t launch_gene_sort(const GeneParams &p, cudaStream_t st);
+cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st);
+cudaError_t launch_gene_tests(const GeneTestParams &p, cudaStream_t st);
+cudaError_t launch_probe_rank(const RankParams &p, cudaStream_t st);
+cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st);
+/* dst[p*ld + s0 + j] = src[j*P + p], j < ns : sample-major chunk -> probe-major rows */
+cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,
+                                  cudaStream_t st);
+/* one-time kernel attribute setup (dynamic shared memory opt-in) */
+cudaError_t kernels_init();
+
+} // namespace epx

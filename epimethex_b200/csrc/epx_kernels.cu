@@ -1,0 +1,673 @@
+/*
+ * epx_kernels.cu — sm_100a kernels of the EpiMethEx association path.
+ *
+ *   k_gene_sort       per gene: stable descending order of the samples (R/EpimethexAnalysis.R:117-122),
+ *                     methylation-side labels by rank (:323-325), centred expression for Pearson (:404-417)
+ *   k_pick_reference  reference gene + RcmdrMisc::bin.var thirds (:134-139)
+ *   k_gene_tests      quantiles (:125-129), group means (:146-155), calcFC (:172, R/Functions.R:26-80),
+ *                     the three expression tests (:184-206, R/Functions.R:192-220)
+ *   k_probe_rank      per referenced probe: ascending order of its methylation row with tie marks
+ *                     (the sort that stats::median / stats::ks.test perform per call in the reference)
+ *   k_pair_stats      per (gene, probe) pair: the gather (:299-302) fused with Analysis
+ *                     (R/Functions.R:85-132) and corr.test (:404-417)
+ */
+#include "epx_device.cuh"
+#include "epx_internal.h"
+
+namespace epx {
+
+/* ============================================================ k_gene_sort */
+
+__global__ void __launch_bounds__(256) k_gene_sort(GeneParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *keys = (unsigned long long *)smem;
+    unsigned short *idx = (unsigned short *)(keys + p.npad);
+    __shared__ double red[40];
+    __shared__ int s_uniq;
+
+    const int g = blockIdx.x, n = p.n;
+    const double *x = p.expr + (int64_t)g * n;
+    if (threadIdx.x == 0) s_uniq = 1;
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
+        if (i < n) {
+            double v = x[i];
+            keys[i] = ~key_of(v); /* descending by value */
+            idx[i] = (unsigned short)i;
+            sum += v;
+        } else {
+            keys[i] = ~0ull;
+            idx[i] = 0xffffu;
+        }
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, idx, p.npad); /* (key, idx) ascending = value descending, ties by sample index */
+
+    int uniq = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int s = idx[i];
+        p.perm[(int64_t)g * n + i] = (uint16_t)s;
+        int lab = i / p.m;
+        p.lab8[(int64_t)g * p.ldl + s] = (uint8_t)(lab > 3 ? 3 : lab);
+        if (i > 0 && keys[i] != keys[i - 1]) uniq++;
+    }
+    if (uniq) atomicAdd(&s_uniq, uniq);
+
+    double mean = block_sum(sum, red) / (double)n;
+    double sxx = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double d = x[i] - mean;
+        p.xc[(int64_t)g * p.ldx + i] = d;
+        sxx += d * d;
+    }
+    sxx = block_sum(sxx, red);
+    if (threadIdx.x == 0) {
+        int u = s_uniq;
+        p.nuniq[g] = u;
+        p.gene_aux[2 * (int64_t)g] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
+        p.gene_aux[2 * (int64_t)g + 1] = mean;
+    }
+}
+
+/* ============================================================ k_pick_reference */
+
+__device__ __forceinline__ double quantile7(const double *x, const uint16_t *perm, int n, double prob)
+{
+    /* type 7 on the ascending order; ascending element k (0-based) = x[perm[n-1-k]] */
+    double index = 1.0 + (double)(n - 1) * prob;
+    double lo = floor(index), hi = ceil(index);
+    double qs = x[perm[n - (int)lo]];
+    double xh = x[perm[n - (int)hi]];
+    if (index > lo && xh != qs) {
+        double h = index - lo;
+        qs = (1.0 - h) * qs + h * xh;
+    }
+    return qs;
+}
+
+__global__ void __launch_bounds__(1024) k_pick_reference(GeneTestParams p)
+{
+    __shared__ int s_best[32], s_arg[32];
+    __shared__ double s_b[4];
+    __shared__ int s_cnt[2];
+    /* which.max(apply(..., function(x) length(unique(x)))): first gene with the most distinct values */
+    int best = -1, arg = 0x7fffffff;
+    for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+        int u = p.nuniq[g];
+        if (u > best) { best = u; arg = g; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        int b2 = __shfl_xor_sync(FULL, best, o), a2 = __shfl_xor_sync(FULL, arg, o);
+        if (b2 > best || (b2 == best && a2 < arg)) { best = b2; arg = a2; }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_best[w] = best; s_arg[w] = arg; }
+    __syncthreads();
+    if (w == 0) {
+        best = s_best[lane]; arg = s_arg[lane];
+        for (int o = 16; o > 0; o >>= 1) {
+            int b2 = __shfl_xor_sync(FULL, best, o), a2 = __shfl_xor_sync(FULL, arg, o);
+            if (b2 > best || (b2 == best && a2 < arg)) { best = b2; arg = a2; }
+        }
+        if (lane == 0) { s_arg[0] = arg; s_cnt[0] = 0; s_cnt[1] = 0; }
+    }
+    __syncthreads();
+    const int ref = s_arg[0], n = p.n;
+    const double *x = p.expr + (int64_t)ref * n;
+    const uint16_t *perm = p.perm + (int64_t)ref * n;
+    if (threadIdx.x == 0) {
+        /* bin.var: cut(x, quantile(x, seq(0,1,1/3)), include.lowest=TRUE) */
+        const double third = 1.0 / 3.0;
+        s_b[0] = quantile7(x, perm, n, 0.0);
+        s_b[1] = quantile7(x, perm, n, third);
+        s_b[2] = quantile7(x, perm, n, 2.0 * third);
+        s_b[3] = quantile7(x, perm, n, 1.0);
+    }
+    __syncthreads();
+    int nup = 0, nm = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = x[i];
+        if (v > s_b[2]) nup++;
+        else if (v > s_b[1]) nm++;
+    }
+    if (nup) atomicAdd(&s_cnt[0], nup);
+    if (nm) atomicAdd(&s_cnt[1], nm);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.counts[0] = s_cnt[0];
+        p.counts[1] = s_cnt[1];
+        p.counts[2] = n - s_cnt[0] - s_cnt[1];
+        *p.ref_gene = ref;
+        *p.status = (s_b[0] < s_b[1] && s_b[1] < s_b[2] && s_b[2] < s_b[3]) ? ST_OK : ST_BREAKS_NOT_UNIQUE;
+    }
+}
+
+/* ============================================================ k_gene_tests */
+
+__global__ void __launch_bounds__(128) k_gene_tests(GeneTestParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *xs = (double *)smem; /* sorted descending; later reused as psmirnov scratch */
+    __shared__ double red[40];
+    __shared__ int s_dmax[3];
+    if (*p.status != ST_OK) return;
+
+    const int g = blockIdx.x, n = p.n, tid = threadIdx.x;
+    const double *x = p.expr + (int64_t)g * n;
+    const uint16_t *perm = p.perm + (int64_t)g * n;
+    const int nUP = p.counts[0], nM = p.counts[1], nD = p.counts[2];
+    /* row blocks of the expression-side labels: UP, then M, then D */
+    const int off[3] = { 0, nUP, nUP + nM };
+    const int len[3] = { nUP, nM, nD };
+
+    for (int i = tid; i < n; i += blockDim.x) xs[i] = x[perm[i]];
+    if (tid < 3) s_dmax[tid] = 0;
+    __syncthreads();
+
+    /* group means and variances (two-pass) */
+    double mean[3], var[3];
+    for (int c = 0; c < 3; c++) {
+        double s = 0.0;
+        for (int i = tid; i < len[c]; i += blockDim.x) s += xs[off[c] + i];
+        mean[c] = len[c] > 0 ? block_sum(s, red) / (double)len[c] : EPX_NAN;
+        double ss = 0.0;
+        for (int i = tid; i < len[c]; i += blockDim.x) { double d = xs[off[c] + i] - mean[c]; ss += d * d; }
+        var[c] = len[c] > 1 ? block_sum(ss, red) / (double)(len[c] - 1) : EPX_NAN;
+    }
+
+    /* the three comparisons of R/EpimethexAnalysis.R:184-206: (UP,M) (UP,D) (M,D) */
+    const int ca[3] = { 0, 0, 1 }, cb[3] = { 1, 2, 2 };
+    int guard[3], ties[3];
+    for (int c = 0; c < 3; c++) {
+        const int la = len[ca[c]], lb = len[cb[c]];
+        const double *A = xs + off[ca[c]], *B = xs + off[cb[c]];
+        /* guard, R/Functions.R:193: sd(mapply('-', a, b)) with recycling of the shorter argument */
+        const int L = la > lb ? la : lb;
+        int differs = 0;
+        if (la > 0 && lb > 0 && L >= 2) {
+            const double d0 = A[0] - B[0];
+            for (int i = 1 + tid; i < L; i += blockDim.x)
+                if (A[i % la] - B[i % lb] != d0) differs = 1;
+        }
+        differs = __syncthreads_or(differs);
+        guard[c] = (la == 0 || lb == 0 || L < 2) ? -1 : (differs ? 1 : 0);
+
+        /* KS numerator: the column is globally sorted, so counts are closed forms of the position;
+         * evaluate at the end of every tie run of the whole column (extra thresholds cannot exceed the sup) */
+        int dmax = 0, tie = 0;
+        if (!p.test_t && la > 0 && lb > 0) {
+            const int a0 = off[ca[c]], b0 = off[cb[c]];
+            for (int i = tid; i < n; i += blockDim.x) {
+                bool run_end = (i == n - 1) || (xs[i] != xs[i + 1]);
+                if (run_end) {
+                    int cA = min(max(i + 1 - a0, 0), la), cB = min(max(i + 1 - b0, 0), lb);
+                    int z = cA * lb - cB * la;
+                    dmax = max(dmax, z < 0 ? -z : z);
+                } else {
+                    /* xs[i] == xs[i+1]: a tie inside the pooled sample iff both lie in A u B, or they
+                     * bracket a fully tied third group between A and B */
+                    bool in_i = (i >= a0 && i < a0 + la) || (i >= b0 && i < b0 + lb);
+                    bool in_n = (i + 1 >= a0 && i + 1 < a0 + la) || (i + 1 >= b0 && i + 1 < b0 + lb);
+                    if (in_i && in_n) tie = 1;
+                }
+            }
+            /* UP vs D with the whole M block tied to both neighbours */
+            if (c == 1 && tid == 0 && nM > 0 && xs[off[1] - 1] == xs[off[2]]) tie = 1;
+            dmax = warp_max_i(dmax);
+            if ((tid & 31) == 0 && dmax) atomicMax(&s_dmax[c], dmax);
+        }
+        ties[c] = __syncthreads_or(tie);
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        double *o = p.gene + (int64_t)g * GENE_COLS;
+        const double q33 = quantile7(x, perm, n, 0.33), q66 = quantile7(x, perm, n, 0.66),
+                     q99 = quantile7(x, perm, n, 0.99);
+        /* calcFC reads the last three rows = perc99/perc66/perc33 (reference quirk) */
+        const double fu = p.fc_from_means ? mean[0] : q99, fm = p.fc_from_means ? mean[1] : q66,
+                     fd = p.fc_from_means ? mean[2] : q33;
+        double fc0, fc1, fc2;
+        if (p.data_linear) { fc0 = epx_linear_fc(fu, fm); fc1 = epx_linear_fc(fu, fd); fc2 = epx_linear_fc(fm, fd); }
+        else { fc0 = epx_log_fc(fu, fm); fc1 = epx_log_fc(fu, fd); fc2 = epx_log_fc(fm, fd); }
+        o[0] = fc0; o[1] = fc1; o[2] = fc2;
+        o[9] = q33; o[10] = q66; o[11] = q99;
+        o[12] = mean[2]; o[13] = mean[1]; o[14] = mean[0];
+        uint16_t na = 0;
+        for (int c = 0; c < 3; c++) {
+            const int la = len[ca[c]], lb = len[cb[c]];
+            double stat = EPX_NAN, pv = EPX_NAN;
+            int dn = -1;
+            bool ok = false;
+            if (p.test_t) {
+                if (guard[c] == 1) {
+                    double t, df;
+                    if (epx_welch(mean[ca[c]], var[ca[c]], (double)la, mean[cb[c]], var[cb[c]], (double)lb, &t, &df) == 0) {
+                        stat = t; pv = epx_t_two_sided_p(t, df); ok = true;
+                    }
+                }
+            } else if (guard[c] != 0 && la > 0 && lb > 0) {
+                dn = s_dmax[c];
+                stat = (double)dn / ((double)la * (double)lb);
+                if ((double)la * (double)lb < 10000.0 && !ties[c]) pv = epx_ks_p_exact((double)dn, la, lb, xs);
+                else pv = epx_ks_p_asym((double)dn, (double)la, (double)lb);
+                ok = true;
+            }
+            o[3 + c] = pv; o[6 + c] = stat;
+            p.gene_dnum[(int64_t)g * 3 + c] = dn;
+            if (!ok) na |= (uint16_t)((1u << (3 + c)) | (1u << (6 + c)));
+        }
+        p.gene_na[g] = na;
+    }
+}
+
+/* ============================================================ k_probe_rank */
+
+__global__ void __launch_bounds__(256) k_probe_rank(RankParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *keys = (unsigned long long *)smem;
+    unsigned short *idx = (unsigned short *)(keys + p.npad);
+    const int64_t slot = blockIdx.x;
+    const int n = p.n;
+    const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
+    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
+        if (i < n) { keys[i] = key_of(row[i]); idx[i] = (unsigned short)i; }
+        else { keys[i] = ~0ull; idx[i] = 0xffffu; }
+    }
+    __syncthreads();
+    block_bitonic_sort(keys, idx, p.npad);
+    uint16_t *o = p.ord + slot * p.ldo;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        unsigned short v = idx[k];
+        if (k + 1 < n && keys[k] == keys[k + 1]) v |= 0x8000u;
+        o[k] = v;
+    }
+}
+
+/* ============================================================ k_pair_stats (warp per pair, n <= 1024) */
+
+constexpr int PAIR_WARPS = 8;
+
+__host__ __device__ inline size_t pair_warp_smem(int n)
+{
+    int npad = (n + 1) & ~1;
+    return (size_t)16 * npad + (size_t)((n + 15) & ~15) + 64; /* xc | row | lab | 6 median slots (+pad) */
+}
+
+template <int EPL, bool TMODE>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = p.n, m = p.m;
+    const int npad = (n + 1) & ~1;
+    unsigned char *base = smem + (size_t)warp * pair_warp_smem(n);
+    double *s_xc = (double *)base;
+    double *s_row = s_xc + npad;
+    double *s_med = s_row + npad;                 /* 6 doubles */
+    uint8_t *s_lab = (uint8_t *)(s_med + 8);
+
+    const int gw = blockIdx.x * PAIR_WARPS + warp, nw = gridDim.x * PAIR_WARPS;
+    const double dm = (double)m, dn_ = (double)n;
+    const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1; /* within-group counts at which the two middle values pass */
+    int cur_gene = -1;
+    double sxx = 0.0;
+    int pm[6] = { 0, 0, 0, 0, 0, 0 };
+    const uint16_t *perm_g = nullptr;
+
+    for (int it = gw; it < p.n_items; it += nw) {
+        const Item item = p.items[it];
+        if (item.gene != cur_gene) {
+            cur_gene = item.gene;
+            __syncwarp();
+            const double *xc = p.xc + (int64_t)cur_gene * p.ldx;
+            const uint8_t *lab = p.lab8 + (int64_t)cur_gene * p.ldl;
+            for (int s = lane; s < n; s += 32) { s_xc[s] = xc[s]; s_lab[s] = lab[s]; }
+            sxx = p.gene_aux[2 * (int64_t)cur_gene];
+            perm_g = p.perm + (int64_t)cur_gene * n;
+            if (m >= 2) {
+                pm[0] = perm_g[0]; pm[1] = perm_g[1]; pm[2] = perm_g[m]; pm[3] = perm_g[m + 1];
+                pm[4] = perm_g[2 * m]; pm[5] = perm_g[2 * m + 1];
+            }
+            __syncwarp();
+        }
+        for (int j = item.begin; j < item.begin + item.count; j++) {
+            const int pi = p.probe_idx[j];
+            if (pi < 0) { /* annotated probe without data: all-NA column (R/EpimethexAnalysis.R:375-394) */
+                if (lane < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + lane] = EPX_NAN;
+                if (lane < 3) { p.pair_stat[(int64_t)j * 3 + lane] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + lane] = -1; }
+                if (lane == 0) p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+                continue;
+            }
+            const double *row = p.meth + (int64_t)pi * p.ld;
+            const uint16_t *ord = p.ord + (int64_t)p.pair_slot[j] * p.ldo;
+
+            /* ---- pass A: the gather. sample-major, coalesced; label = the gene's rank third ---- */
+            double y[EPL];
+            unsigned long long labs = 0; /* 2 bits per element */
+            double s_all = 0.0, sg0 = 0.0, sg1 = 0.0, sg2 = 0.0;
+            __syncwarp(); /* previous pair's readers of s_row are done */
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+                const int s = lane + 32 * e;
+                double v = 0.0;
+                unsigned lab = 3;
+                if (s < n) {
+                    v = __ldg(row + s);
+                    lab = s_lab[s];
+                    s_row[s] = v;
+                    s_all += v;
+                    if (TMODE) { sg0 += lab == 0 ? v : 0.0; sg1 += lab == 1 ? v : 0.0; sg2 += lab == 2 ? v : 0.0; }
+                }
+                y[e] = v;
+                labs |= (unsigned long long)lab << (2 * e);
+            }
+            s_all = warp_sum(s_all);
+            double mg0 = 0, mg1 = 0, mg2 = 0;
+            if (TMODE) { mg0 = warp_sum(sg0) / dm; mg1 = warp_sum(sg1) / dm; mg2 = warp_sum(sg2) / dm; }
+            const double mean_all = s_all / dn_;
+            const double y_first = __shfl_sync(FULL, y[0], 0);
+            bool same = true;
+            double syy = 0.0, sxy = 0.0, ss0 = 0.0, ss1 = 0.0, ss2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+                const int s = lane + 32 * e;
+                if (s < n) {
+                    const double d = y[e] - mean_all;
+                    syy += d * d;
+                    sxy += s_xc[s] * d;
+                    same = same && (y[e] == y_first);
+                    if (TMODE) {
+                        const unsigned lab = (unsigned)(labs >> (2 * e)) & 3u;
+                        const double mgl = lab == 0 ? mg0 : (lab == 1 ? mg1 : mg2);
+                        const double dg = y[e] - mgl;
+                        const double q = dg * dg;
+                        ss0 += lab == 0 ? q : 0.0; ss1 += lab == 1 ? q : 0.0; ss2 += lab == 2 ? q : 0.0;
+                    }
+                }
+            }
+            syy = warp_sum(syy);
+            sxy = warp_sum(sxy);
+            if (TMODE) { ss0 = warp_sum(ss0); ss1 = warp_sum(ss1); ss2 = warp_sum(ss2); }
+            if (__all_sync(FULL, same)) syy = 0.0; /* constant row: sd is exactly 0 in R -> NA */
+            __syncwarp(); /* s_row complete */
+
+            /* ---- sorted walk: lane owns EPL consecutive positions of the probe's ascending order ---- */
+            unsigned short o[EPL];
+            unsigned long long wl = 0; /* labels along the walk, 2 bits each */
+            unsigned cnt = 0;          /* 3 x 10-bit label counts */
+            bool anytie = false;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+                const int k = lane * EPL + e;
+                unsigned short v = 0;
+                unsigned lab = 3;
+                if (k < n) {
+                    v = ord[k];
+                    lab = s_lab[v & 0x7fffu];
+                    anytie = anytie || (v & 0x8000u);
+                }
+                o[e] = v;
+                wl |= (unsigned long long)lab << (2 * e);
+                if (lab < 3) cnt += 1u << (10 * lab);
+            }
+            unsigned inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned t = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const unsigned excl = inc - cnt;
+            int c0 = excl & 1023, c1 = (excl >> 10) & 1023, c2 = (excl >> 20) & 1023;
+            int d01 = 0, d02 = 0, d12 = 0;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+                const int k = lane * EPL + e;
+                if (k < n) {
+                    const unsigned lab = (unsigned)(wl >> (2 * e)) & 3u;
+                    const int s = o[e] & 0x7fffu;
+                    int c = -1;
+                    if (lab == 0) c = ++c0; else if (lab == 1) c = ++c1; else if (lab == 2) c = ++c2;
+                    if (c == t1) s_med[lab * 2] = s_row[s];
+                    if (c == t2) s_med[lab * 2 + 1] = s_row[s];
+                    if (!TMODE && !(o[e] & 0x8000u)) { /* end of a tie run */
+                        d01 = max(d01, abs(c0 - c1)); d02 = max(d02, abs(c0 - c2)); d12 = max(d12, abs(c1 - c2));
+                    }
+                }
+            }
+            if (!TMODE) { d01 = warp_max_i(d01); d02 = warp_max_i(d02); d12 = warp_max_i(d12); }
+            __syncwarp();
+            /* labels: 0 UP, 1 Medium, 2 Down */
+            const double medUP = (s_med[0] + s_med[1]) * 0.5, medMID = (s_med[2] + s_med[3]) * 0.5,
+                         medDOWN = (s_med[4] + s_med[5]) * 0.5;
+
+            /* ---- guard of calculateTtest (R/Functions.R:193): are all rank-paired differences identical? ---- */
+            int guard[3] = { -1, -1, -1 };
+            if (m >= 2) {
+                const double a0 = s_row[pm[0]], a1 = s_row[pm[1]], b0 = s_row[pm[2]], b1 = s_row[pm[3]],
+                             e0 = s_row[pm[4]], e1 = s_row[pm[5]];
+                const double dd[3] = { a0 - b0, a0 - e0, b0 - e0 };
+                const bool eq[3] = { dd[0] == a1 - b1, dd[1] == a1 - e1, dd[2] == b1 - e1 };
+                const int offA[3] = { 0, 0, m }, offB[3] = { m, 2 * m, 2 * m };
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (!eq[c]) { guard[c] = 1; continue; }
+                    int differs = 0; /* rare: walk the whole group */
+                    for (int i = 2 + lane; i < m; i += 32)
+                        if (s_row[perm_g[offA[c] + i]] - s_row[perm_g[offB[c] + i]] != dd[c]) differs = 1;
+                    guard[c] = __any_sync(FULL, differs) ? 1 : 0;
+                }
+            }
+
+            /* ---- tests ---- */
+            double stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+            int dnum[3] = { -1, -1, -1 };
+            unsigned na = 0;
+            /* Pearson (psych::corr.test): r clamped, NA when either sd is 0 */
+            double r = EPX_NAN, tq = EPX_NAN, dfq = EPX_NAN;
+            bool r_ok = (sxx != 0.0 && syy != 0.0 && n >= 3);
+            if (r_ok) {
+                r = sxy / (sqrt(sxx) * sqrt(syy));
+                r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+            } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
+            if (TMODE) {
+                const double mg[3] = { mg0, mg1, mg2 };
+                const double vg[3] = { ss0 / (dm - 1.0), ss1 / (dm - 1.0), ss2 / (dm - 1.0) };
+                const int ga[3] = { 0, 0, 1 }, gb[3] = { 1, 2, 2 };
+                bool ok[3];
+                double tt[3], df[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    ok[c] = false; tt[c] = EPX_NAN; df[c] = EPX_NAN;
+                    if (guard[c] == 1)
+                        ok[c] = epx_welch(mg[ga[c]], vg[ga[c]], dm, mg[gb[c]], vg[gb[c]], dm, &tt[c], &df[c]) == 0;
+                    stat[c] = tt[c];
+                    if (!ok[c]) na |= 1u << (EPX_P_UP_MID + c);
+                }
+                /* the four Student-t tails of this pair run on four lanes at once */
+                bool mine = false;
+                if (lane < 3) { tq = lane == 0 ? tt[0] : (lane == 1 ? tt[1] : tt[2]); dfq = lane == 0 ? df[0] : (lane == 1 ? df[1] : df[2]);
+                                mine = lane == 0 ? ok[0] : (lane == 1 ? ok[1] : ok[2]); }
+                else if (lane == 3) { tq = (r * sqrt(dn_ - 2.0)) / sqrt(1.0 - r * r); dfq = dn_ - 2.0; mine = r_ok; }
+                double pq = EPX_NAN;
+                if (mine) pq = epx_t_two_sided_p(tq, dfq);
+                pv[0] = __shfl_sync(FULL, pq, 0); pv[1] = __shfl_sync(FULL, pq, 1); pv[2] = __shfl_sync(FULL, pq, 2);
+                tq = __shfl_sync(FULL, pq, 3); /* Pearson p */
+            } else {
+                int ties[3] = { 0, 0, 0 };
+                if (p.exact_ok && __any_sync(FULL, anytie)) {
+                    /* small groups with tied values: ks.test drops to the asymptotic p-value when the POOLED
+                     * pair of groups holds a tie. Rare and tiny (m < 100): one lane walks the order. */
+                    if (lane == 0) {
+                        int r0 = 0, r1 = 0, r2 = 0;
+                        for (int k = 0; k < n; k++) {
+                            const unsigned short v = ord[k];
+                            const unsigned lab = s_lab[v & 0x7fffu];
+                            r0 += lab == 0; r1 += lab == 1; r2 += lab == 2;
+                            if (!(v & 0x8000u)) {
+                                if (r0 + r1 >= 2) ties[0] = 1;
+                                if (r0 + r2 >= 2) ties[1] = 1;
+                                if (r1 + r2 >= 2) ties[2] = 1;
+                                r0 = r1 = r2 = 0;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) ties[c] = __shfl_sync(FULL, ties[c], 0);
+                }
+                const int dd[3] = { d01, d02, d12 };
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (guard[c] != 0) { /* difference != 0 || is.na(difference) */
+                        dnum[c] = dd[c] * m;
+                        stat[c] = (double)dnum[c] / (dm * dm);
+                        pv[c] = (p.exact_ok && !ties[c]) ? p.lut_exact[dd[c]] : p.lut_asym[dd[c]];
+                    } else na |= 1u << (EPX_P_UP_MID + c);
+                }
+                double pq = EPX_NAN;
+                if (lane == 0 && r_ok) pq = epx_pearson_p(r, dn_);
+                tq = __shfl_sync(FULL, pq, 0);
+            }
+            const double p_r = tq;
+
+            /* ---- write the 11 columns (R/Functions.R:224-226 order) ---- */
+            double out = 0.0;
+            switch (lane) {
+            case 0: out = medDOWN; break;
+            case 1: out = medMID; break;
+            case 2: out = medUP; break;
+            case 3: out = medUP - medMID; break;
+            case 4: out = medUP - medDOWN; break;
+            case 5: out = medMID - medDOWN; break;
+            case 6: out = pv[0]; break;
+            case 7: out = pv[1]; break;
+            case 8: out = pv[2]; break;
+            case 9: out = r; break;
+            case 10: out = p_r; break;
+            default: break;
+            }
+            if (lane < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + lane] = out;
+            if (lane < 3) {
+                p.pair_stat[(int64_t)j * 3 + lane] = lane == 0 ? stat[0] : (lane == 1 ? stat[1] : stat[2]);
+                p.pair_dnum[(int64_t)j * 3 + lane] = lane == 0 ? dnum[0] : (lane == 1 ? dnum[1] : dnum[2]);
+            }
+            if (lane == 0) p.pair_na[j] = (uint16_t)na;
+        }
+    }
+}
+
+/* ============================================================ transpose (sample-major upload) */
+
+__global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict__ src, double *__restrict__ dst,
+                                                        int64_t P, int ns, int64_t s0, int64_t ld)
+{
+    __shared__ double tile[32][33];
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; /* 32 x 8 */
+    for (int r = ty; r < 32; r += 8) {
+        int j = j0 + r;
+        int64_t pp = p0 + tx;
+        if (j < ns && pp < P) tile[r][tx] = src[(int64_t)j * P + pp];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int64_t pp = p0 + r;
+        int j = j0 + tx;
+        if (j < ns && pp < P) dst[pp * ld + s0 + j] = tile[tx][r];
+    }
+}
+
+/* ============================================================ launchers */
+
+static size_t sort_smem(int npad) { return (size_t)npad * 10; }
+
+cudaError_t kernels_init()
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_gene_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_probe_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_gene_tests, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+#define EPX_PAIR_ATTR(E)                                                                                           \
+    e = cudaFuncSetAttribute(k_pair_stats<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
+    if (e != cudaSuccess) return e;                                                                                \
+    e = cudaFuncSetAttribute(k_pair_stats<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
+    if (e != cudaSuccess) return e;
+    EPX_PAIR_ATTR(1) EPX_PAIR_ATTR(2) EPX_PAIR_ATTR(4) EPX_PAIR_ATTR(8) EPX_PAIR_ATTR(15) EPX_PAIR_ATTR(16)
+    EPX_PAIR_ATTR(24) EPX_PAIR_ATTR(32)
+#undef EPX_PAIR_ATTR
+    return cudaSuccess;
+}
+
+cudaError_t launch_gene_sort(const GeneParams &p, cudaStream_t st)
+{
+    if (p.G <= 0) return cudaSuccess;
+    k_gene_sort<<<p.G, 256, sort_smem(p.npad), st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st)
+{
+    k_pick_reference<<<1, 1024, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gene_tests(const GeneTestParams &p, cudaStream_t st)
+{
+    if (p.G <= 0) return cudaSuccess;
+    k_gene_tests<<<p.G, 128, (size_t)(p.n + 2) * sizeof(double), st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe_rank(const RankParams &p, cudaStream_t st)
+{
+    if (p.U <= 0) return cudaSuccess;
+    k_probe_rank<<<(unsigned)p.U, 256, sort_smem(p.npad), st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int EPL>
+static cudaError_t launch_pair_epl(const PairParams &p, int sm_count, cudaStream_t st)
+{
+    const size_t smem = pair_warp_smem(p.n) * PAIR_WARPS;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int grid = sm_count * per_sm;
+    const int need = (p.n_items + PAIR_WARPS - 1) / PAIR_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (p.test_t) k_pair_stats<EPL, true><<<grid, PAIR_WARPS * 32, smem, st>>>(p);
+    else k_pair_stats<EPL, false><<<grid, PAIR_WARPS * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st)
+{
+    if (p.n_items <= 0) return cudaSuccess;
+    const int epl = (p.n + 31) / 32;
+    if (epl <= 1) return launch_pair_epl<1>(p, sm_count, st);
+    if (epl <= 2) return launch_pair_epl<2>(p, sm_count, st);
+    if (epl <= 4) return launch_pair_epl<4>(p, sm_count, st);
+    if (epl <= 8) return launch_pair_epl<8>(p, sm_count, st);
+    if (epl <= 15) return launch_pair_epl<15>(p, sm_count, st);
+    if (epl <= 16) return launch_pair_epl<16>(p, sm_count, st);
+    if (epl <= 24) return launch_pair_epl<24>(p, sm_count, st);
+    if (epl <= 32) return launch_pair_epl<32>(p, sm_count, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,
+                                  cudaStream_t st)
+{
+    dim3 grid((unsigned)((P + 31) / 32), (unsigned)((ns + 31) / 32));
+    k_transpose_cols<<<grid, 256, 0, st>>>(src, dst, P, ns, s0, ld);
+    return cudaGetLastError();
+}
+
+} // namespace epx

@@ -1,0 +1,190 @@
+/*
+ * epx_math.h — scalar fp64 math shared by the CUDA kernels and the host part of libepx:
+ * Student-t tail (regularised incomplete beta), Kolmogorov-Smirnov p-values as stats::ks.test
+ * computes them (classic R 3.4-4.0 dialect), type-7 quantile, fold changes.
+ *
+ * Everything is EPX_HD (__host__ __device__ under nvcc, plain inline under gcc) so the very same
+ * source is compiled into the kernels and into tests/_mathtest (a CPU unit-test build of this header;
+ * it is not a fallback path — libepx never computes statistics on the host).
+ *
+ * Reference call sites (into /root/reference): stats::t.test R/Functions.R:198; stats::ks.test
+ * R/Functions.R:210; psych::corr.test R/EpimethexAnalysis.R:414; colQuantiles :125; calcFC R/Functions.R:26-80.
+ */
+#ifndef EPX_MATH_H
+#define EPX_MATH_H
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EPX_HD __host__ __device__ __forceinline__
+#else
+#define EPX_HD static inline
+#endif
+
+#define EPX_NAN (__builtin_nan(""))
+
+/* log B(a, 1/2) = lgamma(a) + lgamma(1/2) - lgamma(a + 1/2).  For a >= 20 the difference of the two
+ * lgammas is taken from its asymptotic series (error < 2e-17) instead of cancelling two ~a*log(a) terms. */
+EPX_HD double epx_lbeta_half(double a)
+{
+    const double half_log_pi = 0.57236494292470008707; /* lgamma(1/2) */
+    if (a >= 20.0) {
+        double r = 1.0 / a, r2 = r * r;
+        /* lgamma(a+1/2) - lgamma(a) = log(a)/2 - 1/(8a) + 1/(192a^3) - 1/(640a^5) + 17/(14336a^7) - 31/(18432a^9) */
+        double s = r * (-0.125 + r2 * (1.0 / 192.0 + r2 * (-1.0 / 640.0 + r2 * (17.0 / 14336.0 + r2 * (-31.0 / 18432.0)))));
+        return half_log_pi - (0.5 * log(a) + s);
+    }
+    return lgamma(a) + half_log_pi - lgamma(a + 0.5);
+}
+
+/* continued fraction of the incomplete beta function, modified Lentz */
+EPX_HD double epx_betacf(double a, double b, double x)
+{
+    const double tiny = 1e-300, eps = 4e-16;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 20000; m++) {
+        double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d; h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < eps) break;
+    }
+    return h;
+}
+
+/* two-sided Student-t p-value 2*pt(-|t|, df) = I_{df/(df+t^2)}(df/2, 1/2), real df > 0 */
+EPX_HD double epx_t_two_sided_p(double t, double df)
+{
+    if (isnan(t) || isnan(df) || !(df > 0.0)) return EPX_NAN;
+    if (isinf(t)) return 0.0;
+    double t2 = t * t;
+    if (t2 == 0.0) return 1.0;
+    double a = 0.5 * df, b = 0.5;
+    double den = df + t2;
+    double x = df / den, y = t2 / den;           /* y = 1 - x without cancellation */
+    double logx = -log1p(t2 / df);               /* log(x) accurately when x is close to 1 */
+    double front = exp(a * logx + b * log(y) - epx_lbeta_half(a));
+    double p;
+    if (x < (a + 1.0) / (a + b + 2.0)) p = front * epx_betacf(a, b, x) / a;
+    else p = 1.0 - front * epx_betacf(b, a, y) / b;
+    if (p > 1.0) p = 1.0;
+    if (p < 0.0) p = 0.0;
+    return p;
+}
+
+/* stats::t.test(var.equal=FALSE) from group moments. returns 0 ok, 1 too few observations,
+ * 2 "data are essentially constant" (the reference would stop; reported as NA) */
+EPX_HD int epx_welch(double mx, double vx, double nx, double my, double vy, double ny,
+                     double *t, double *df)
+{
+    if (nx < 2.0 || ny < 2.0) return 1;
+    double sx = sqrt(vx / nx), sy = sqrt(vy / ny);
+    double se = sqrt(sx * sx + sy * sy);
+    double amx = fabs(mx), amy = fabs(my);
+    if (se < 10.0 * 2.220446049250313e-16 * (amx > amy ? amx : amy)) return 2;
+    double se2 = se * se, sx2 = sx * sx, sy2 = sy * sy;
+    *df = se2 * se2 / (sx2 * sx2 / (nx - 1.0) + sy2 * sy2 / (ny - 1.0));
+    *t = (mx - my) / se;
+    return 0;
+}
+
+/* stats ks.c pkstwo(x, tol=1e-6).  For x < 1 only k = 1 of the alternative series is summed
+ * (k_max = (int)sqrt(2 - log(tol)) = 3, k += 2): replicated, not "fixed" (SURVEY 8c-3). */
+EPX_HD double epx_pkstwo(double x)
+{
+    const double tol = 1e-6;
+    if (isnan(x)) return EPX_NAN;
+    if (x <= 0.0) return 0.0;
+    if (x < 1.0) {
+        const double pi2_8 = 1.570796326794896619231321691640 * 0.785398163397448309615660845820;
+        const double inv_sqrt_2pi = 0.398942280401432677939946059934;
+        int k_max = (int)sqrt(2.0 - log(tol));
+        double z = -pi2_8 / (x * x), w = log(x), s = 0.0;
+        for (int k = 1; k < k_max; k += 2) s += exp(k * k * z - w);
+        return s / inv_sqrt_2pi;
+    }
+    double z = -2.0 * x * x, s = -1.0, old = 0.0, nw = 1.0;
+    int k = 1;
+    while (fabs(old - nw) > tol) {
+        old = nw;
+        nw += 2.0 * s * exp(z * k * k);
+        s = -s;
+        k++;
+    }
+    return nw;
+}
+
+/* asymptotic two-sided KS p-value for numerator dnum = max|c_a*lb - c_b*la| */
+EPX_HD double epx_ks_p_asym(double dnum, double la, double lb)
+{
+    double D = dnum / (la * lb);
+    double nn = la * lb / (la + lb);
+    double p = 1.0 - epx_pkstwo(sqrt(nn) * D);
+    return p > 1.0 ? 1.0 : (p < 0.0 ? 0.0 : p);
+}
+
+/* stats ks.c psmirnov2x: exact P(D < statistic), no ties. u = scratch of max(m,n)+1 doubles. */
+EPX_HD double epx_psmirnov2x(double statistic, int m, int n, double *u)
+{
+    if (m > n) { int t = n; n = m; m = t; }
+    double md = (double)m, nd = (double)n;
+    double q = (0.5 + floor(statistic * md * nd - 1e-7)) / (md * nd);
+    for (int j = 0; j <= n; j++) u[j] = ((j / nd) > q) ? 0.0 : 1.0;
+    for (int i = 1; i <= m; i++) {
+        double w = (double)i / ((double)(i + n));
+        if ((i / md) > q) u[0] = 0.0; else u[0] = w * u[0];
+        for (int j = 1; j <= n; j++) {
+            if (fabs(i / md - j / nd) > q) u[j] = 0.0;
+            else u[j] = w * u[j] + u[j - 1];
+        }
+    }
+    return u[n];
+}
+
+EPX_HD double epx_ks_p_exact(double dnum, int la, int lb, double *u)
+{
+    double D = dnum / ((double)la * (double)lb);
+    double p = 1.0 - epx_psmirnov2x(D, la, lb, u);
+    return p > 1.0 ? 1.0 : (p < 0.0 ? 0.0 : p);
+}
+
+/* R/Functions.R:59-63 */
+EPX_HD double epx_log_fc(double a, double b)
+{
+    if (isnan(a) || isnan(b)) return EPX_NAN;
+    double fold = exp2(fabs(a - b));
+    return (b < a) ? fold : -fold;
+}
+
+/* R/Functions.R:68-79 (sign(0) = 0, so a zero and a positive value count as "different sign") */
+EPX_HD double epx_linear_fc(double a, double b)
+{
+    if (isnan(a) || isnan(b)) return EPX_NAN;
+    double aa = fabs(a), ab = fabs(b);
+    double maxabs = aa > ab ? aa : ab, minabs = aa < ab ? aa : ab;
+    double mx = a > b ? a : b, mn = a < b ? a : b;
+    int sa = (a > 0.0) - (a < 0.0), sb = (b > 0.0) - (b < 0.0);
+    double fc = (sa == sb) ? maxabs / minabs : mx - mn;
+    return (b < a) ? fc : -fc;
+}
+
+/* psych::corr.test: p of r on n-2 df */
+EPX_HD double epx_pearson_p(double r, double n)
+{
+    double t = (r * sqrt(n - 2.0)) / sqrt(1.0 - r * r);
+    return epx_t_two_sided_p(t, n - 2.0);
+}
+
+#endif /* EPX_MATH_H */

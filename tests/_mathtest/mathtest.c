@@ -1,0 +1,13 @@
+/* CPU unit-test build of epimethex_b200/csrc/epx_math.h (the header the CUDA kernels include).
+ * Built by tests/conftest.py with gcc; used only by tests/test_math_cpu.py. */
+#include "../../epimethex_b200/csrc/epx_math.h"
+double mt_t_two_sided_p(double t, double df) { return epx_t_two_sided_p(t, df); }
+double mt_pkstwo(double x) { return epx_pkstwo(x); }
+double mt_ks_p_asym(double dnum, double la, double lb) { return epx_ks_p_asym(dnum, la, lb); }
+double mt_ks_p_exact(double dnum, int la, int lb, double *u) { return epx_ks_p_exact(dnum, la, lb, u); }
+double mt_log_fc(double a, double b) { return epx_log_fc(a, b); }
+double mt_linear_fc(double a, double b) { return epx_linear_fc(a, b); }
+double mt_pearson_p(double r, double n) { return epx_pearson_p(r, n); }
+double mt_lbeta_half(double a) { return epx_lbeta_half(a); }
+int mt_welch(double mx, double vx, double nx, double my, double vy, double ny, double *t, double *df)
+{ return epx_welch(mx, vx, nx, my, vy, ny, t, df); }

@@ -1,0 +1,170 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the oracle. Run with -m gpu on a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from epimethex_b200 import _native, analysis, synth
+from parity import assert_parity, run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def sess():
+    s = _native.Session(0)
+    yield s
+    s.close()
+
+
+def _synth(n_genes, n, n_probes, *, decimals=None, ties=True, missing_every=0):
+    ann = synth.annotation(n_probes, n_genes)
+    x = synth.expression(n_genes, n, ties=ties)
+    y = synth.methylation(n_probes, n, ann, decimals=decimals, threads=4)
+    has = None
+    if missing_every:
+        has = np.ones(n_probes, bool); has[::missing_every] = False
+    return x, y, synth.probe_index(ann, 0, n_genes, probe_has_data=has)
+
+
+def test_device_is_b200():
+    info = _native.device_info(0)
+    assert "B200" in info["name"] and info["sm_count"] == 148, info
+
+
+def test_readme_fixture_against_golden_and_oracle(sess, readme_frames):
+    """BASELINE config 1: epimethex.analysis(Expr, Annot, Meth, 1, 3, 2, TRUE, TRUE, FALSE)"""
+    dfe, dfa, dfm = readme_frames
+    prep = analysis.prepare(dfe, dfa, dfm, 1, 3)
+    got = run_gpu(sess, prep.expr, prep.meth, prep.index)
+    assert_parity(got, run_oracle(prep.expr, prep.meth, prep.index), "readme")
+    gold = json.load(open(os.path.join(HERE, "golden", "readme_fixture.json")))
+    df = analysis.assemble_table(prep, got)
+    for name, want in gold["rows"].items():
+        np.testing.assert_allclose(df.loc[name].to_numpy()[:17].astype(float), want, rtol=1e-8, atol=1e-10)
+        assert df.loc[name, "island"] == gold["islands"][name]
+
+
+def test_public_api_writes_the_reference_csv(tmp_path, readme_frames):
+    from epimethex_b200 import epimethex_analysis
+    dfe, dfa, dfm = readme_frames
+    df = epimethex_analysis(dfe, dfa, dfm, 1, 3, 2, True, True, False, output_dir=str(tmp_path))
+    text = (tmp_path / "1-3" / "CG_data_individually.csv").read_text().splitlines()
+    assert len(text) == 4 and text[0].count(",") == 18
+    assert text[1].startswith('"cg11663302_Body_ARHGEF10L","0.9841","0.9825","0.9872"')
+    assert df.shape == (3, 18)
+
+
+@pytest.mark.parametrize("te,tm", [(True, False), (True, True), (False, False), (False, True)])
+@pytest.mark.parametrize("n", [6, 30, 99, 474, 999])
+def test_modes_and_sizes_divisible_by_3(sess, n, te, tm):
+    G, P = (300, 4000) if n <= 99 else (120, 2500)
+    x, y, idx = _synth(G, n, P)
+    got = run_gpu(sess, x, y, idx, te=te, tm=tm)
+    assert_parity(got, run_oracle(x, y, idx, te=te, tm=tm), f"n={n} te={te} tm={tm}")
+
+
+@pytest.mark.parametrize("n", [7, 31, 473, 1000])
+def test_extension_for_n_not_divisible_by_3(sess, n):
+    """the reference stops here; extension = the n mod 3 lowest-expression samples are unlabelled."""
+    x, y, idx = _synth(100, n, 2000)
+    for tm in (False, True):
+        got = run_gpu(sess, x, y, idx, tm=tm)
+        assert_parity(got, run_oracle(x, y, idx, tm=tm), f"n={n} tm={tm}")
+    with pytest.raises(_native.EpxError) as e:
+        sess.run(_native.make_options(strict_n3=True))
+    assert e.value.code == -6
+
+
+@pytest.mark.parametrize("n,decimals", [(30, 2), (99, 2), (474, 3), (999, 4)])
+def test_ties_in_methylation(sess, n, decimals):
+    """Xena-style rounded beta values: KS evaluated at tie-run ends; exact p only without pooled ties."""
+    x, y, idx = _synth(150, n, 3000, decimals=decimals)
+    got = run_gpu(sess, x, y, idx)
+    ref = run_oracle(x, y, idx)
+    assert_parity(got, ref, f"ties n={n}")
+
+
+def test_missing_probes_constant_rows_and_guard(sess):
+    x, y, idx = _synth(80, 30, 1500, missing_every=4)
+    y = y.copy()
+    rows = np.unique(idx.probe_idx[idx.probe_idx >= 0])
+    y[rows[0]] = 0.25                                   # constant row: guard NA x3, Pearson NA
+    y[rows[1]] = np.tile([0.1, 0.2, 0.3], 10)           # differences between rank-paired groups may be constant
+    g = idx.pair_gene[np.nonzero(idx.probe_idx == rows[2])[0][0]]
+    perm = np.argsort(-x[g], kind="stable")
+    v = np.empty(30); v[perm] = np.concatenate([np.linspace(0.5, 0.6, 10), np.linspace(0.4, 0.5, 10), np.linspace(0.1, 0.9, 10)])
+    y[rows[2]] = v                                      # UP - Medium is exactly constant for gene g: guard hits one test
+    for tm in (False, True):
+        got = run_gpu(sess, x, y, idx, tm=tm)
+        ref = run_oracle(x, y, idx, tm=tm)
+        assert_parity(got, ref, f"edge tm={tm}")
+        assert (ref.pair_na == 0x7FF).any() and ((ref.pair_na & 0x1C0) != 0).any()
+
+
+def test_log_fold_change_and_means_variant(sess):
+    x, y, idx = _synth(200, 60, 1000, ties=False)
+    for linear, fcm in ((False, False), (True, True), (False, True)):
+        got = run_gpu(sess, x, y, idx, linear=linear, fc_means=fcm)
+        assert_parity(got, run_oracle(x, y, idx, linear=linear, fc_means=fcm), f"linear={linear} means={fcm}")
+
+
+def test_session_reuse_across_gene_ranges(sess):
+    """README: users call per gene range; the uploaded methylation matrix stays on the device."""
+    ann = synth.annotation(3000, 200)
+    y = synth.methylation(3000, 99, ann, threads=4)
+    sess.set_methylation(y)
+    for g0, g1 in ((0, 70), (70, 200), (0, 200)):
+        x = synth.expression(g1 - g0, 99, g0=g0)
+        idx = synth.probe_index(ann, g0, g1)
+        got = run_gpu(sess, x, y, idx, upload=False)
+        assert_parity(got, run_oracle(x, y, idx), f"range {g0}-{g1}")
+
+
+def test_sample_major_upload_matches_row_major(sess):
+    x, y, idx = _synth(60, 45, 700)
+    a = run_gpu(sess, x, y, idx)
+    sess.set_methylation_columns([np.ascontiguousarray(y[:, j]) for j in range(y.shape[1])])
+    b = run_gpu(sess, x, y, idx, upload=False)
+    assert np.array_equal(a.pair, b.pair, equal_nan=True) and np.array_equal(a.ks_dnum, b.ks_dnum)
+
+
+def test_breaks_not_unique_is_reported(sess):
+    """bin.var stops with "'breaks' are not unique" when the reference gene is mostly tied (reference behaviour)."""
+    x = np.zeros((3, 9)); x[:, 0] = [1, 2, 3]
+    y = np.random.default_rng(0).random((4, 9))
+    sess.set_methylation(y)
+    with pytest.raises(_native.EpxError) as e:
+        sess.analyze(x, np.array([0, 1, 2, 4]), np.array([0, 1, 2, 3], np.int32))
+    assert e.value.code == -5
+
+
+def test_full_size_properties_skcm_slice(sess):
+    """BASELINE-size rows (473 samples), a 1,500-gene slice: size-independent properties instead of the oracle:
+    (i) relabelling symmetry: reversing every expression row swaps UP and Down (no ties): medians swap, KS
+    numerators of UPvsMID / MIDvsDOWN swap, Pearson r flips sign; (ii) affine invariance of r."""
+    ann = synth.annotation(40000, 1500)
+    y = synth.methylation(40000, 474, ann, threads=8)
+    idx = synth.probe_index(ann, 0, 1500)
+    x = synth.expression(1500, 474, ties=False)
+    sess.set_methylation(y)
+    a = run_gpu(sess, x, y, idx, upload=False)
+    b = run_gpu(sess, -x, y, idx, upload=False)
+    ok = a.pair_na == 0
+    np.testing.assert_array_equal(a.pair[ok][:, [0, 1, 2]], b.pair[ok][:, [2, 1, 0]])
+    np.testing.assert_array_equal(a.ks_dnum[ok][:, [0, 1, 2]], b.ks_dnum[ok][:, [2, 1, 0]])
+    np.testing.assert_allclose(a.pair[ok][:, 9], -b.pair[ok][:, 9], rtol=1e-9, atol=1e-12)
+    c = run_gpu(sess, 3.0 * x + 1.0, y, idx, upload=False)
+    np.testing.assert_allclose(a.pair[ok][:, 9], c.pair[ok][:, 9], rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(a.ks_dnum, c.ks_dnum)
+    # and a sample of genes against the oracle
+    sel = np.arange(0, 1500, 25)
+    ptr = np.zeros(sel.size + 1, np.int64); pi = []
+    for k, g in enumerate(sel):
+        pi.append(idx.probe_idx[idx.row_ptr[g]:idx.row_ptr[g + 1]]); ptr[k + 1] = ptr[k] + pi[-1].size
+    sub = type(idx)(ptr, np.concatenate(pi), None, None, None, None, None)
+    ref = run_oracle(x[sel], y, sub)
+    got = run_gpu(sess, x[sel], y, sub, upload=False)
+    assert_parity(got, ref, "skcm slice sample")

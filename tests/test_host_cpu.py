@@ -1,0 +1,137 @@
+"""Host-side logic (annotation join -> CSR, input filters, table assembly) and the C-ABI surface. CPU only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from epimethex_b200 import _native, analysis, annotation, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ann(rows):
+    cols = ["ID", "Relation_to_UCSC_CpG_Island", "UCSC_CpG_Islands_Name", "UCSC_RefGene_Accession", "Chromosome_36",
+            "Coordinate_36", "UCSC_RefGene_Name", "UCSC_RefGene_Group"]
+    return pd.DataFrame(rows, columns=cols)
+
+
+def test_library_exports_every_declared_symbol():
+    """every function include/epx.h declares is exported by libepx.so (loading only; no compute without a GPU)"""
+    header = open(os.path.join(ROOT, "include", "epx.h")).read()
+    declared = set(re.findall(r"\b(epx_[a-z_0-9]+)\s*\(", header)) - {"epx_session", "epx_options", "epx_result", "epx_timing"}
+    assert declared == set(_native.EXPORTS)
+    L = C.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _native.lib().epx_abi_version() == 1
+
+
+def test_no_gpu_is_an_error_not_a_fallback():
+    try:
+        n = _native.device_count()
+    except _native.EpxError:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.EpxError):
+        _native.Session(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "epimethex_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "epx_oracle" not in src and "from oracle" not in src, f
+
+
+def test_explode_sort_dedup_semantics():
+    """R/EpimethexAnalysis.R:248-257, :287-291 incl. SURVEY 8g-6 (dedup on (cg, position) ignores the gene)."""
+    dfa = _ann([
+        ["cg1", "Island", "chr1:1-2", "NM_1;NM_2", "1", "300", "B;A", "Body;Body"],      # shared probe, same group
+        ["cg2", "N_Shore", "chr1:5-9", "NM_3;NM_4", "1", "100", "A;A", "TSS200;Body"],   # two groups in one gene
+        ["cg3", "", "", "NM_5", "1", "1000", "A", "Body"],                               # "1000" < "300" as strings
+        ["cg4", "Island", "chr2:1-2", "NM_6", "2", "50", "", "Body"],                    # no gene -> dropped
+        ["cg5", "S_Shelf", "chr3:1-2", "NM_7", "3", "70", "C", "3'UTR"],                 # gene not analysed
+        ["cg6", "Island", "chr4:1-2", "NM_8", "4", "10", "B", "1stExon"],                # annotated, no data row
+    ])
+    idx = annotation.build_probe_index(dfa, ["B", "A", "Z"], ["cg1", "cg2", "cg3", "cg5"])
+    # reference order: gene A (sorted names) by coordinate STRING: "100","100","1000","300"; then gene B: "10","300"
+    ref_rows = [(idx.cg[i], idx.position[i], ["B", "A", "Z"][idx.pair_gene[i]]) for i in idx.output_order]
+    assert ref_rows == [("cg2", "TSS200", "A"), ("cg2", "Body", "A"), ("cg3", "Body", "A"), ("cg1", "Body", "A"),
+                        ("cg6", "1stExon", "B")]          # cg1/Body survives only under A (alphabetically first)
+    assert idx.row_ptr.tolist() == [0, 1, 5, 5]           # CSR is in EXPRESSION order: B, A, Z
+    assert idx.probe_idx.tolist() == [-1, 1, 1, 2, 0]     # cg6 has no methylation row
+    assert idx.island[idx.output_order].tolist()[:3] == ["N_Shore_chr1:5-9", "N_Shore_chr1:5-9", "_"]
+
+
+def test_numeric_coordinates_sort_numerically():
+    dfa = _ann([["cg1", "Island", "x", "NM", "1", 300, "A", "Body"], ["cg2", "Island", "x", "NM", "1", 1000, "A", "Body"]])
+    idx = annotation.build_probe_index(dfa, ["A"], ["cg1", "cg2"])
+    assert idx.cg.tolist() == ["cg1", "cg2"]
+    dfa["Coordinate_36"] = dfa["Coordinate_36"].astype(str)
+    assert annotation.build_probe_index(dfa, ["A"], ["cg1", "cg2"]).cg.tolist() == ["cg2", "cg1"]
+
+
+def test_expression_filters():
+    """R/EpimethexAnalysis.R:86, :103-114"""
+    df = pd.DataFrame({"sample": ["g1", "g2", "g3", "g4", "g5"],
+                       "s1": [1.0, 0.0, 2.0, 0.0, 9.0], "s2": [2.0, 0.0, np.nan, np.nan, 9.0],
+                       "s3": [3.0, 0.0, 4.0, 0.0, 9.0], "s4": [4.0, 0.0, 5.0, 0.0, 9.0]})
+    x, genes, samples = analysis.prepare_expression(df, 1, 4)      # g5 is outside the range
+    assert genes == ["g1", "g3"]                                    # g2 all zero; g4 zero-or-NA -> dropped
+    assert samples == ["s1", "s3", "s4"]                            # s2 has an NA in a kept gene
+    assert x.tolist() == [[1.0, 3.0, 4.0], [2.0, 4.0, 5.0]]
+
+
+def test_methylation_matched_by_sample_name_and_na_probes_dropped():
+    dfm = pd.DataFrame({"sample": ["cg1", "cg2", "cg3"], "s3": [0.3, 0.6, 0.9], "s1": [0.1, np.nan, 0.7], "s2": [0.2, 0.5, 0.8]})
+    m, ids = analysis.prepare_methylation(dfm, ["s1", "s3"])
+    assert ids.tolist() == ["cg1", "cg3"] and m.tolist() == [[0.1, 0.3], [0.7, 0.9]]
+    with pytest.raises(KeyError):
+        analysis.prepare_methylation(dfm, ["s1", "s9"])
+
+
+def test_synthetic_index_agrees_with_string_path():
+    dfe, dfa, dfm, ann = synth.frames(50, 12, 400)
+    prep = analysis.prepare(dfe, dfa, dfm, 1, 50)
+    assert len(prep.gene_names) == 50
+    idx = synth.probe_index(ann, 0, 50)
+    for f in ("row_ptr", "probe_idx", "pair_gene", "output_order", "cg", "position", "island"):
+        assert np.array_equal(getattr(prep.index, f), getattr(idx, f)), f
+    sub = analysis.prepare(dfe, dfa, dfm, 11, 30)                   # a gene range, as the README recommends
+    idx2 = synth.probe_index(ann, 10, 30)
+    assert np.array_equal(sub.index.row_ptr, idx2.row_ptr) and np.array_equal(sub.index.probe_idx, idx2.probe_idx)
+
+
+def test_synth_is_counter_based():
+    ann = synth.annotation(300, 20)
+    full = synth.methylation(300, 17, ann, threads=2, chunk=64)
+    part = synth.methylation_rows([5, 250, 7], 17, ann)
+    assert np.array_equal(full[[5, 250, 7]], part)
+    assert np.array_equal(synth.expression(20, 17)[3:9], synth.expression(6, 17, g0=3))
+    assert (synth.expression(2000, 30) == 0).mean() > 0.01          # genuine zero ties exist
+
+
+def test_assemble_and_csv(tmp_path, readme_frames):
+    """table assembly (R/EpimethexAnalysis.R:425-470) from an engine result (here: canned numbers)"""
+    dfe, dfa, dfm = readme_frames
+    prep = analysis.prepare(dfe, dfa, dfm, 1, 3)
+    res = _native.Result(pair=np.arange(33, dtype=float).reshape(3, 11) / 7, pair_na=np.array([0, 1 << 6, 0], np.uint16),
+                         pair_stat=np.zeros((3, 3)), ks_dnum=np.zeros((3, 3), np.int32), gene=np.ones((3, 15)) * 0.5,
+                         gene_na=np.array([0, 0, 1 << 3], np.uint16), gene_ks_dnum=np.zeros((3, 3), np.int32),
+                         perm=np.zeros((3, 6), np.uint16))
+    df = analysis.assemble_table(prep, res)
+    assert list(df.columns) == analysis.OUTPUT_COLUMNS
+    assert list(df.index) == ["cg11663302_Body_ARHGEF10L", "cg01552731_1stExon_HIF3A", "cg09081385_TSS200_RNF10"]
+    assert np.isnan(df.iloc[1, 6]) and np.isnan(df.iloc[2, 14]) and df.iloc[0, 17] == "Island_chr1:18023481-18023792"
+    p = tmp_path / "t.csv"
+    analysis.write_csv_like_r(df, str(p))
+    lines = p.read_text().splitlines()
+    assert lines[0].startswith('"","medianDown","medianMedium"') and lines[0].endswith('"island"')
+    assert lines[1].split(",")[2] == '"0.142857142857143"'          # 15 significant digits, quoted
+    assert "NA" in lines[2].split(",")
