@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — gene-probe pairs/s of the EpiMethEx association path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload skcm_full] [--impl ours|reference]
+
+A "step" is one pass of the whole device pipeline (gene stratification + tests, per-probe rank, fused
+gather/moments/medians/KS per pair) over the synthetic workload, inputs resident in HBM.  One JSON line
+is printed by rank 0.  `value` is device-timed (CUDA events, max over ranks); `e2e` is the same metric
+through the blocking C-ABI call epx_analyze with pinned HOST buffers (methylation + expression + index
+H2D, kernels, result tables D2H inside the timed region); `roofline` is the dominant kernel's algorithmic
+bytes over its CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` is the CPU oracle (the restated
+reference, C + OpenMP, all host cores) on a bounded gene sample of the same workload.
+
+Under torchrun (N > 1) every rank runs its own cohort of the same shape (weak scaling: genes/probes shard
+with no data-path collective) and the per-rank result tables are gathered to rank 0 over NCCL inside the
+timed region, as the path's only exchange step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the north_star target shape (fits one GPU; inputs 1.8 GB >> 126 MB L2)
+    "skcm_full": dict(shape="skcm", genes=(0, 20531), te=True, tm=False,
+                      desc="synthetic SKCM full genome: 20,531 genes x 473 samples, 485,577 probes, t-test expression + KS methylation"),
+    "skcm_full_tt": dict(shape="skcm", genes=(0, 20531), te=True, tm=True,
+                         desc="synthetic SKCM full genome, t-test on both"),
+    # BASELINE.json configs[1]
+    "skcm_1000": dict(shape="skcm", genes=(0, 1000), te=True, tm=True,
+                      desc="synthetic SKCM shape, gene range 1-1000, 473 samples, HM450 annotation, t-test on both"),
+    "skcm474_full": dict(shape="skcm474", genes=(0, 20531), te=True, tm=False,
+                         desc="SKCM full genome at 474 samples (nearest multiple of 3: the reference's defined case)"),
+    "epic": dict(shape="epic", genes=(0, 20531), te=False, tm=False,
+                 desc="synthetic EPIC-array shape: 866k probes x 1,000 samples, KS on both"),
+    "tiny": dict(shape=None, genes=(0, 300), te=True, tm=False, n_samples=99, n_probes=6000, n_genes=300,
+                 desc="tiny self-test workload"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v == "Active":
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name: str, rank: int):
+    """Synthetic inputs for one rank. Rank r draws its own cohort (data seeds + r) over the same annotation."""
+    from epimethex_b200 import _native, synth
+
+    w = WORKLOADS[name]
+    dims = dict(synth.SHAPES[w["shape"]]) if w["shape"] else dict(n_genes=w["n_genes"], n_samples=w["n_samples"], n_probes=w["n_probes"])
+    n, P = dims["n_samples"], dims["n_probes"]
+    g0, g1 = w["genes"]
+    t0 = time.time()
+    ann = synth.annotation(P, dims["n_genes"])
+    idx = synth.probe_index(ann, g0, g1)
+    expr = synth.expression(g1 - g0, n, g0=g0, seed=synth.SEED_EXPR + rank)
+    try:
+        meth = _native.pinned_empty((P, n))
+    except Exception:
+        meth = np.empty((P, n))
+    threads = max(1, min(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    # only rows some pair references are ever read; generate those, zero the rest
+    used = np.unique(idx.probe_idx[idx.probe_idx >= 0])
+    meth[...] = 0.0
+    from concurrent.futures import ThreadPoolExecutor
+
+    def work(chunk):
+        meth[chunk] = synth.methylation_rows(chunk, n, ann, seed=synth.SEED_METH + rank)
+
+    chunks = [used[i:i + 4096] for i in range(0, used.size, 4096)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, chunks))
+    return dict(w=w, n=n, P=P, G=g1 - g0, ann=ann, idx=idx, expr=np.ascontiguousarray(expr), meth=meth,
+                gen_s=time.time() - t0, n_unique=int(used.size))
+
+
+def cpu_baseline(wl, target_s: float, threads: int):
+    """oracle (restated reference, C + OpenMP over genes) on every k-th gene of the same workload"""
+    import oracle
+
+    idx, expr, meth = wl["idx"], wl["expr"], wl["meth"]
+    G = wl["G"]
+
+    def subset(stride):
+        sel = np.arange(0, G, stride)
+        counts = (idx.row_ptr[sel + 1] - idx.row_ptr[sel])
+        ptr = np.zeros(sel.size + 1, np.int64)
+        np.cumsum(counts, out=ptr[1:])
+        pi = np.concatenate([idx.probe_idx[idx.row_ptr[g]:idx.row_ptr[g + 1]] for g in sel]) if sel.size else np.zeros(0, np.int32)
+        return sel, ptr, pi
+
+    def run(stride):
+        sel, ptr, pi = subset(stride)
+        t = time.perf_counter()
+        oracle.analyze(expr[sel], meth, ptr, pi, test_expr_t=wl["w"]["te"], test_meth_t=wl["w"]["tm"], threads=threads)
+        return int(ptr[-1]), time.perf_counter() - t, sel.size
+
+    probe_stride = max(1, G // 64)
+    pairs, dt, _ = run(probe_stride)
+    rate = pairs / max(dt, 1e-6)
+    total_pairs = int(idx.row_ptr[-1])
+    want_pairs = min(total_pairs, max(pairs, int(rate * target_s)))
+    stride = max(1, int(round(total_pairs / max(want_pairs, 1))))
+    pairs, dt, ngenes = run(stride)
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"every {stride}th gene of the workload ({ngenes} genes, {pairs} pairs) in {dt:.1f} s; "
+                      "C/OpenMP restatement of the R reference (R is not installable here)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="skcm_full", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # the reference's CPU implementation of the path on this host's cores; rank 0 only
+        if rank != 0:
+            return 0
+        wl = make_workload(args.workload, 0)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_baseline(wl, max(2.0, args.cpu_seconds / max(1, args.steps)), cores)
+            if i >= args.warmup:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals]))
+        line = {"impl": "reference", "metric": "gene-probe pairs/s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["w"]["desc"], "name": args.workload},
+                "cpu_baseline": dict(vals[-1], value=v),
+                "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from epimethex_b200 import _native
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = make_workload(args.workload, rank)
+    idx, n, G, P = wl["idx"], wl["n"], wl["G"], wl["P"]
+    Np = idx.n_pairs
+    opts = _native.make_options(True, wl["w"]["te"], wl["w"]["tm"])
+    sess = _native.Session(local_rank)
+    sess.set_methylation(wl["meth"])
+    sess.set_expression(wl["expr"])
+    sess.set_index(idx.row_ptr, idx.probe_idx)
+    # an explicit (non-default) torch stream: its handle is what the library launches on, so
+    # torch.cuda.Event timings below see exactly the library's kernels
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    # result gather (the path's only exchange step): per-rank pair/gene tables -> rank 0 over NCCL
+    gather_bufs = None
+
+    def step():
+        sess.run(opts, stream)
+        if world > 1:
+            nonlocal gather_bufs
+            if gather_bufs is None:
+                gather_bufs = {}
+                for which, cols, count in ((0, 11, Np), (4, 15, G)):
+                    ptr, nbytes = sess.result_device_ptr(which)
+                    # view the library's device table as a torch tensor (no copy)
+                    t = torch.as_tensor(_DevArray(ptr, (count, cols)), device="cuda")
+                    dst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+                    gather_bufs[which] = (t, dst)
+            for t, dst in gather_bufs.values():
+                dist.gather(t, dst, dst=0)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {"gene_sort_ms": 0.0, "gene_tests_ms": 0.0, "probe_rank_ms": 0.0, "pair_stats_ms": 0.0}
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    # per-kernel CUDA-event times of the last step (events recorded by the library on the same stream)
+    tim = sess.timing()
+    # average the per-kernel times over a few more steps, each read back right after it ran
+    reps = min(5, args.steps)
+    for _ in range(reps):
+        sess.run(opts, stream)
+        t = sess.timing()
+        for k in kern:
+            kern[k] += t[k] / reps
+    clocks = sampler.stop()
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        tot = torch.tensor([float(Np)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot)
+        total_pairs = float(tot.item())
+    else:
+        total_pairs = float(Np)
+    ms_per_step = ms / args.steps
+    value = total_pairs / (ms_per_step * 1e-3)
+
+    # ---- e2e through the blocking C-ABI call with host buffers ----
+    h2d = P * n * 8 + G * n * 8 + (G + 1) * 8 + Np * 4
+    d2h = Np * (11 * 8 + 2) + G * (15 * 8 + 2)
+    e2e_ms = []
+    for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sess.set_methylation(wl["meth"])
+        sess.analyze(wl["expr"], idx.row_ptr, idx.probe_idx, opts, full=False)
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_ms.append(dt * 1e3)
+    e2e_t = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
+    if args.e2e_steps <= 0:
+        e2e_t = float("nan")
+    if world > 1:
+        tmax = torch.tensor([e2e_t], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_t = float(tmax.item())
+    e2e_value = total_pairs / (e2e_t * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # algorithmic bytes per launch: pair kernel N_p*(8n+88); rank kernel U*(8n read + 2n written)
+        alg = {"pair_stats_ms": Np * (8 * n + 88), "probe_rank_ms": wl["n_unique"] * (8 * n + 2 * n),
+               "gene_sort_ms": G * (8 * n + 2 * n + 8 * n + n), "gene_tests_ms": G * (10 * n + 15 * 8)}
+        kernels = {}
+        for k, t in kern.items():
+            gbs = alg[k] / (t * 1e-3) / 1e9 if t > 0 else 0.0
+            kernels[k[:-3]] = {"ms": round(t, 4), "algorithmic_bytes": int(alg[k]), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        dom = max(kern, key=lambda k: kern[k])
+        line = {
+            "metric": "gene-probe pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["w"]["desc"], "name": args.workload, "pairs_per_gpu": Np, "genes": G, "samples": n,
+                       "probes": P, "unique_probes": wl["n_unique"], "l2": "inputs (%.2f GB methylation) exceed the 126 MB L2; no flush" % (P * n * 8 / 1e9),
+                       "parallelism": f"genes sharded, {world} rank(s), NCCL gather of result tables" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "kernel": dom[:-3], "achieved": kernels[dom[:-3]]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom[:-3]]["frac"], "traffic": None, "peak_source": peak_src},
+            "kernels": kernels,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_t, "steps": len(e2e_ms)},
+            "gpu_launches": int(tim["kernel_launches"]) * args.steps,
+            "clocks": clocks,
+            "setup_s": round(wl["gen_s"], 1),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds, cores)
+        print(json.dumps(line))
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+class _DevArray:
+    """minimal __cuda_array_interface__ holder so torch can view a libepx device table without copying"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -394,12 +394,12 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
 
     s->launches = 0;
     EPX_CUDA(cudaEventRecord(s->ev[0], st));
-    EPX_CUDA(launch_gene_sort(gp, st)); s->launches++;
+    EPX_CUDA(launch_gene_sort(gp, s->sm_count, st)); s->launches++;
     EPX_CUDA(cudaEventRecord(s->ev[1], st));
     EPX_CUDA(launch_pick_reference(tp, st)); s->launches++;
     EPX_CUDA(launch_gene_tests(tp, st)); s->launches++;
     EPX_CUDA(cudaEventRecord(s->ev[2], st));
-    if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, st)); s->launches++; }
+    if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[3], st));
     if (s->n_items > 0) { EPX_CUDA(launch_pair_stats(pp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[4], st));

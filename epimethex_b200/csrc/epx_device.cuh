@@ -20,6 +20,16 @@ __device__ __forceinline__ unsigned long long key_of(double v)
     return (b < 0) ? ~u : (u | 0x8000000000000000ull);
 }
 
+/* the same key as two 32-bit halves (what the warp sort consumes) */
+__device__ __forceinline__ void key_halves(double v, unsigned &hi, unsigned &lo)
+{
+    v = v + 0.0;
+    const int h = __double2hiint(v);
+    const unsigned m = (unsigned)(h >> 31);
+    hi = (unsigned)h ^ (m | 0x80000000u);
+    lo = (unsigned)__double2loint(v) ^ m;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

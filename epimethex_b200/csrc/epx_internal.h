@@ -18,7 +18,7 @@ struct Item {
 
 constexpr int PAIR_COLS = 11;
 constexpr int GENE_COLS = 15;
-constexpr int ITEM_PAIRS = 16;       /* pairs per work item */
+constexpr int ITEM_PAIRS = 32;       /* pairs per work item (one deferred p-value per lane) */
 constexpr int MAX_WARP_SAMPLES = 1024; /* warp-per-pair kernel: n <= 32 lanes * 32 elements */
 
 /* device status word (d_status) */
@@ -86,10 +86,10 @@ struct PairParams {
     int32_t *pair_dnum;     /* [Np][3] */
 };
 
-cudaError_t launch_gene_sort(const GeneParams &p, cudaStream_t st);
+cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st);
 cudaError_t launch_gene_tests(const GeneTestParams &p, cudaStream_t st);
-cudaError_t launch_probe_rank(const RankParams &p, cudaStream_t st);
+cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st);
 /* dst[p*ld + s0 + j] = src[j*P + p], j < ns : sample-major chunk -> probe-major rows */
 cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,

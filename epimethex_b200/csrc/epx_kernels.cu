@@ -13,6 +13,7 @@
  */
 #include "epx_device.cuh"
 #include "epx_internal.h"
+#include "epx_warpsort.cuh"
 
 namespace epx {
 
@@ -286,17 +287,119 @@ __global__ void __launch_bounds__(256) k_probe_rank(RankParams p)
     }
 }
 
+
+/* ============================================================ warp-per-row variants (n <= 1024) */
+
+constexpr int SORT_WARPS = 8;
+
+/* k_gene_sort, one warp per gene */
+template <int EPS>
+__global__ void __launch_bounds__(SORT_WARPS * 32) k_gene_sort_w(GeneParams p)
+{
+    __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
+    const int nw = gridDim.x * SORT_WARPS;
+    for (int g = blockIdx.x * SORT_WARPS + warp; g < p.G; g += nw) {
+        const double *x = p.expr + (int64_t)g * n;
+        unsigned khi[EPS], klo[EPS];
+        double xv[EPS];
+        double sum = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int s = lane + 32 * e;
+            xv[e] = s < n ? __ldg(x + s) : 0.0;
+            key_halves(xv[e], khi[e], klo[e]);
+            khi[e] = ~khi[e]; klo[e] = ~klo[e]; /* descending by value */
+            sum += xv[e];
+        }
+        unsigned short out[EPS];
+        WarpSort<EPS>::order(khi, klo, n, lane, s_ord[warp], [&](int i) { return ~key_of(__ldg(x + i)); }, out);
+        int ties = 0;
+#pragma unroll
+        for (int r = 0; r < EPS; r++) {
+            const int k = lane * EPS + r;
+            if (k < n) {
+                const int s = out[r] & 0x7fff;
+                ties += (out[r] >> 15) & 1;
+                p.perm[(int64_t)g * n + k] = (uint16_t)s;
+                const int lab = k / p.m;
+                p.lab8[(int64_t)g * p.ldl + s] = (uint8_t)(lab > 3 ? 3 : lab);
+            }
+        }
+        ties = __reduce_add_sync(FULL, ties);
+        const double mean = warp_sum(sum) / (double)n;
+        double sxx = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int s = lane + 32 * e;
+            if (s < n) {
+                const double d = xv[e] - mean;
+                p.xc[(int64_t)g * p.ldx + s] = d;
+                sxx += d * d;
+            }
+        }
+        sxx = warp_sum(sxx);
+        if (lane == 0) {
+            const int u = n - ties;
+            p.nuniq[g] = u;
+            p.gene_aux[2 * (int64_t)g] = (u == 1) ? 0.0 : sxx;
+            p.gene_aux[2 * (int64_t)g + 1] = mean;
+        }
+    }
+}
+
+/* k_probe_rank, one warp per referenced probe */
+template <int EPS>
+__global__ void __launch_bounds__(SORT_WARPS * 32) k_probe_rank_w(RankParams p)
+{
+    __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
+    const int64_t nw = (int64_t)gridDim.x * SORT_WARPS;
+    for (int64_t slot = (int64_t)blockIdx.x * SORT_WARPS + warp; slot < p.U; slot += nw) {
+        const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
+        unsigned khi[EPS], klo[EPS];
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int s = lane + 32 * e;
+            key_halves(s < n ? __ldg(row + s) : 0.0, khi[e], klo[e]);
+        }
+        unsigned short out[EPS];
+        WarpSort<EPS>::order(khi, klo, n, lane, s_ord[warp], [&](int i) { return key_of(__ldg(row + i)); }, out);
+        uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
+        if (EPS >= 8) {
+#pragma unroll
+            for (int c = 0; c < EPS / 8; c++) {
+                if (lane * EPS + c * 8 < p.ldo) {
+                    uint4 q;
+                    q.x = out[c * 8 + 0] | ((unsigned)out[c * 8 + 1] << 16);
+                    q.y = out[c * 8 + 2] | ((unsigned)out[c * 8 + 3] << 16);
+                    q.z = out[c * 8 + 4] | ((unsigned)out[c * 8 + 5] << 16);
+                    q.w = out[c * 8 + 6] | ((unsigned)out[c * 8 + 7] << 16);
+                    *reinterpret_cast<uint4 *>(o + c * 8) = q;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < EPS; r++)
+                if (lane * EPS + r < p.ldo) o[r] = out[r];
+        }
+    }
+}
+
 /* ============================================================ k_pair_stats (warp per pair, n <= 1024) */
 
 constexpr int PAIR_WARPS = 8;
 
 __host__ __device__ inline size_t pair_warp_smem(int n)
 {
-    int npad = (n + 1) & ~1;
-    return (size_t)16 * npad + (size_t)((n + 15) & ~15) + 64; /* xc | row | lab | 6 median slots (+pad) */
+    const int npad = (n + 1) & ~1;
+    /* xc | row | 8 median slots | deferred Student-t arguments (r, 3 t, 3 df per pair of the item) | labels */
+    return (size_t)16 * npad + 64 + (size_t)ITEM_PAIRS * 7 * 8 + (size_t)((n + 15) & ~15);
 }
 
-template <int EPL, bool TMODE>
+/* EPL: elements per lane of the sample-major pass (ceil(n/32) rounded up to an instantiated value);
+ * EPW: positions per lane of the sorted walk = the power of two k_probe_rank_w blocks its output by. */
+template <int EPL, int EPW, bool TMODE>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -306,8 +409,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
     unsigned char *base = smem + (size_t)warp * pair_warp_smem(n);
     double *s_xc = (double *)base;
     double *s_row = s_xc + npad;
-    double *s_med = s_row + npad;                 /* 6 doubles */
-    uint8_t *s_lab = (uint8_t *)(s_med + 8);
+    double *s_med = s_row + npad;                 /* 6 used */
+    double *s_r = s_med + 8;                      /* [ITEM_PAIRS] Pearson r (NaN = NA) */
+    double *s_t = s_r + ITEM_PAIRS;               /* [ITEM_PAIRS][3] Welch t (NaN = NA) */
+    double *s_df = s_t + 3 * ITEM_PAIRS;          /* [ITEM_PAIRS][3] */
+    uint8_t *s_lab = (uint8_t *)(s_df + 3 * ITEM_PAIRS);
 
     const int gw = blockIdx.x * PAIR_WARPS + warp, nw = gridDim.x * PAIR_WARPS;
     const double dm = (double)m, dn_ = (double)n;
@@ -333,12 +439,17 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
             }
             __syncwarp();
         }
-        for (int j = item.begin; j < item.begin + item.count; j++) {
+        for (int jj = 0; jj < item.count; jj++) {
+            const int j = item.begin + jj;
             const int pi = p.probe_idx[j];
             if (pi < 0) { /* annotated probe without data: all-NA column (R/EpimethexAnalysis.R:375-394) */
                 if (lane < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + lane] = EPX_NAN;
                 if (lane < 3) { p.pair_stat[(int64_t)j * 3 + lane] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + lane] = -1; }
-                if (lane == 0) p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+                if (lane == 0) {
+                    p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+                    s_r[jj] = EPX_NAN;
+                    if (TMODE) { s_t[jj * 3] = EPX_NAN; s_t[jj * 3 + 1] = EPX_NAN; s_t[jj * 3 + 2] = EPX_NAN; }
+                }
                 continue;
             }
             const double *row = p.meth + (int64_t)pi * p.ld;
@@ -363,6 +474,22 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
                 }
                 y[e] = v;
                 labs |= (unsigned long long)lab << (2 * e);
+            }
+            /* the probe's ascending order, EPW consecutive positions per lane (as k_probe_rank_w wrote it) */
+            unsigned short o[EPW];
+            if (EPW >= 8) {
+#pragma unroll
+                for (int c = 0; c < EPW / 8; c++) {
+                    uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                    if (lane * EPW + c * 8 < p.ldo) q = __ldg(reinterpret_cast<const uint4 *>(ord + lane * EPW + c * 8));
+                    o[c * 8 + 0] = (unsigned short)q.x; o[c * 8 + 1] = (unsigned short)(q.x >> 16);
+                    o[c * 8 + 2] = (unsigned short)q.y; o[c * 8 + 3] = (unsigned short)(q.y >> 16);
+                    o[c * 8 + 4] = (unsigned short)q.z; o[c * 8 + 5] = (unsigned short)(q.z >> 16);
+                    o[c * 8 + 6] = (unsigned short)q.w; o[c * 8 + 7] = (unsigned short)(q.w >> 16);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPW; e++) o[e] = lane * EPW + e < n ? __ldg(ord + lane * EPW + e) : (unsigned short)0xffffu;
             }
             s_all = warp_sum(s_all);
             double mg0 = 0, mg1 = 0, mg2 = 0;
@@ -394,22 +521,18 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
             if (__all_sync(FULL, same)) syy = 0.0; /* constant row: sd is exactly 0 in R -> NA */
             __syncwarp(); /* s_row complete */
 
-            /* ---- sorted walk: lane owns EPL consecutive positions of the probe's ascending order ---- */
-            unsigned short o[EPL];
+            /* ---- sorted walk ---- */
             unsigned long long wl = 0; /* labels along the walk, 2 bits each */
             unsigned cnt = 0;          /* 3 x 10-bit label counts */
             bool anytie = false;
 #pragma unroll
-            for (int e = 0; e < EPL; e++) {
-                const int k = lane * EPL + e;
-                unsigned short v = 0;
+            for (int e = 0; e < EPW; e++) {
+                const int k = lane * EPW + e;
                 unsigned lab = 3;
                 if (k < n) {
-                    v = ord[k];
-                    lab = s_lab[v & 0x7fffu];
-                    anytie = anytie || (v & 0x8000u);
+                    lab = s_lab[o[e] & 0x7fffu];
+                    anytie = anytie || (o[e] & 0x8000u);
                 }
-                o[e] = v;
                 wl |= (unsigned long long)lab << (2 * e);
                 if (lab < 3) cnt += 1u << (10 * lab);
             }
@@ -423,8 +546,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
             int c0 = excl & 1023, c1 = (excl >> 10) & 1023, c2 = (excl >> 20) & 1023;
             int d01 = 0, d02 = 0, d12 = 0;
 #pragma unroll
-            for (int e = 0; e < EPL; e++) {
-                const int k = lane * EPL + e;
+            for (int e = 0; e < EPW; e++) {
+                const int k = lane * EPW + e;
                 if (k < n) {
                     const unsigned lab = (unsigned)(wl >> (2 * e)) & 3u;
                     const int s = o[e] & 0x7fffu;
@@ -461,13 +584,13 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
                 }
             }
 
-            /* ---- tests ---- */
+            /* ---- tests. Student-t tails (Welch, Pearson) are deferred to the end of the item so that up to
+             * 32 of them run on 32 lanes at once instead of one lane carrying a continued fraction ---- */
             double stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
             int dnum[3] = { -1, -1, -1 };
             unsigned na = 0;
-            /* Pearson (psych::corr.test): r clamped, NA when either sd is 0 */
-            double r = EPX_NAN, tq = EPX_NAN, dfq = EPX_NAN;
-            bool r_ok = (sxx != 0.0 && syy != 0.0 && n >= 3);
+            double r = EPX_NAN;
+            const bool r_ok = (sxx != 0.0 && syy != 0.0 && n >= 3);
             if (r_ok) {
                 r = sxy / (sqrt(sxx) * sqrt(syy));
                 r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
@@ -476,25 +599,18 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
                 const double mg[3] = { mg0, mg1, mg2 };
                 const double vg[3] = { ss0 / (dm - 1.0), ss1 / (dm - 1.0), ss2 / (dm - 1.0) };
                 const int ga[3] = { 0, 0, 1 }, gb[3] = { 1, 2, 2 };
-                bool ok[3];
-                double tt[3], df[3];
+                double df[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    ok[c] = false; tt[c] = EPX_NAN; df[c] = EPX_NAN;
+                    bool ok = false;
                     if (guard[c] == 1)
-                        ok[c] = epx_welch(mg[ga[c]], vg[ga[c]], dm, mg[gb[c]], vg[gb[c]], dm, &tt[c], &df[c]) == 0;
-                    stat[c] = tt[c];
-                    if (!ok[c]) na |= 1u << (EPX_P_UP_MID + c);
+                        ok = epx_welch(mg[ga[c]], vg[ga[c]], dm, mg[gb[c]], vg[gb[c]], dm, &stat[c], &df[c]) == 0;
+                    if (!ok) { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
                 }
-                /* the four Student-t tails of this pair run on four lanes at once */
-                bool mine = false;
-                if (lane < 3) { tq = lane == 0 ? tt[0] : (lane == 1 ? tt[1] : tt[2]); dfq = lane == 0 ? df[0] : (lane == 1 ? df[1] : df[2]);
-                                mine = lane == 0 ? ok[0] : (lane == 1 ? ok[1] : ok[2]); }
-                else if (lane == 3) { tq = (r * sqrt(dn_ - 2.0)) / sqrt(1.0 - r * r); dfq = dn_ - 2.0; mine = r_ok; }
-                double pq = EPX_NAN;
-                if (mine) pq = epx_t_two_sided_p(tq, dfq);
-                pv[0] = __shfl_sync(FULL, pq, 0); pv[1] = __shfl_sync(FULL, pq, 1); pv[2] = __shfl_sync(FULL, pq, 2);
-                tq = __shfl_sync(FULL, pq, 3); /* Pearson p */
+                if (lane < 3) {
+                    s_t[jj * 3 + lane] = lane == 0 ? stat[0] : (lane == 1 ? stat[1] : stat[2]);
+                    s_df[jj * 3 + lane] = lane == 0 ? df[0] : (lane == 1 ? df[1] : df[2]);
+                }
             } else {
                 int ties[3] = { 0, 0, 0 };
                 if (p.exact_ok && __any_sync(FULL, anytie)) {
@@ -526,14 +642,12 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
                         pv[c] = (p.exact_ok && !ties[c]) ? p.lut_exact[dd[c]] : p.lut_asym[dd[c]];
                     } else na |= 1u << (EPX_P_UP_MID + c);
                 }
-                double pq = EPX_NAN;
-                if (lane == 0 && r_ok) pq = epx_pearson_p(r, dn_);
-                tq = __shfl_sync(FULL, pq, 0);
             }
-            const double p_r = tq;
+            if (lane == 0) s_r[jj] = r;
 
-            /* ---- write the 11 columns (R/Functions.R:224-226 order) ---- */
+            /* ---- write the columns (R/Functions.R:224-226 order); deferred p-values come later ---- */
             double out = 0.0;
+            bool wr = lane < PAIR_COLS - 1; /* column 10 (Pearson p) is always deferred */
             switch (lane) {
             case 0: out = medDOWN; break;
             case 1: out = medMID; break;
@@ -541,20 +655,38 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
             case 3: out = medUP - medMID; break;
             case 4: out = medUP - medDOWN; break;
             case 5: out = medMID - medDOWN; break;
-            case 6: out = pv[0]; break;
-            case 7: out = pv[1]; break;
-            case 8: out = pv[2]; break;
+            case 6: out = pv[0]; wr = !TMODE; break;
+            case 7: out = pv[1]; wr = !TMODE; break;
+            case 8: out = pv[2]; wr = !TMODE; break;
             case 9: out = r; break;
-            case 10: out = p_r; break;
             default: break;
             }
-            if (lane < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + lane] = out;
+            if (wr) p.pair[(int64_t)j * PAIR_COLS + lane] = out;
             if (lane < 3) {
                 p.pair_stat[(int64_t)j * 3 + lane] = lane == 0 ? stat[0] : (lane == 1 ? stat[1] : stat[2]);
                 p.pair_dnum[(int64_t)j * 3 + lane] = lane == 0 ? dnum[0] : (lane == 1 ? dnum[1] : dnum[2]);
             }
             if (lane == 0) p.pair_na[j] = (uint16_t)na;
         }
+
+        /* ---- deferred Student-t tails of the whole item, one per lane ---- */
+        __syncwarp();
+        constexpr int PER = TMODE ? 4 : 1;
+        for (int q = lane; q < item.count * PER; q += 32) {
+            const int jj = q / PER, slot = q % PER;
+            double pq = EPX_NAN;
+            int col = EPX_PEARSON_P;
+            if (TMODE && slot < 3) {
+                const double t = s_t[jj * 3 + slot];
+                if (!isnan(t)) pq = epx_t_two_sided_p(t, s_df[jj * 3 + slot]);
+                col = EPX_P_UP_MID + slot;
+            } else {
+                const double rr = s_r[jj];
+                if (!isnan(rr)) pq = epx_pearson_p(rr, dn_);
+            }
+            p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
+        }
+        __syncwarp();
     }
 }
 
@@ -584,30 +716,60 @@ __global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict
 
 static size_t sort_smem(int npad) { return (size_t)npad * 10; }
 
+template <typename F> static cudaError_t allow_max_dynamic_smem(F *func)
+{
+    /* opt in to the full per-CTA shared memory: device limit minus the kernel's static shared memory */
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, (const void *)func);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute((const void *)func, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                optin - (int)fa.sharedSizeBytes);
+}
+
+#define EPX_FOR_PAIR_VARIANTS(X) X(1, 1) X(2, 2) X(4, 4) X(8, 8) X(15, 16) X(16, 16) X(24, 32) X(32, 32)
+#define EPX_FOR_SORT_VARIANTS(X) X(1) X(2) X(4) X(8) X(16) X(32)
+
 cudaError_t kernels_init()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_gene_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_probe_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gene_tests, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-#define EPX_PAIR_ATTR(E)                                                                                           \
-    e = cudaFuncSetAttribute(k_pair_stats<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
-    if (e != cudaSuccess) return e;                                                                                \
-    e = cudaFuncSetAttribute(k_pair_stats<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
-    if (e != cudaSuccess) return e;
-    EPX_PAIR_ATTR(1) EPX_PAIR_ATTR(2) EPX_PAIR_ATTR(4) EPX_PAIR_ATTR(8) EPX_PAIR_ATTR(15) EPX_PAIR_ATTR(16)
-    EPX_PAIR_ATTR(24) EPX_PAIR_ATTR(32)
+    if ((e = allow_max_dynamic_smem(k_gene_sort)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_probe_rank)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_gene_tests)) != cudaSuccess) return e;
+#define EPX_PAIR_ATTR(L, W)                                                                  \
+    if ((e = allow_max_dynamic_smem(k_pair_stats<L, W, true>)) != cudaSuccess) return e;     \
+    if ((e = allow_max_dynamic_smem(k_pair_stats<L, W, false>)) != cudaSuccess) return e;
+    EPX_FOR_PAIR_VARIANTS(EPX_PAIR_ATTR)
 #undef EPX_PAIR_ATTR
     return cudaSuccess;
 }
 
-cudaError_t launch_gene_sort(const GeneParams &p, cudaStream_t st)
+static int sort_eps(int n)
+{
+    int eps = 1;
+    while (32 * eps < n) eps <<= 1;
+    return eps;
+}
+
+cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
 {
     if (p.G <= 0) return cudaSuccess;
-    k_gene_sort<<<p.G, 256, sort_smem(p.npad), st>>>(p);
+    if (p.n > MAX_WARP_SAMPLES) {
+        k_gene_sort<<<p.G, 256, sort_smem(p.npad), st>>>(p);
+        return cudaGetLastError();
+    }
+    int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS;
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    switch (sort_eps(p.n)) {
+#define EPX_CASE(E) case E: k_gene_sort_w<E><<<grid, SORT_WARPS * 32, 0, st>>>(p); break;
+        EPX_FOR_SORT_VARIANTS(EPX_CASE)
+#undef EPX_CASE
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
@@ -624,14 +786,25 @@ cudaError_t launch_gene_tests(const GeneTestParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_probe_rank(const RankParams &p, cudaStream_t st)
+cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st)
 {
     if (p.U <= 0) return cudaSuccess;
-    k_probe_rank<<<(unsigned)p.U, 256, sort_smem(p.npad), st>>>(p);
+    if (p.n > MAX_WARP_SAMPLES) {
+        k_probe_rank<<<(unsigned)p.U, 256, sort_smem(p.npad), st>>>(p);
+        return cudaGetLastError();
+    }
+    int64_t grid = (p.U + SORT_WARPS - 1) / SORT_WARPS;
+    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+    switch (sort_eps(p.n)) {
+#define EPX_CASE(E) case E: k_probe_rank_w<E><<<(unsigned)grid, SORT_WARPS * 32, 0, st>>>(p); break;
+        EPX_FOR_SORT_VARIANTS(EPX_CASE)
+#undef EPX_CASE
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
-template <int EPL>
+template <int EPL, int EPW>
 static cudaError_t launch_pair_epl(const PairParams &p, int sm_count, cudaStream_t st)
 {
     const size_t smem = pair_warp_smem(p.n) * PAIR_WARPS;
@@ -642,8 +815,8 @@ static cudaError_t launch_pair_epl(const PairParams &p, int sm_count, cudaStream
     const int need = (p.n_items + PAIR_WARPS - 1) / PAIR_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if (p.test_t) k_pair_stats<EPL, true><<<grid, PAIR_WARPS * 32, smem, st>>>(p);
-    else k_pair_stats<EPL, false><<<grid, PAIR_WARPS * 32, smem, st>>>(p);
+    if (p.test_t) k_pair_stats<EPL, EPW, true><<<grid, PAIR_WARPS * 32, smem, st>>>(p);
+    else k_pair_stats<EPL, EPW, false><<<grid, PAIR_WARPS * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -651,14 +824,9 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
 {
     if (p.n_items <= 0) return cudaSuccess;
     const int epl = (p.n + 31) / 32;
-    if (epl <= 1) return launch_pair_epl<1>(p, sm_count, st);
-    if (epl <= 2) return launch_pair_epl<2>(p, sm_count, st);
-    if (epl <= 4) return launch_pair_epl<4>(p, sm_count, st);
-    if (epl <= 8) return launch_pair_epl<8>(p, sm_count, st);
-    if (epl <= 15) return launch_pair_epl<15>(p, sm_count, st);
-    if (epl <= 16) return launch_pair_epl<16>(p, sm_count, st);
-    if (epl <= 24) return launch_pair_epl<24>(p, sm_count, st);
-    if (epl <= 32) return launch_pair_epl<32>(p, sm_count, st);
+#define EPX_CASE(L, W) if (epl <= L) return launch_pair_epl<L, W>(p, sm_count, st);
+    EPX_FOR_PAIR_VARIANTS(EPX_CASE)
+#undef EPX_CASE
     return cudaErrorInvalidValue;
 }
 

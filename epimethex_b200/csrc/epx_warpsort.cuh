@@ -1,0 +1,169 @@
+/*
+ * epx_warpsort.cuh — one warp orders one row (n <= 32*EPS values) entirely in registers.
+ *
+ * The row's doubles are mapped to order-preserving 64-bit keys, the bits all keys share are stripped,
+ * and the leading (32 - IDXB) remaining bits ("coarse key") are packed above the sample index into ONE
+ * 32-bit word per element.  A direction-free bitonic network then sorts the words with one VIMNMX per
+ * compare-exchange half: strides below EPS stay inside a thread, larger strides are one SHFL each.
+ * Only rows in which two neighbours of the sorted order share a coarse key (exact ties, or values closer
+ * than ~2^-22 of the row's key range) take the exact path: an odd-even transposition on the full keys,
+ * restricted to those neighbours, which also yields the tie marks.  The result is exact for any input.
+ */
+#pragma once
+#include "epx_device.cuh"
+
+namespace epx {
+
+template <int EPS> struct WarpSort {
+    static constexpr int N = 32 * EPS;
+    static constexpr int IDXB = (EPS == 1 ? 5 : EPS == 2 ? 6 : EPS == 4 ? 7 : EPS == 8 ? 8 : EPS == 16 ? 9 : 10);
+    static constexpr unsigned IDXM = (1u << IDXB) - 1u;
+    static_assert(EPS == 1 || EPS == 2 || EPS == 4 || EPS == 8 || EPS == 16 || EPS == 32, "EPS must be a power of two <= 32");
+
+    /* ascending sort of the 32*EPS words held as v[r] by 32 lanes; on return position k = lane*EPS + r */
+    __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane)
+    {
+#pragma unroll
+        for (int k = 2; k <= N; k <<= 1) {
+            /* mirror step: i <-> i ^ (k-1), the lower index keeps the minimum */
+            if (k <= EPS) {
+#pragma unroll
+                for (int r = 0; r < EPS; r++) {
+                    const int q = r ^ (k - 1);
+                    if (r < q) {
+                        const unsigned a = v[r], b = v[q];
+                        v[r] = min(a, b);
+                        v[q] = max(a, b);
+                    }
+                }
+            } else {
+                const int lm = k / EPS - 1;
+                const bool lower = (lane & (k / EPS / 2)) == 0;
+                unsigned t[EPS];
+#pragma unroll
+                for (int r = 0; r < EPS; r++) t[r] = __shfl_xor_sync(FULL, v[r ^ (EPS - 1)], lm);
+#pragma unroll
+                for (int r = 0; r < EPS; r++) v[r] = lower ? min(v[r], t[r]) : max(v[r], t[r]);
+            }
+            /* half-cleaners: i <-> i ^ j */
+#pragma unroll
+            for (int j = k / 4; j >= 1; j >>= 1) {
+                if (j < EPS) {
+#pragma unroll
+                    for (int r = 0; r < EPS; r++) {
+                        if ((r & j) == 0) {
+                            const unsigned a = v[r], b = v[r | j];
+                            v[r] = min(a, b);
+                            v[r | j] = max(a, b);
+                        }
+                    }
+                } else {
+                    const int lm = j / EPS;
+                    const bool lower = (lane & lm) == 0;
+#pragma unroll
+                    for (int r = 0; r < EPS; r++) {
+                        const unsigned t = __shfl_xor_sync(FULL, v[r], lm);
+                        v[r] = lower ? min(v[r], t) : max(v[r], t);
+                    }
+                }
+            }
+        }
+    }
+
+    /*
+     * Orders one row. (khi[e], klo[e]) = the full 64-bit key (key_hi/key_lo below) of the element with sample
+     * index lane + 32*e (any value for indices >= n). Ascending by (key, index). Returns in out[r] the sample
+     * index at sorted position lane*EPS + r, with bit 15 set when the NEXT position holds an equal key (tie
+     * mark); positions >= n hold 0xffff. s_ord: N uint16 of per-warp shared scratch. fullkey(idx) must return
+     * the 64-bit key of a sample (only called on the exact path).
+     */
+    template <typename KeyOf>
+    __device__ __forceinline__ static void order(const unsigned (&khi)[EPS], const unsigned (&klo)[EPS], const int n,
+                                                 const int lane, unsigned short *s_ord, KeyOf fullkey,
+                                                 unsigned short (&out)[EPS])
+    {
+        /* bits shared by all keys: OR of (key ^ key0) tells where they start to differ */
+        const unsigned h0 = __shfl_sync(FULL, khi[0], 0), l0 = __shfl_sync(FULL, klo[0], 0);
+        unsigned dhi = 0, dlo = 0;
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            if (lane + 32 * e < n) {
+                dhi |= khi[e] ^ h0;
+                dlo |= klo[e] ^ l0;
+            }
+        }
+        dhi = __reduce_or_sync(FULL, dhi);
+        dlo = __reduce_or_sync(FULL, dlo);
+        const int lz = dhi ? __clz(dhi) : 32 + (dlo ? __clz(dlo) : 32); /* 64: all keys equal */
+        unsigned v[EPS];
+        if (lz < 32) {
+#pragma unroll
+            for (int e = 0; e < EPS; e++) {
+                const int s = lane + 32 * e;
+                v[e] = s < n ? ((__funnelshift_l(klo[e], khi[e], lz) & ~IDXM) | (unsigned)s) : 0xffffffffu;
+            }
+        } else {
+            const int sh = lz - 32; /* 0..32 */
+#pragma unroll
+            for (int e = 0; e < EPS; e++) {
+                const int s = lane + 32 * e;
+                const unsigned w = sh < 32 ? (klo[e] << sh) : 0u;
+                v[e] = s < n ? ((w & ~IDXM) | (unsigned)s) : 0xffffffffu;
+            }
+        }
+        sort(v, lane);
+
+        /* do two neighbours share a coarse key? */
+        bool eq = false;
+#pragma unroll
+        for (int r = 0; r + 1 < EPS; r++) eq = eq || (((v[r] ^ v[r + 1]) & ~IDXM) == 0 && lane * EPS + r + 1 < n);
+        {
+            const unsigned nx = __shfl_down_sync(FULL, v[0], 1);
+            eq = eq || (lane < 31 && ((v[EPS - 1] ^ nx) & ~IDXM) == 0 && (lane + 1) * EPS < n);
+        }
+        if (!__any_sync(FULL, eq)) {
+#pragma unroll
+            for (int r = 0; r < EPS; r++) out[r] = (lane * EPS + r < n) ? (unsigned short)(v[r] & IDXM) : (unsigned short)0xffffu;
+            return;
+        }
+
+        /* exact path: odd-even transposition on full keys, restricted to neighbours with equal coarse keys
+         * (elements with different coarse keys are already in their final relative order) */
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < EPS; r++) s_ord[lane * EPS + r] = (unsigned short)(v[r] & IDXM);
+        __syncwarp();
+        /* same[k]: positions k and k+1 share a coarse key (a property of the position pair, invariant under
+         * swaps inside a run). One bit per owned pair; a lane owns pairs k = 2*(lane + 32*q) + parity. */
+        for (;;) {
+            int swapped = 0;
+#pragma unroll
+            for (int parity = 0; parity < 2; parity++) {
+                for (int k = 2 * lane + parity; k + 1 < n; k += 64) {
+                    const unsigned short ia = s_ord[k], ib = s_ord[k + 1];
+                    const unsigned long long ka = fullkey(ia), kb = fullkey(ib);
+                    if (ka > kb || (ka == kb && ia > ib)) {
+                        /* only possible inside a run of equal coarse keys */
+                        s_ord[k] = ib; s_ord[k + 1] = ia;
+                        swapped = 1;
+                    }
+                }
+                __syncwarp();
+            }
+            if (!__any_sync(FULL, swapped)) break;
+        }
+#pragma unroll
+        for (int r = 0; r < EPS; r++) {
+            const int k = lane * EPS + r;
+            unsigned short o = 0xffffu;
+            if (k < n) {
+                o = s_ord[k];
+                if (k + 1 < n && fullkey(o) == fullkey(s_ord[k + 1])) o |= 0x8000u;
+            }
+            out[r] = o;
+        }
+        __syncwarp();
+    }
+};
+
+} // namespace epx
