@@ -355,7 +355,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     EPX_CUDA(s->perm.reserve((size_t)(G * n)));
     EPX_CUDA(s->lab8.reserve((size_t)(G * s->ldl)));
     EPX_CUDA(s->xc.reserve((size_t)(G * s->ldx)));
-    EPX_CUDA(s->gene_aux.reserve((size_t)(G * 2)));
+    EPX_CUDA(s->gene_aux.reserve((size_t)(G * 4)));
     EPX_CUDA(s->nuniq.reserve((size_t)G));
     EPX_CUDA(s->ord.reserve((size_t)(s->U * s->ldo)));
     EPX_CUDA(s->gene.reserve((size_t)(G * GENE_COLS)));
@@ -389,6 +389,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items;
     pp.n = n; pp.m = m; pp.test_t = opt.test_meth_t;
     pp.exact_ok = ((double)m * (double)m < 10000.0) ? 1 : 0;
+    pp.warp_smem = 0;
     pp.lut_exact = s->lut.p; pp.lut_asym = s->lut.p + (m + 1);
     pp.pair = s->pair.p; pp.pair_na = s->pair_na.p; pp.pair_stat = s->pair_stat.p; pp.pair_dnum = s->pair_dnum.p;
 

@@ -32,7 +32,7 @@ struct GeneParams {
     int64_t ldl;
     double *xc;             /* [G][ldx]  x - mean(x), original sample order */
     int64_t ldx;
-    double *gene_aux;       /* [G][2]    {sum (x-mean)^2, mean} */
+    double *gene_aux;       /* [G][4]    {sxx = sum (x-mean)^2 (0 for a constant gene), mean, sum (x-mean), 1/sqrt(sxx)} */
     int32_t *nuniq;         /* [G] */
 };
 
@@ -78,6 +78,7 @@ struct PairParams {
     int n, m;
     int test_t;
     int exact_ok;           /* m*m < 10000: exact KS p-value unless the two groups hold ties */
+    unsigned warp_smem;     /* k_pair_stats2: bytes of shared memory per warp */
     const double *lut_exact; /* [m+1] p-value for max|cA-cB| = d */
     const double *lut_asym;  /* [m+1] */
     double *pair;           /* [Np][11] */

@@ -14,6 +14,7 @@
 #include "epx_device.cuh"
 #include "epx_internal.h"
 #include "epx_warpsort.cuh"
+#include "epx_pair.cuh"
 
 namespace epx {
 
@@ -56,18 +57,21 @@ __global__ void __launch_bounds__(256) k_gene_sort(GeneParams p)
     if (uniq) atomicAdd(&s_uniq, uniq);
 
     double mean = block_sum(sum, red) / (double)n;
-    double sxx = 0.0;
+    double sxx = 0.0, sxc = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double d = x[i] - mean;
         p.xc[(int64_t)g * p.ldx + i] = d;
         sxx += d * d;
+        sxc += d;
     }
     sxx = block_sum(sxx, red);
+    sxc = block_sum(sxc, red);
     if (threadIdx.x == 0) {
         int u = s_uniq;
         p.nuniq[g] = u;
-        p.gene_aux[2 * (int64_t)g] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
-        p.gene_aux[2 * (int64_t)g + 1] = mean;
+        double *ga = p.gene_aux + 4 * (int64_t)g;
+        ga[0] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
+        ga[1] = mean; ga[2] = sxc; ga[3] = (u == 1 || sxx == 0.0) ? 0.0 : rsqrt(sxx);
     }
 }
 
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_gene_sort_w(GeneParams p)
         }
         ties = __reduce_add_sync(FULL, ties);
         const double mean = warp_sum(sum) / (double)n;
-        double sxx = 0.0;
+        double sxx = 0.0, sxc = 0.0;
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
             const int s = lane + 32 * e;
@@ -336,14 +340,17 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_gene_sort_w(GeneParams p)
                 const double d = xv[e] - mean;
                 p.xc[(int64_t)g * p.ldx + s] = d;
                 sxx += d * d;
+                sxc += d;
             }
         }
         sxx = warp_sum(sxx);
+        sxc = warp_sum(sxc);
         if (lane == 0) {
             const int u = n - ties;
             p.nuniq[g] = u;
-            p.gene_aux[2 * (int64_t)g] = (u == 1) ? 0.0 : sxx;
-            p.gene_aux[2 * (int64_t)g + 1] = mean;
+            double *ga = p.gene_aux + 4 * (int64_t)g;
+            ga[0] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
+            ga[1] = mean; ga[2] = sxc; ga[3] = (u == 1 || sxx == 0.0) ? 0.0 : rsqrt(sxx);
         }
     }
 }
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
             const double *xc = p.xc + (int64_t)cur_gene * p.ldx;
             const uint8_t *lab = p.lab8 + (int64_t)cur_gene * p.ldl;
             for (int s = lane; s < n; s += 32) { s_xc[s] = xc[s]; s_lab[s] = lab[s]; }
-            sxx = p.gene_aux[2 * (int64_t)cur_gene];
+            sxx = p.gene_aux[4 * (int64_t)cur_gene];
             perm_g = p.perm + (int64_t)cur_gene * n;
             if (m >= 2) {
                 pm[0] = perm_g[0]; pm[1] = perm_g[1]; pm[2] = perm_g[m]; pm[3] = perm_g[m + 1];
@@ -732,6 +739,7 @@ template <typename F> static cudaError_t allow_max_dynamic_smem(F *func)
 }
 
 #define EPX_FOR_PAIR_VARIANTS(X) X(1, 1) X(2, 2) X(4, 4) X(8, 8) X(15, 16) X(16, 16) X(24, 32) X(32, 32)
+#define EPX_FOR_PAIR2_VARIANTS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(32)
 #define EPX_FOR_SORT_VARIANTS(X) X(1) X(2) X(4) X(8) X(16) X(32)
 
 cudaError_t kernels_init()
@@ -745,6 +753,11 @@ cudaError_t kernels_init()
     if ((e = allow_max_dynamic_smem(k_pair_stats<L, W, false>)) != cudaSuccess) return e;
     EPX_FOR_PAIR_VARIANTS(EPX_PAIR_ATTR)
 #undef EPX_PAIR_ATTR
+#define EPX_PAIR2_ATTR(E)                                                                 \
+    if ((e = allow_max_dynamic_smem(k_pair_stats2<E, true>)) != cudaSuccess) return e;    \
+    if ((e = allow_max_dynamic_smem(k_pair_stats2<E, false>)) != cudaSuccess) return e;
+    EPX_FOR_PAIR2_VARIANTS(EPX_PAIR2_ATTR)
+#undef EPX_PAIR2_ATTR
     return cudaSuccess;
 }
 
@@ -820,10 +833,37 @@ static cudaError_t launch_pair_epl(const PairParams &p, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
+template <int EPL>
+static cudaError_t launch_pair2(PairParams p, int sm_count, cudaStream_t st)
+{
+    p.warp_smem = (unsigned)pair2_warp_smem(p.n, p.ld, p.ldo, p.test_t != 0);
+    const size_t smem = (size_t)p.warp_smem * PAIR2_WARPS;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    int grid = sm_count * per_sm;
+    const int need = (p.n_items + PAIR2_WARPS - 1) / PAIR2_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (p.test_t) k_pair_stats2<EPL, true><<<grid, PAIR2_WARPS * 32, smem, st>>>(p);
+    else k_pair_stats2<EPL, false><<<grid, PAIR2_WARPS * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st)
 {
     if (p.n_items <= 0) return cudaSuccess;
     const int epl = (p.n + 31) / 32;
+    /* bulk-copy path: rows and order rows must be 16-byte aligned with a 16-byte multiple length */
+    const bool aligned = (((uintptr_t)p.meth) & 15) == 0 && (p.ld & 1) == 0 && (((uintptr_t)p.ord) & 15) == 0 && (p.ldo & 7) == 0;
+    if (aligned && pair2_warp_smem(p.n, p.ld, p.ldo, p.test_t != 0) * PAIR2_WARPS <= 200 * 1024) {
+        switch (epl) {
+#define EPX_CASE2(E) case E: return launch_pair2<E>(p, sm_count, st);
+            EPX_FOR_PAIR2_VARIANTS(EPX_CASE2)
+#undef EPX_CASE2
+        default: break;
+        }
+    }
 #define EPX_CASE(L, W) if (epl <= L) return launch_pair_epl<L, W>(p, sm_count, st);
     EPX_FOR_PAIR_VARIANTS(EPX_CASE)
 #undef EPX_CASE

@@ -38,30 +38,35 @@ EPX_HD double epx_lbeta_half(double a)
     return lgamma(a) + half_log_pi - lgamma(a + 0.5);
 }
 
-/* continued fraction of the incomplete beta function, modified Lentz */
+/* Continued fraction of the incomplete beta function, I_x(a,b) = front/a * betacf(a,b,x), evaluated by the
+ * forward (Wallis) recurrence.  Both partial numerators of one double step share the factor 1/(a+2m), so
+ * a step costs ONE reciprocal; numerator/denominator are renormalised and the convergence test is run only
+ * every 4th step (the recurrences are linear, so scaling both by the same factor changes nothing).
+ * fp64 division is ~15 instructions on the GPU: this form is ~5x cheaper than modified Lentz (6 divisions
+ * per step) at the same accuracy. */
 EPX_HD double epx_betacf(double a, double b, double x)
 {
-    const double tiny = 1e-300, eps = 4e-16;
-    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-    double c = 1.0, d = 1.0 - qab * x / qap;
-    if (fabs(d) < tiny) d = tiny;
-    d = 1.0 / d;
-    double h = d;
-    for (int m = 1; m <= 20000; m++) {
-        double m2 = 2.0 * m;
-        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
-        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d; h *= d * c;
-        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
-        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < eps) break;
+    const double eps = 2e-16;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double am = 1.0, bm = 1.0, az = 1.0, bz = 1.0 - qab * x / qap;
+    double fold = az / bz;
+    for (int m = 1; m <= 40000; m++) {
+        const double em = (double)m, tem = em + em;
+        const double t0 = qam + tem, t1 = a + tem, t2 = qap + tem;
+        const double r = x / (t0 * t1 * t2);
+        const double de = em * (b - em) * t2 * r;            /* d_{2m}   = m(b-m)x / ((a+2m-1)(a+2m)) */
+        const double dodd = -(a + em) * (qab + em) * t0 * r; /* d_{2m+1} = -(a+m)(a+b+m)x / ((a+2m)(a+2m+1)) */
+        const double ap = az + de * am, bp = bz + de * bm;
+        const double app = ap + dodd * az, bpp = bp + dodd * bz;
+        am = ap; bm = bp; az = app; bz = bpp;
+        if ((m & 3) == 0) {
+            const double rb = 1.0 / bz;
+            am *= rb; bm *= rb; az *= rb; bz = 1.0;
+            if (fabs(az - fold) <= eps * fabs(az)) return az;
+            fold = az;
+        }
     }
-    return h;
+    return az / bz;
 }
 
 /* two-sided Student-t p-value 2*pt(-|t|, df) = I_{df/(df+t^2)}(df/2, 1/2), real df > 0 */

@@ -1,0 +1,449 @@
+/*
+ * epx_pair.cuh — k_pair_stats2: the gather/statistics kernel of the path, one warp per (gene, probe) pair.
+ *
+ * Reference code replaced: the per-pair gather dfMethylation[cg, samples-in-the-gene's-order]
+ * (R/EpimethexAnalysis.R:299-302), Analysis (R/Functions.R:85-132: three group medians, beta differences,
+ * three two-sample tests with the calculateTtest guard, R/Functions.R:192-220) and psych::corr.test
+ * (R/EpimethexAnalysis.R:404-417).
+ *
+ * Data movement: each warp streams its pairs through a two-stage ring in shared memory.  One elected lane
+ * issues cp.async.bulk (SASS UBLKCP) for the probe's methylation row (8n bytes) and its ascending order
+ * (2n bytes, from k_probe_rank) of the NEXT pair while all lanes compute the current one; completion is
+ * tracked by an mbarrier per stage (expect_tx / try_wait.parity).  The gene's centred expression vector
+ * lives in registers and its labels in a small shared table, both reused by every probe of the gene.
+ *
+ * Arithmetic per pair: one pass over the row accumulates pivot-shifted moments (sum d, sum d^2, sum xc*d with
+ * d = y - y[0]) for Pearson r (+ per-group sums for Welch); one walk over the probe's sorted order with
+ * running label counts yields the three medians and the three KS numerators at tie-run ends.  Student-t
+ * tails are deferred to the end of the work item so that 32 of them run on 32 lanes at once.
+ */
+#pragma once
+#include "epx_device.cuh"
+#include "epx_internal.h"
+
+namespace epx {
+
+/* ---- mbarrier + bulk-copy (TMA, non-tensor) wrappers ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+/* bounded wait: a lost transaction traps (kernel error) instead of hanging the GPU */
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    for (unsigned spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+
+constexpr int PAIR2_WARPS = 4;
+
+__host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+/* per-warp shared memory: 2 mbarriers | 2 x (row, order) | label table | 16 output slots | 8 median slots |
+ * deferred Pearson r [32] | (t-mode) deferred Welch t and df [32][3] each */
+__host__ __device__ inline size_t pair2_warp_smem(int n, int64_t ld, int64_t ldo, bool tmode)
+{
+    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)n * 4) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
+                   (tmode ? (size_t)ITEM_PAIRS * 6 * 8 : 0));
+}
+
+template <int EPL, bool TMODE>
+__global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_stats2(PairParams p)
+{
+    constexpr int EPW = EPL <= 1 ? 1 : EPL <= 2 ? 2 : EPL <= 4 ? 4 : EPL <= 8 ? 8 : EPL <= 16 ? 16 : 32;
+    static_assert(EPL <= 32, "warp-per-pair kernel handles n <= 1024");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = p.n, m = p.m;
+    const uint32_t rowb = (uint32_t)p.ld * 8u, ordb = (uint32_t)p.ldo * 2u;
+    unsigned char *base = smem + (size_t)warp * p.warp_smem;
+    uint64_t *bar = (uint64_t *)base;
+    unsigned char *buf[2] = { base + 16, base + 16 + rowb + ordb };
+    uint32_t *tab = (uint32_t *)(base + 16 + 2 * (size_t)(rowb + ordb));
+    double *s_out = (double *)((unsigned char *)tab + round16((size_t)n * 4));
+    double *s_med = s_out + 16;
+    double *s_r = s_med + 8;
+    double *s_t = s_r + ITEM_PAIRS;
+    double *s_df = s_t + 3 * ITEM_PAIRS;
+
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+
+    const int gw = blockIdx.x * PAIR2_WARPS + warp, nw = gridDim.x * PAIR2_WARPS;
+    const double dm = (double)m, dn_ = (double)n, inv_n = 1.0 / dn_, inv_m = 1.0 / dm;
+    const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
+    const unsigned T1P = (unsigned)t1 * 0x00100401u, T2P = (unsigned)t2 * 0x00100401u;
+    const bool m_even = (m & 1) == 0;
+
+    int fill = 0, use = 0;
+    uint32_t ph0 = 0, ph1 = 0;
+    auto issue = [&](int pi, int slot) {
+        if (lane == 0) {
+            uint64_t *b = &bar[fill];
+            mbar_expect_tx(b, rowb + ordb);
+            bulk_g2s(buf[fill], p.meth + (int64_t)pi * p.ld, rowb, b);
+            bulk_g2s(buf[fill] + rowb, p.ord + (int64_t)slot * p.ldo, ordb, b);
+        }
+        fill ^= 1;
+    };
+
+    /* gene state */
+    int cur_gene = -1;
+    double xc_r[EPL];
+    unsigned labs = 0; /* t-mode: 2-bit label of this lane's element e (EPL <= 16) */
+    unsigned long long labs64 = 0;
+    double rsx = 0.0, sxc = 0.0;
+    bool x_const = true;
+    int pm[6] = { 0, 0, 0, 0, 0, 0 };
+    const uint16_t *perm_g = nullptr;
+
+    int it = gw;
+    Item item, nitem;
+    item.gene = -1; item.begin = 0; item.count = 0; item.pad = 0;
+    nitem = item;
+    int my_pi = -1, my_slot = -1, nmy_pi = -1, nmy_slot = -1;
+    if (it < p.n_items) {
+        item = p.items[it];
+        if (lane < item.count) { my_pi = p.probe_idx[item.begin + lane]; my_slot = p.pair_slot[item.begin + lane]; }
+        const int fpi = __shfl_sync(FULL, my_pi, 0), fsl = __shfl_sync(FULL, my_slot, 0);
+        if (fpi >= 0) issue(fpi, fsl);
+    }
+
+    for (; it < p.n_items; it += nw) {
+        /* descriptor + probe list of the NEXT item, fetched now so the latency hides behind this item */
+        const bool has_next = it + nw < p.n_items;
+        nmy_pi = -1; nmy_slot = -1;
+        if (has_next) {
+            nitem = p.items[it + nw];
+            if (lane < nitem.count) { nmy_pi = p.probe_idx[nitem.begin + lane]; nmy_slot = p.pair_slot[nitem.begin + lane]; }
+        }
+        if (item.gene != cur_gene) {
+            cur_gene = item.gene;
+            const double *xc = p.xc + (int64_t)cur_gene * p.ldx;
+            const uint8_t *lab = p.lab8 + (int64_t)cur_gene * p.ldl;
+            labs = 0; labs64 = 0;
+            __syncwarp(); /* the previous gene's walk is done with tab */
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+                const int s = lane + 32 * e;
+                unsigned l = 3;
+                double v = 0.0;
+                if (s < n) { v = xc[s]; l = lab[s]; tab[s] = l < 3 ? (1u << (10 * l)) : 0u; }
+                xc_r[e] = v;
+                if (EPL <= 16) labs |= l << (2 * e); else labs64 |= (unsigned long long)l << (2 * e);
+            }
+            const double *ga = p.gene_aux + 4 * (int64_t)cur_gene;
+            x_const = ga[0] == 0.0;
+            sxc = ga[2];
+            rsx = ga[3];
+            perm_g = p.perm + (int64_t)cur_gene * n;
+            if (m >= 2) {
+                pm[0] = perm_g[0]; pm[1] = perm_g[1]; pm[2] = perm_g[m]; pm[3] = perm_g[m + 1];
+                pm[4] = perm_g[2 * m]; pm[5] = perm_g[2 * m + 1];
+            }
+            __syncwarp();
+        }
+
+        for (int jj = 0; jj < item.count; jj++) {
+            const int j = item.begin + jj;
+            const int pi = __shfl_sync(FULL, my_pi, jj);
+            /* prefetch the next pair's row + order into the other stage */
+            int npi, nsl;
+            if (jj + 1 < item.count) { npi = __shfl_sync(FULL, my_pi, jj + 1); nsl = __shfl_sync(FULL, my_slot, jj + 1); }
+            else { npi = __shfl_sync(FULL, nmy_pi, 0); nsl = __shfl_sync(FULL, nmy_slot, 0); }
+            __syncwarp(); /* every lane has finished reading the stage about to be refilled */
+            if (npi >= 0) issue(npi, nsl);
+
+            if (pi < 0) { /* annotated probe without data: all-NA column (R/EpimethexAnalysis.R:375-394) */
+                if (lane < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + lane] = EPX_NAN;
+                if (lane < 3) { p.pair_stat[(int64_t)j * 3 + lane] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + lane] = -1; }
+                if (lane == 0) {
+                    p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+                    s_r[jj] = EPX_NAN;
+                    if (TMODE) { s_t[jj * 3] = EPX_NAN; s_t[jj * 3 + 1] = EPX_NAN; s_t[jj * 3 + 2] = EPX_NAN; }
+                }
+                continue;
+            }
+            const double *row = (const double *)buf[use];
+            const uint32_t *ordw = (const uint32_t *)(buf[use] + rowb);
+            if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; }
+            use ^= 1;
+
+            /* ---- pass A: pivot-shifted moments, sample-major (conflict-free LDS.64) ---- */
+            const double K = row[0];
+            double sd = 0.0, sdd = 0.0, sxd = 0.0;
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPL; e++) {
+                const int s = lane + 32 * e;
+                /* out-of-range lanes of the last element read row[0]: d = 0 contributes nothing */
+                const double d = row[(e < EPL - 1 || s < n) ? s : 0] - K;
+                sd += d;
+                sdd = fma(d, d, sdd);
+                sxd = fma(xc_r[e], d, sxd);
+                if (TMODE) {
+                    const unsigned l = EPL <= 16 ? (labs >> (2 * e)) & 3u : (unsigned)(labs64 >> (2 * e)) & 3u;
+                    if (l == 0) { g0 += d; q0 = fma(d, d, q0); }
+                    else if (l == 1) { g1 += d; q1 = fma(d, d, q1); }
+                    else if (l == 2) { g2 += d; q2 = fma(d, d, q2); }
+                }
+            }
+            sd = warp_sum(sd); sdd = warp_sum(sdd); sxd = warp_sum(sxd);
+            double syy = sdd - sd * sd * inv_n;
+            double sxy = sxd - (sd * inv_n) * sxc;
+            double mg0 = 0, mg1 = 0, mg2 = 0, ss0 = 0, ss1 = 0, ss2 = 0;
+            bool redo = sdd > 0.0 && syy < 1e-7 * sdd;
+            if (TMODE) {
+                g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+                q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2);
+                ss0 = q0 - g0 * g0 * inv_m; ss1 = q1 - g1 * g1 * inv_m; ss2 = q2 - g2 * g2 * inv_m;
+                mg0 = K + g0 * inv_m; mg1 = K + g1 * inv_m; mg2 = K + g2 * inv_m;
+                redo = redo || (q0 > 0.0 && ss0 < 1e-7 * q0) || (q1 > 0.0 && ss1 < 1e-7 * q1) || (q2 > 0.0 && ss2 < 1e-7 * q2);
+            }
+            if (sdd == 0.0) syy = 0.0; /* constant row: sd is exactly 0 in R -> NA */
+            if (redo) {
+                /* the pivot sat far outside a very tight row: redo with centred two-pass sums (rare) */
+                const double mean_all = K + sd * inv_n;
+                double a0 = 0, a1 = 0, b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+                for (int e = 0; e < EPL; e++) {
+                    const int s = lane + 32 * e;
+                    if (s < n) {
+                        const double yv = row[s];
+                        const double d = yv - mean_all;
+                        a0 = fma(d, d, a0);
+                        a1 = fma(xc_r[e], d, a1);
+                        if (TMODE) {
+                            const unsigned l = EPL <= 16 ? (labs >> (2 * e)) & 3u : (unsigned)(labs64 >> (2 * e)) & 3u;
+                            const double dg = yv - (l == 0 ? mg0 : (l == 1 ? mg1 : mg2));
+                            if (l == 0) b0 = fma(dg, dg, b0); else if (l == 1) b1 = fma(dg, dg, b1); else if (l == 2) b2 = fma(dg, dg, b2);
+                        }
+                    }
+                }
+                syy = warp_sum(a0); sxy = warp_sum(a1);
+                if (TMODE) { ss0 = warp_sum(b0); ss1 = warp_sum(b1); ss2 = warp_sum(b2); }
+            }
+
+            /* ---- sorted walk: lane owns EPW consecutive positions of the probe's ascending order ---- */
+            unsigned ow[(EPW + 1) / 2];
+            if (EPW >= 8) {
+#pragma unroll
+                for (int c = 0; c < EPW / 8; c++) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(ordw + lane * (EPW / 2) + c * 4);
+                    ow[c * 4 + 0] = q.x; ow[c * 4 + 1] = q.y; ow[c * 4 + 2] = q.z; ow[c * 4 + 3] = q.w;
+                }
+            } else if (EPW >= 2) {
+#pragma unroll
+                for (int c = 0; c < EPW / 2; c++) ow[c] = ordw[lane * (EPW / 2) + c];
+            } else {
+                const unsigned short h = ((const unsigned short *)ordw)[lane];
+                ow[0] = h | 0xffff0000u;
+            }
+            unsigned inc[EPW];
+            unsigned tot = 0, tiebits = 0;
+            bool mytie = false;
+#pragma unroll
+            for (int e = 0; e < EPW; e++) {
+                const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
+                const bool valid = lane * EPW + e < n;
+                inc[e] = valid ? tab[h & 0x7fffu] : 0u;
+                tiebits |= (valid ? ((h >> 15) & 1u) : 1u) << e; /* invalid positions never evaluate */
+                mytie = mytie || (valid && (h & 0x8000u));
+                tot += inc[e];
+            }
+            unsigned incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            unsigned cnt = incl - tot;
+            int mx01 = 0, mn01 = 0, mx02 = 0, mn02 = 0, mx12 = 0, mn12 = 0;
+#pragma unroll
+            for (int e = 0; e < EPW; e++) {
+                cnt += inc[e];
+                /* median: did the group that just grew reach its middle count? (zero-field test on the
+                 * 10-bit field selected by inc, whose single set bit sits at the field's bit 0) */
+                const unsigned hb = inc[e] << 9;
+                unsigned x = cnt ^ T1P;
+                if (~(x + 0x1ff7fdffu) & hb) { /* every field < 512: adding 511 sets bit 9 iff the field is non-zero */
+                    const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
+                    const int g = (inc[e] >> 10) ? ((inc[e] >> 20) ? 2 : 1) : 0;
+                    const double v = row[h & 0x7fffu];
+                    s_med[g * 2] = v;
+                    if (!m_even) s_med[g * 2 + 1] = v;
+                }
+                if (m_even) {
+                    x = cnt ^ T2P;
+                    if (~(x + 0x1ff7fdffu) & hb) {
+                        const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
+                        const int g = (inc[e] >> 10) ? ((inc[e] >> 20) ? 2 : 1) : 0;
+                        s_med[g * 2 + 1] = row[h & 0x7fffu];
+                    }
+                }
+                if (!TMODE && !((tiebits >> e) & 1u)) { /* end of a tie run: evaluate the ECDF differences */
+                    const int c0 = cnt & 1023, c1 = (cnt >> 10) & 1023, c2 = cnt >> 20;
+                    const int d01 = c0 - c1, d02 = c0 - c2, d12 = c1 - c2;
+                    mx01 = max(mx01, d01); mn01 = min(mn01, d01);
+                    mx02 = max(mx02, d02); mn02 = min(mn02, d02);
+                    mx12 = max(mx12, d12); mn12 = min(mn12, d12);
+                }
+            }
+            int d01 = 0, d02 = 0, d12 = 0;
+            if (!TMODE) {
+                d01 = warp_max_i(max(mx01, -mn01)); d02 = warp_max_i(max(mx02, -mn02)); d12 = warp_max_i(max(mx12, -mn12));
+            }
+            const bool anytie = __any_sync(FULL, mytie);
+            __syncwarp();
+            /* labels: 0 UP, 1 Medium, 2 Down */
+            const double medUP = (s_med[0] + s_med[1]) * 0.5, medMID = (s_med[2] + s_med[3]) * 0.5,
+                         medDOWN = (s_med[4] + s_med[5]) * 0.5;
+
+            /* ---- guard of calculateTtest (R/Functions.R:193): are all rank-paired differences identical? ---- */
+            int guard[3] = { -1, -1, -1 };
+            if (m >= 2) {
+                const double a0 = row[pm[0]], a1 = row[pm[1]], b0 = row[pm[2]], b1 = row[pm[3]], e0 = row[pm[4]],
+                             e1 = row[pm[5]];
+                const double dd[3] = { a0 - b0, a0 - e0, b0 - e0 };
+                const bool eq[3] = { dd[0] == a1 - b1, dd[1] == a1 - e1, dd[2] == b1 - e1 };
+                const int offA[3] = { 0, 0, m }, offB[3] = { m, 2 * m, 2 * m };
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (!eq[c]) { guard[c] = 1; continue; }
+                    int differs = 0; /* rare: walk the whole group */
+                    for (int i = 2 + lane; i < m; i += 32)
+                        if (row[perm_g[offA[c] + i]] - row[perm_g[offB[c] + i]] != dd[c]) differs = 1;
+                    guard[c] = __any_sync(FULL, differs) ? 1 : 0;
+                }
+            }
+
+            /* ---- tests ---- */
+            double stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+            int dnum[3] = { -1, -1, -1 };
+            unsigned na = 0;
+            double r = EPX_NAN;
+            const bool r_ok = (!x_const && syy != 0.0 && n >= 3);
+            if (r_ok) {
+                r = sxy * rsx * rsqrt(syy);
+                r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+            } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
+            if (TMODE) {
+                const double mg[3] = { mg0, mg1, mg2 };
+                const double vg[3] = { ss0 / (dm - 1.0), ss1 / (dm - 1.0), ss2 / (dm - 1.0) };
+                const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
+                double df[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    bool ok = false;
+                    if (guard[c] == 1)
+                        ok = epx_welch(mg[ga_[c]], vg[ga_[c]], dm, mg[gb_[c]], vg[gb_[c]], dm, &stat[c], &df[c]) == 0;
+                    if (!ok) { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
+                }
+                if (lane < 3) {
+                    s_t[jj * 3 + lane] = lane == 0 ? stat[0] : (lane == 1 ? stat[1] : stat[2]);
+                    s_df[jj * 3 + lane] = lane == 0 ? df[0] : (lane == 1 ? df[1] : df[2]);
+                }
+            } else {
+                int ties[3] = { 0, 0, 0 };
+                if (p.exact_ok && anytie) {
+                    /* small groups with tied values: ks.test drops to the asymptotic p-value when the POOLED
+                     * pair of groups holds a tie. Rare and tiny (m < 100): one lane walks the order. */
+                    if (lane == 0) {
+                        const unsigned short *ord16 = (const unsigned short *)ordw;
+                        int r0 = 0, r1 = 0, r2 = 0;
+                        for (int k = 0; k < n; k++) {
+                            const unsigned short v = ord16[k];
+                            const unsigned w = tab[v & 0x7fffu];
+                            r0 += w & 1u; r1 += (w >> 10) & 1u; r2 += (w >> 20) & 1u;
+                            if (!(v & 0x8000u)) {
+                                if (r0 + r1 >= 2) ties[0] = 1;
+                                if (r0 + r2 >= 2) ties[1] = 1;
+                                if (r1 + r2 >= 2) ties[2] = 1;
+                                r0 = r1 = r2 = 0;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) ties[c] = __shfl_sync(FULL, ties[c], 0);
+                }
+                const int dd[3] = { d01, d02, d12 };
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (guard[c] != 0) { /* difference != 0 || is.na(difference) */
+                        dnum[c] = dd[c] * m;
+                        stat[c] = (double)dnum[c] / (dm * dm);
+                        pv[c] = (p.exact_ok && !ties[c]) ? p.lut_exact[dd[c]] : p.lut_asym[dd[c]];
+                    } else na |= 1u << (EPX_P_UP_MID + c);
+                }
+            }
+
+            /* ---- stage the row of results, then one coalesced store per table ---- */
+            s_out[0] = medDOWN; s_out[1] = medMID; s_out[2] = medUP;
+            s_out[3] = medUP - medMID; s_out[4] = medUP - medDOWN; s_out[5] = medMID - medDOWN;
+            s_out[6] = pv[0]; s_out[7] = pv[1]; s_out[8] = pv[2];
+            s_out[9] = r;
+            s_out[11] = stat[0]; s_out[12] = stat[1]; s_out[13] = stat[2];
+            if (lane == 0) s_r[jj] = r;
+            __syncwarp();
+            /* columns 6-8 (t mode) and 10 are written by the deferred pass */
+            if (lane < PAIR_COLS - 1 && !(TMODE && lane >= 6 && lane <= 8)) p.pair[(int64_t)j * PAIR_COLS + lane] = s_out[lane];
+            if (lane >= 11 && lane < 14) p.pair_stat[(int64_t)j * 3 + (lane - 11)] = s_out[lane];
+            if (lane >= 14 && lane < 17) p.pair_dnum[(int64_t)j * 3 + (lane - 14)] = lane == 14 ? dnum[0] : (lane == 15 ? dnum[1] : dnum[2]);
+            if (lane == 17) p.pair_na[j] = (uint16_t)na;
+        }
+
+        /* ---- deferred Student-t tails of the whole item, one per lane ---- */
+        __syncwarp();
+        constexpr int PER = TMODE ? 4 : 1;
+        for (int q = lane; q < item.count * PER; q += 32) {
+            const int jj = q / PER, slot = q % PER;
+            double pq = EPX_NAN;
+            int col = EPX_PEARSON_P;
+            if (TMODE && slot < 3) {
+                const double t = s_t[jj * 3 + slot];
+                if (!isnan(t)) pq = epx_t_two_sided_p(t, s_df[jj * 3 + slot]);
+                col = EPX_P_UP_MID + slot;
+            } else {
+                const double rr = s_r[jj];
+                if (!isnan(rr)) pq = epx_pearson_p(rr, dn_);
+            }
+            p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
+        }
+        __syncwarp();
+        item = nitem;
+        my_pi = nmy_pi; my_slot = nmy_slot;
+    }
+}
+
+} // namespace epx
