@@ -351,7 +351,8 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     const int m = n / 3;
     const int64_t G = s->G, Np = s->Np;
 
-    s->ldl = round_up(n, 16); s->ldx = round_up(n, 2); s->ldo = round_up(n, 16);
+    s->ldl = round_up(n, 16); s->ldx = round_up(n, 2);
+    s->ldo = n <= MAX_WARP_SAMPLES ? 32 * next_pow2((n + 31) / 32) : round_up(n, 16); /* every lane of the walk reads real or pad entries */
     EPX_CUDA(s->perm.reserve((size_t)(G * n)));
     EPX_CUDA(s->lab8.reserve((size_t)(G * s->ldl)));
     EPX_CUDA(s->xc.reserve((size_t)(G * s->ldx)));

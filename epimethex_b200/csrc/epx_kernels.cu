@@ -284,9 +284,12 @@ __global__ void __launch_bounds__(256) k_probe_rank(RankParams p)
     __syncthreads();
     block_bitonic_sort(keys, idx, p.npad);
     uint16_t *o = p.ord + slot * p.ldo;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        unsigned short v = idx[k];
-        if (k + 1 < n && keys[k] == keys[k + 1]) v |= 0x8000u;
+    for (int k = threadIdx.x; k < p.ldo; k += blockDim.x) {
+        unsigned short v = (unsigned short)n; /* pad */
+        if (k < n) {
+            v = idx[k];
+            if (k + 1 < n && keys[k] == keys[k + 1]) v |= 0x8000u;
+        }
         o[k] = v;
     }
 }
@@ -373,6 +376,9 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_probe_rank_w(RankParams p)
         unsigned short out[EPS];
         WarpSort<EPS>::order(khi, klo, n, lane, s_ord[warp], [&](int i) { return key_of(__ldg(row + i)); }, out);
         uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
+#pragma unroll
+        for (int r = 0; r < EPS; r++)
+            if (lane * EPS + r >= n) out[r] = (unsigned short)n; /* pad: the pair kernel's inert table entry */
         if (EPS >= 8) {
 #pragma unroll
             for (int c = 0; c < EPS / 8; c++) {

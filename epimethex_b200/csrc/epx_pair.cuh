@@ -70,7 +70,7 @@ __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t
  * deferred Pearson r [32] | (t-mode) deferred Welch t and df [32][3] each */
 __host__ __device__ inline size_t pair2_warp_smem(int n, int64_t ld, int64_t ldo, bool tmode)
 {
-    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)n * 4) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
+    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 4) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
                    (tmode ? (size_t)ITEM_PAIRS * 6 * 8 : 0));
 }
 
@@ -85,9 +85,10 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     const uint32_t rowb = (uint32_t)p.ld * 8u, ordb = (uint32_t)p.ldo * 2u;
     unsigned char *base = smem + (size_t)warp * p.warp_smem;
     uint64_t *bar = (uint64_t *)base;
-    unsigned char *buf[2] = { base + 16, base + 16 + rowb + ordb };
-    uint32_t *tab = (uint32_t *)(base + 16 + 2 * (size_t)(rowb + ordb));
-    double *s_out = (double *)((unsigned char *)tab + round16((size_t)n * 4));
+    const uint32_t stageb = rowb + ordb;
+    unsigned char *buf0 = base + 16; /* stage s lives at buf0 + s*stageb */
+    uint32_t *tab = (uint32_t *)(base + 16 + 2 * (size_t)stageb);
+    double *s_out = (double *)((unsigned char *)tab + round16((size_t)(n + 1) * 4));
     double *s_med = s_out + 16;
     double *s_r = s_med + 8;
     double *s_t = s_r + ITEM_PAIRS;
@@ -111,9 +112,10 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     auto issue = [&](int pi, int slot) {
         if (lane == 0) {
             uint64_t *b = &bar[fill];
-            mbar_expect_tx(b, rowb + ordb);
-            bulk_g2s(buf[fill], p.meth + (int64_t)pi * p.ld, rowb, b);
-            bulk_g2s(buf[fill] + rowb, p.ord + (int64_t)slot * p.ldo, ordb, b);
+            unsigned char *dst = buf0 + (fill ? stageb : 0u);
+            mbar_expect_tx(b, stageb);
+            bulk_g2s(dst, p.meth + (int64_t)pi * p.ld, rowb, b);
+            bulk_g2s(dst + rowb, p.ord + (int64_t)slot * p.ldo, ordb, b);
         }
         fill ^= 1;
     };
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             const double *xc = p.xc + (int64_t)cur_gene * p.ldx;
             const uint8_t *lab = p.lab8 + (int64_t)cur_gene * p.ldl;
             labs = 0; labs64 = 0;
+            if (lane == 0) tab[n] = 0u;
             __syncwarp(); /* the previous gene's walk is done with tab */
 #pragma unroll
             for (int e = 0; e < EPL; e++) {
@@ -195,8 +198,8 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 }
                 continue;
             }
-            const double *row = (const double *)buf[use];
-            const uint32_t *ordw = (const uint32_t *)(buf[use] + rowb);
+            const double *row = (const double *)(buf0 + (use ? stageb : 0u));
+            const uint32_t *ordw = (const uint32_t *)(buf0 + (use ? stageb : 0u) + rowb);
             if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; }
             use ^= 1;
 
@@ -267,19 +270,16 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
 #pragma unroll
                 for (int c = 0; c < EPW / 2; c++) ow[c] = ordw[lane * (EPW / 2) + c];
             } else {
-                const unsigned short h = ((const unsigned short *)ordw)[lane];
-                ow[0] = h | 0xffff0000u;
+                ow[0] = ((const unsigned short *)ordw)[lane];
             }
+            /* pass 1: label increments (one 10-bit count field per group) of this lane's positions. Pad
+             * positions (k >= n) carry index n and no tie mark (k_probe_rank_w): tab[n] = 0 makes them inert. */
             unsigned inc[EPW];
-            unsigned tot = 0, tiebits = 0;
-            bool mytie = false;
+            unsigned tot = 0;
 #pragma unroll
             for (int e = 0; e < EPW; e++) {
                 const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
-                const bool valid = lane * EPW + e < n;
-                inc[e] = valid ? tab[h & 0x7fffu] : 0u;
-                tiebits |= (valid ? ((h >> 15) & 1u) : 1u) << e; /* invalid positions never evaluate */
-                mytie = mytie || (valid && (h & 0x8000u));
+                inc[e] = tab[h & 0x7fffu];
                 tot += inc[e];
             }
             unsigned incl = tot;
@@ -288,43 +288,47 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 const unsigned t = __shfl_up_sync(FULL, incl, d);
                 if (lane >= d) incl += t;
             }
+            /* pass 2: running counts; medians by an exact zero-field test on the group that just grew (every
+             * field < 512, so adding 511 sets a field's bit 9 iff it is non-zero); KS at tie-run ends */
             unsigned cnt = incl - tot;
+            unsigned hw1 = 0, hw2 = 0; /* per group: 1 + position (inside this lane) of the t1-th / t2-th member */
             int mx01 = 0, mn01 = 0, mx02 = 0, mn02 = 0, mx12 = 0, mn12 = 0;
 #pragma unroll
             for (int e = 0; e < EPW; e++) {
                 cnt += inc[e];
-                /* median: did the group that just grew reach its middle count? (zero-field test on the
-                 * 10-bit field selected by inc, whose single set bit sits at the field's bit 0) */
-                const unsigned hb = inc[e] << 9;
-                unsigned x = cnt ^ T1P;
-                if (~(x + 0x1ff7fdffu) & hb) { /* every field < 512: adding 511 sets bit 9 iff the field is non-zero */
+                hw1 += ((~((cnt ^ T1P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
+                if (m_even) hw2 += ((~((cnt ^ T2P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
+                if (!TMODE) {
                     const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
-                    const int g = (inc[e] >> 10) ? ((inc[e] >> 20) ? 2 : 1) : 0;
-                    const double v = row[h & 0x7fffu];
-                    s_med[g * 2] = v;
-                    if (!m_even) s_med[g * 2 + 1] = v;
-                }
-                if (m_even) {
-                    x = cnt ^ T2P;
-                    if (~(x + 0x1ff7fdffu) & hb) {
-                        const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
-                        const int g = (inc[e] >> 10) ? ((inc[e] >> 20) ? 2 : 1) : 0;
-                        s_med[g * 2 + 1] = row[h & 0x7fffu];
-                    }
-                }
-                if (!TMODE && !((tiebits >> e) & 1u)) { /* end of a tie run: evaluate the ECDF differences */
+                    const int keep = (int)((h >> 15) & 1u) - 1; /* 0 inside a tie run, -1 at its end */
                     const int c0 = cnt & 1023, c1 = (cnt >> 10) & 1023, c2 = cnt >> 20;
-                    const int d01 = c0 - c1, d02 = c0 - c2, d12 = c1 - c2;
+                    const int d01 = (c0 - c1) & keep, d02 = (c0 - c2) & keep, d12 = (c1 - c2) & keep;
                     mx01 = max(mx01, d01); mn01 = min(mn01, d01);
                     mx02 = max(mx02, d02); mn02 = min(mn02, d02);
                     mx12 = max(mx12, d12); mn12 = min(mn12, d12);
+                }
+            }
+            if (!m_even) hw2 = hw1;
+            if (hw1 | hw2) { /* this lane holds a middle element of some group */
+                const unsigned short *ord16 = (const unsigned short *)ordw + lane * EPW;
+#pragma unroll
+                for (int g = 0; g < 3; g++) {
+                    const unsigned a1 = (hw1 >> (10 * g)) & 1023u, a2 = (hw2 >> (10 * g)) & 1023u;
+                    if (a1) s_med[g * 2] = row[ord16[a1 - 1] & 0x7fffu];
+                    if (a2) s_med[g * 2 + 1] = row[ord16[a2 - 1] & 0x7fffu];
                 }
             }
             int d01 = 0, d02 = 0, d12 = 0;
             if (!TMODE) {
                 d01 = warp_max_i(max(mx01, -mn01)); d02 = warp_max_i(max(mx02, -mn02)); d12 = warp_max_i(max(mx12, -mn12));
             }
-            const bool anytie = __any_sync(FULL, mytie);
+            bool anytie = false;
+            if (p.exact_ok) {
+                bool mytie = false;
+#pragma unroll
+                for (int c = 0; c < (EPW + 1) / 2; c++) mytie = mytie || (ow[c] & 0x80008000u);
+                anytie = __any_sync(FULL, mytie);
+            }
             __syncwarp();
             /* labels: 0 UP, 1 Medium, 2 Down */
             const double medUP = (s_med[0] + s_med[1]) * 0.5, medMID = (s_med[2] + s_med[3]) * 0.5,
