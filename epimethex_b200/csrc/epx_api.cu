@@ -76,10 +76,11 @@ struct epx_session {
     /* per-gene and per-probe intermediates */
     DevBuf<uint16_t> perm, ord;
     DevBuf<uint8_t> lab8;
-    DevBuf<double> xc, gene_aux, lut;
+    DevBuf<double> xc, gene_aux, lut, pt_tab;
+    int pt_n = 0;
     DevBuf<int32_t> nuniq, scal; /* scal: counts[3], ref_gene, status */
     int64_t ldl = 0, ldx = 0, ldo = 0;
-    int lut_m = -1;
+    int lut_m = -1, lut_n = -1;
     /* results */
     DevBuf<double> pair, pair_stat, gene;
     DevBuf<uint16_t> pair_na, gene_na;
@@ -170,7 +171,7 @@ void epx_session_destroy(epx_session *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->meth_own.release(); s->expr.release(); s->probe_idx.release(); s->pair_slot.release();
     s->uniq_probe.release(); s->items.release(); s->perm.release(); s->ord.release(); s->lab8.release();
-    s->xc.release(); s->gene_aux.release(); s->lut.release(); s->nuniq.release(); s->scal.release();
+    s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->nuniq.release(); s->scal.release();
     s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
     s->pair_dnum.release(); s->gene_dnum.release();
     for (int i = 0; i < 6; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -311,10 +312,23 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     return EPX_OK;
 }
 
-/* KS p-value lookup for two groups of equal size m: index d = max|cA - cB|, numerator d*m */
-static int build_ks_lut(epx_session *s, int m, cudaStream_t st, char *err, size_t errlen)
+/* Tables that depend on the sample count alone, built once per n on the host with the same epx_math.h code the
+ * kernels use: the KS p-value lookup for two groups of equal size m (index d = max|cA - cB|, numerator d*m)
+ * and the Pearson p-value table of epx_pearson_h. */
+static int build_ks_lut(epx_session *s, int n, int m, cudaStream_t st, char *err, size_t errlen)
 {
-    if (s->lut_m == m) return EPX_OK;
+    if (s->lut_m == m && s->pt_n > 0 && s->lut_n == n) return EPX_OK;
+    {
+        const double df = (double)n - 2.0;
+        const int N = epx_pearson_grid(df > 1.0 ? df : 1.0);
+        std::vector<double> tab((size_t)N + 1);
+        for (int i = 0; i <= N; i++) tab[(size_t)i] = df >= 1.0 ? epx_pearson_h((double)i / (double)N, df) : 0.0;
+        EPX_CUDA(s->pt_tab.reserve(tab.size()));
+        EPX_CUDA(cudaMemcpyAsync(s->pt_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, st));
+        EPX_CUDA(cudaStreamSynchronize(st));
+        s->pt_n = N;
+        s->lut_n = n;
+    }
     std::vector<double> lut((size_t)2 * (m + 1)), u((size_t)m + 2);
     const bool exact_ok = (double)m * (double)m < 10000.0;
     for (int d = 0; d <= m; d++) {
@@ -366,7 +380,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     EPX_CUDA(s->pair_na.reserve((size_t)Np));
     EPX_CUDA(s->pair_stat.reserve((size_t)(Np * 3)));
     EPX_CUDA(s->pair_dnum.reserve((size_t)(Np * 3)));
-    int rc = build_ks_lut(s, m, st, err, errlen);
+    int rc = build_ks_lut(s, n, m, st, err, errlen);
     if (rc) return rc;
 
     GeneParams gp;
@@ -391,6 +405,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     pp.n = n; pp.m = m; pp.test_t = opt.test_meth_t;
     pp.exact_ok = ((double)m * (double)m < 10000.0) ? 1 : 0;
     pp.warp_smem = 0;
+    pp.pt_tab = s->pt_tab.p; pp.pt_n = s->pt_n;
     pp.lut_exact = s->lut.p; pp.lut_asym = s->lut.p + (m + 1);
     pp.pair = s->pair.p; pp.pair_na = s->pair_na.p; pp.pair_stat = s->pair_stat.p; pp.pair_dnum = s->pair_dnum.p;
 
@@ -399,7 +414,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     EPX_CUDA(launch_gene_sort(gp, s->sm_count, st)); s->launches++;
     EPX_CUDA(cudaEventRecord(s->ev[1], st));
     EPX_CUDA(launch_pick_reference(tp, st)); s->launches++;
-    EPX_CUDA(launch_gene_tests(tp, st)); s->launches++;
+    EPX_CUDA(launch_gene_tests(tp, s->sm_count, st)); s->launches++;
     EPX_CUDA(cudaEventRecord(s->ev[2], st));
     if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[3], st));

@@ -79,6 +79,8 @@ struct PairParams {
     int test_t;
     int exact_ok;           /* m*m < 10000: exact KS p-value unless the two groups hold ties */
     unsigned warp_smem;     /* k_pair_stats2: bytes of shared memory per warp */
+    const double *pt_tab;   /* [pt_n + 1] epx_pearson_h on the grid r = i / pt_n (see epx_math.h) */
+    int pt_n;
     const double *lut_exact; /* [m+1] p-value for max|cA-cB| = d */
     const double *lut_asym;  /* [m+1] */
     double *pair;           /* [Np][11] */
@@ -89,7 +91,7 @@ struct PairParams {
 
 cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st);
-cudaError_t launch_gene_tests(const GeneTestParams &p, cudaStream_t st);
+cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st);
 /* dst[p*ld + s0 + j] = src[j*P + p], j < ns : sample-major chunk -> probe-major rows */

@@ -301,7 +301,7 @@ constexpr int SORT_WARPS = 8;
 
 /* k_gene_sort, one warp per gene */
 template <int EPS>
-__global__ void __launch_bounds__(SORT_WARPS * 32) k_gene_sort_w(GeneParams p)
+__global__ void __launch_bounds__(SORT_WARPS * 32, 2) k_gene_sort_w(GeneParams p)
 {
     __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
@@ -309,38 +309,39 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_gene_sort_w(GeneParams p)
     for (int g = blockIdx.x * SORT_WARPS + warp; g < p.G; g += nw) {
         const double *x = p.expr + (int64_t)g * n;
         unsigned khi[EPS], klo[EPS];
-        double xv[EPS];
         double sum = 0.0;
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
             const int s = lane + 32 * e;
-            xv[e] = s < n ? __ldg(x + s) : 0.0;
-            key_halves(xv[e], khi[e], klo[e]);
+            const double v = s < n ? __ldg(x + s) : 0.0;
+            key_halves(v, khi[e], klo[e]);
             khi[e] = ~khi[e]; klo[e] = ~klo[e]; /* descending by value */
-            sum += xv[e];
+            sum += v;
         }
+        const double mean = warp_sum(sum) / (double)n;
         unsigned short out[EPS];
         WarpSort<EPS>::order(khi, klo, n, lane, s_ord[warp], [&](int i) { return ~key_of(__ldg(x + i)); }, out);
         int ties = 0;
+        uint16_t *perm = p.perm + (int64_t)g * n;
+        uint8_t *lab8 = p.lab8 + (int64_t)g * p.ldl;
 #pragma unroll
         for (int r = 0; r < EPS; r++) {
             const int k = lane * EPS + r;
             if (k < n) {
                 const int s = out[r] & 0x7fff;
                 ties += (out[r] >> 15) & 1;
-                p.perm[(int64_t)g * n + k] = (uint16_t)s;
+                perm[k] = (uint16_t)s;
                 const int lab = k / p.m;
-                p.lab8[(int64_t)g * p.ldl + s] = (uint8_t)(lab > 3 ? 3 : lab);
+                lab8[s] = (uint8_t)(lab > 3 ? 3 : lab);
             }
         }
         ties = __reduce_add_sync(FULL, ties);
-        const double mean = warp_sum(sum) / (double)n;
         double sxx = 0.0, sxc = 0.0;
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
             const int s = lane + 32 * e;
             if (s < n) {
-                const double d = xv[e] - mean;
+                const double d = __ldg(x + s) - mean; /* L1 hit: the row was just read */
                 p.xc[(int64_t)g * p.ldx + s] = d;
                 sxx += d * d;
                 sxc += d;
@@ -355,6 +356,157 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_gene_sort_w(GeneParams p)
             ga[0] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
             ga[1] = mean; ga[2] = sxc; ga[3] = (u == 1 || sxx == 0.0) ? 0.0 : rsqrt(sxx);
         }
+    }
+}
+
+/* k_gene_tests, one warp per gene: the column in the gene's descending order is staged in shared memory */
+constexpr int GT_WARPS = 4;
+
+template <int EPS>
+__global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (*p.status != ST_OK) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
+    double *xs = (double *)smem + (size_t)warp * (32 * EPS + 2); /* sorted descending; later psmirnov scratch */
+    const int nUP = p.counts[0], nM = p.counts[1], nD = p.counts[2];
+    const int off[3] = { 0, nUP, nUP + nM };
+    const int len[3] = { nUP, nM, nD };
+    const int ca[3] = { 0, 0, 1 }, cb[3] = { 1, 2, 2 };
+    const int nw = gridDim.x * GT_WARPS;
+    for (int g = blockIdx.x * GT_WARPS + warp; g < p.G; g += nw) {
+        const double *x = p.expr + (int64_t)g * n;
+        const uint16_t *perm = p.perm + (int64_t)g * n;
+        __syncwarp();
+        /* position k = lane + 32*e of the sorted column; group by position block */
+        double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int k = lane + 32 * e;
+            if (k < n) {
+                const double v = __ldg(x + perm[k]);
+                xs[k] = v;
+                if (k < off[1]) s0 += v; else if (k < off[2]) s1 += v; else s2 += v;
+            }
+        }
+        __syncwarp();
+        double mean[3], var[3];
+        mean[0] = len[0] > 0 ? warp_sum(s0) / (double)len[0] : EPX_NAN;
+        mean[1] = len[1] > 0 ? warp_sum(s1) / (double)len[1] : EPX_NAN;
+        mean[2] = len[2] > 0 ? warp_sum(s2) / (double)len[2] : EPX_NAN;
+        double q0 = 0, q1 = 0, q2 = 0;
+        int dmaxv[3] = { 0, 0, 0 }, tiev[3] = { 0, 0, 0 }, differs[3] = { 0, 0, 0 };
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int k = lane + 32 * e;
+            if (k < n) {
+                const double v = xs[k];
+                if (k < off[1]) { const double d = v - mean[0]; q0 += d * d; }
+                else if (k < off[2]) { const double d = v - mean[1]; q1 += d * d; }
+                else { const double d = v - mean[2]; q2 += d * d; }
+                if (!p.test_t) {
+                    /* KS: the column is globally sorted, so counts are closed forms of the position; evaluate at
+                     * the end of every tie run of the whole column (extra thresholds cannot exceed the sup) */
+                    const bool run_end = (k == n - 1) || (v != xs[k + 1]);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const int la = len[ca[c]], lb = len[cb[c]], a0 = off[ca[c]], b0 = off[cb[c]];
+                        if (run_end) {
+                            const int cA = min(max(k + 1 - a0, 0), la), cB = min(max(k + 1 - b0, 0), lb);
+                            const int z = cA * lb - cB * la;
+                            dmaxv[c] = max(dmaxv[c], z < 0 ? -z : z);
+                        } else {
+                            const bool in_i = (k >= a0 && k < a0 + la) || (k >= b0 && k < b0 + lb);
+                            const bool in_n = (k + 1 >= a0 && k + 1 < a0 + la) || (k + 1 >= b0 && k + 1 < b0 + lb);
+                            if (in_i && in_n) tiev[c] = 1;
+                        }
+                    }
+                }
+            }
+        }
+        var[0] = len[0] > 1 ? warp_sum(q0) / (double)(len[0] - 1) : EPX_NAN;
+        var[1] = len[1] > 1 ? warp_sum(q1) / (double)(len[1] - 1) : EPX_NAN;
+        var[2] = len[2] > 1 ? warp_sum(q2) / (double)(len[2] - 1) : EPX_NAN;
+        /* guard, R/Functions.R:193: sd(mapply('-', a, b)) with recycling of the shorter argument */
+        int guard[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int la = len[ca[c]], lb = len[cb[c]];
+            const double *A = xs + off[ca[c]], *B = xs + off[cb[c]];
+            const int L = la > lb ? la : lb;
+            if (la > 0 && lb > 0 && L >= 2) {
+                const double d0 = A[0] - B[0];
+                for (int i = 1 + lane; i < L; i += 32)
+                    if (A[i % la] - B[i % lb] != d0) differs[c] = 1;
+            }
+            guard[c] = (la == 0 || lb == 0 || L < 2) ? -1 : (__any_sync(FULL, differs[c]) ? 1 : 0);
+        }
+        if (!p.test_t) {
+            /* UP vs D with the whole M block tied to both neighbours */
+            if (lane == 0 && nM > 0 && nUP > 0 && nD > 0 && xs[off[1] - 1] == xs[off[2]]) tiev[1] = 1;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { dmaxv[c] = warp_max_i(dmaxv[c]); tiev[c] = __any_sync(FULL, tiev[c]); }
+        }
+        __syncwarp(); /* all reads of xs are done: lane 0 may reuse it as psmirnov scratch */
+        if (lane == 0) {
+            double *o = p.gene + (int64_t)g * GENE_COLS;
+            const double q33 = quantile7(x, perm, n, 0.33), q66 = quantile7(x, perm, n, 0.66),
+                         q99 = quantile7(x, perm, n, 0.99);
+            /* calcFC reads the last three rows = perc99/perc66/perc33 (reference quirk) */
+            const double fu = p.fc_from_means ? mean[0] : q99, fm = p.fc_from_means ? mean[1] : q66,
+                         fd = p.fc_from_means ? mean[2] : q33;
+            if (p.data_linear) { o[0] = epx_linear_fc(fu, fm); o[1] = epx_linear_fc(fu, fd); o[2] = epx_linear_fc(fm, fd); }
+            else { o[0] = epx_log_fc(fu, fm); o[1] = epx_log_fc(fu, fd); o[2] = epx_log_fc(fm, fd); }
+            o[9] = q33; o[10] = q66; o[11] = q99;
+            o[12] = mean[2]; o[13] = mean[1]; o[14] = mean[0];
+        }
+        /* the three p-values on three lanes at once */
+        uint16_t na = 0;
+        if (lane < 3) {
+            const int c = lane;
+            const int la = len[ca[c]], lb = len[cb[c]];
+            double stat = EPX_NAN, pv = EPX_NAN;
+            int dn = -1;
+            bool ok = false;
+            const int gd = c == 0 ? guard[0] : (c == 1 ? guard[1] : guard[2]);
+            if (p.test_t) {
+                if (gd == 1) {
+                    double t, df;
+                    const double ma = c == 2 ? mean[1] : mean[0], va = c == 2 ? var[1] : var[0];
+                    const double mb = c == 0 ? mean[1] : mean[2], vb = c == 0 ? var[1] : var[2];
+                    if (epx_welch(ma, va, (double)la, mb, vb, (double)lb, &t, &df) == 0) {
+                        stat = t; pv = epx_t_two_sided_p(t, df); ok = true;
+                    }
+                }
+            } else if (gd != 0 && la > 0 && lb > 0) {
+                dn = c == 0 ? dmaxv[0] : (c == 1 ? dmaxv[1] : dmaxv[2]);
+                const int tv = c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]);
+                stat = (double)dn / ((double)la * (double)lb);
+                ok = true;
+                if ((double)la * (double)lb < 10000.0 && !tv) pv = EPX_NAN; /* exact: done serially below */
+                else pv = epx_ks_p_asym((double)dn, (double)la, (double)lb);
+            }
+            double *o = p.gene + (int64_t)g * GENE_COLS;
+            const bool exact_pending = !p.test_t && ok && (double)la * (double)lb < 10000.0 &&
+                                       !(c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]));
+            if (!exact_pending) o[3 + c] = pv; /* otherwise lane 0 writes it below */
+            o[6 + c] = stat;
+            p.gene_dnum[(int64_t)g * 3 + c] = dn;
+            if (!ok) na = (uint16_t)((1u << (3 + c)) | (1u << (6 + c)));
+        }
+        if (!p.test_t) {
+            /* exact KS p-values (small groups, no pooled ties): psmirnov2x needs the shared scratch -> serial */
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int la = len[ca[c]], lb = len[cb[c]];
+                if (guard[c] != 0 && la > 0 && lb > 0 && (double)la * (double)lb < 10000.0 && !tiev[c]) {
+                    if (lane == 0) p.gene[(int64_t)g * GENE_COLS + 3 + c] = epx_ks_p_exact((double)dmaxv[c], la, lb, xs);
+                }
+            }
+        }
+        na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 1);
+        na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 2);
+        if (lane == 0) p.gene_na[g] = na;
     }
 }
 
@@ -695,7 +847,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
                 col = EPX_P_UP_MID + slot;
             } else {
                 const double rr = s_r[jj];
-                if (!isnan(rr)) pq = epx_pearson_p(rr, dn_);
+                if (!isnan(rr)) pq = epx_pearson_p_tab(rr, p.pt_tab, p.pt_n, dn_ - 2.0);
             }
             p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
         }
@@ -798,10 +950,23 @@ cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_gene_tests(const GeneTestParams &p, cudaStream_t st)
+cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_t st)
 {
     if (p.G <= 0) return cudaSuccess;
-    k_gene_tests<<<p.G, 128, (size_t)(p.n + 2) * sizeof(double), st>>>(p);
+    if (p.n > MAX_WARP_SAMPLES) {
+        k_gene_tests<<<p.G, 128, (size_t)(p.n + 2) * sizeof(double), st>>>(p);
+        return cudaGetLastError();
+    }
+    int grid = (p.G + GT_WARPS - 1) / GT_WARPS;
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    const int eps = sort_eps(p.n);
+    const size_t smem = (size_t)GT_WARPS * (32 * eps + 2) * sizeof(double);
+    switch (eps) {
+#define EPX_CASE(E) case E: k_gene_tests_w<E><<<grid, GT_WARPS * 32, smem, st>>>(p); break;
+        EPX_FOR_SORT_VARIANTS(EPX_CASE)
+#undef EPX_CASE
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

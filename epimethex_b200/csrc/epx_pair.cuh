@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 col = EPX_P_UP_MID + slot;
             } else {
                 const double rr = s_r[jj];
-                if (!isnan(rr)) pq = epx_pearson_p(rr, dn_);
+                if (!isnan(rr)) pq = epx_pearson_p_tab(rr, p.pt_tab, p.pt_n, dn_ - 2.0);
             }
             p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
         }

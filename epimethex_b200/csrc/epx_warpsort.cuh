@@ -113,22 +113,53 @@ template <int EPS> struct WarpSort {
         }
         sort(v, lane);
 
-        /* do two neighbours share a coarse key? */
-        bool eq = false;
+        /* Neighbours that share a coarse key are either exact ties (common: rounded or clipped data) or
+         * values closer than the coarse resolution (rare). Fetch the full keys of just those positions:
+         * equal -> tie mark (the packed index already orders ties by sample index); inverted -> the rare
+         * transposition pass below. */
+        bool eqn[EPS];
+        bool anyeq = false;
+        const unsigned nx0 = __shfl_down_sync(FULL, v[0], 1);
 #pragma unroll
-        for (int r = 0; r + 1 < EPS; r++) eq = eq || (((v[r] ^ v[r + 1]) & ~IDXM) == 0 && lane * EPS + r + 1 < n);
-        {
-            const unsigned nx = __shfl_down_sync(FULL, v[0], 1);
-            eq = eq || (lane < 31 && ((v[EPS - 1] ^ nx) & ~IDXM) == 0 && (lane + 1) * EPS < n);
+        for (int r = 0; r < EPS; r++) {
+            const unsigned nxt = r + 1 < EPS ? v[r + 1] : nx0;
+            eqn[r] = ((v[r] ^ nxt) & ~IDXM) == 0 && lane * EPS + r + 1 < n && (r + 1 < EPS || lane < 31);
+            anyeq = anyeq || eqn[r];
         }
-        if (!__any_sync(FULL, eq)) {
+        if (!__any_sync(FULL, anyeq)) {
 #pragma unroll
             for (int r = 0; r < EPS; r++) out[r] = (lane * EPS + r < n) ? (unsigned short)(v[r] & IDXM) : (unsigned short)0xffffu;
             return;
         }
+        {
+            const bool prev_eq = __shfl_up_sync(FULL, (int)eqn[EPS - 1], 1) != 0 && lane > 0;
+            unsigned long long fk[EPS];
+#pragma unroll
+            for (int r = 0; r < EPS; r++) {
+                const bool involved = eqn[r] || (r > 0 ? eqn[r - 1] : prev_eq);
+                fk[r] = involved ? fullkey((int)(v[r] & IDXM)) : 0ull;
+            }
+            const unsigned long long fnx = __shfl_down_sync(FULL, fk[0], 1);
+            bool bad = false;
+            unsigned ties = 0;
+#pragma unroll
+            for (int r = 0; r < EPS; r++) {
+                const unsigned long long fn = r + 1 < EPS ? fk[r + 1] : fnx;
+                if (eqn[r]) {
+                    bad = bad || fk[r] > fn;
+                    ties |= (fk[r] == fn ? 1u : 0u) << r;
+                }
+            }
+            if (!__any_sync(FULL, bad)) {
+#pragma unroll
+                for (int r = 0; r < EPS; r++)
+                    out[r] = (lane * EPS + r < n) ? (unsigned short)((v[r] & IDXM) | (((ties >> r) & 1u) << 15)) : (unsigned short)0xffffu;
+                return;
+            }
+        }
 
-        /* exact path: odd-even transposition on full keys, restricted to neighbours with equal coarse keys
-         * (elements with different coarse keys are already in their final relative order) */
+        /* rare: two values closer than the coarse resolution came out inverted. Odd-even transposition on the
+         * full keys (only neighbours inside a run of equal coarse keys can ever swap). */
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < EPS; r++) s_ord[lane * EPS + r] = (unsigned short)(v[r] & IDXM);

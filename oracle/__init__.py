@@ -144,6 +144,12 @@ def median(x):
     return lib().epo_median(p, a.size)
 
 
+def pearson_p_from_r(r, n):
+    """two-sided p of a correlation r over n samples, as psych::corr.test computes it"""
+    t = r * np.sqrt(n - 2.0) / np.sqrt(1.0 - r * r)
+    return 2.0 * pt(-abs(t), n - 2.0)
+
+
 def pearson(x, y):
     x, px = _d(x); y, py = _d(y)
     r, p = C.c_double(), C.c_double()

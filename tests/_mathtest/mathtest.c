@@ -11,3 +11,6 @@ double mt_pearson_p(double r, double n) { return epx_pearson_p(r, n); }
 double mt_lbeta_half(double a) { return epx_lbeta_half(a); }
 int mt_welch(double mx, double vx, double nx, double my, double vy, double ny, double *t, double *df)
 { return epx_welch(mx, vx, nx, my, vy, ny, t, df); }
+double mt_pearson_h(double r, double df) { return epx_pearson_h(r, df); }
+int mt_pearson_grid(double df) { return epx_pearson_grid(df); }
+double mt_pearson_p_tab(double r, const double *h, int N, double df) { return epx_pearson_p_tab(r, h, N, df); }

@@ -78,3 +78,28 @@ def test_welch_and_fc_match_oracle(mt):
         got, want = mt.mt_linear_fc(a, b), oracle.linear_fc(a, b)
         assert (np.isnan(got) and np.isnan(want)) or got == want
         assert mt.mt_log_fc(a, b) == oracle.log_fc(a, b)
+
+
+def test_pearson_p_table_vs_mpmath(mt):
+    """the pair kernel interpolates a per-n table of h(r) = log p - (df/2) log(1-r^2); check the whole scheme"""
+    mt.mt_pearson_h.restype = C.c_double; mt.mt_pearson_h.argtypes = [C.c_double] * 2
+    mt.mt_pearson_grid.restype = C.c_int; mt.mt_pearson_grid.argtypes = [C.c_double]
+    mt.mt_pearson_p_tab.restype = C.c_double
+    mt.mt_pearson_p_tab.argtypes = [C.c_double, C.POINTER(C.c_double), C.c_int, C.c_double]
+    mp.mp.dps = 30
+    rng = np.random.default_rng(5)
+    for n in (6, 30, 99, 473, 1000, 9000):
+        df = n - 2.0
+        N = mt.mt_pearson_grid(df)
+        tab = np.array([mt.mt_pearson_h(i / N, df) for i in range(N + 1)])
+        ptr = tab.ctypes.data_as(C.POINTER(C.c_double))
+        rs = np.concatenate([rng.random(120), rng.random(120) * 8 / np.sqrt(df) * rng.random(120), 1 - rng.random(20) * 2 / N,
+                             [0.0, 1e-12, 0.5]])
+        for r in rs[rs < 1]:
+            want = mp.betainc(mp.mpf(df) / 2, mp.mpf(1) / 2, 0, 1 - mp.mpf(float(r)) ** 2, regularized=True)
+            got = mt.mt_pearson_p_tab(-float(r), ptr, N, df)
+            err = abs(got - want)
+            assert err <= 1e-11 or err <= 1e-9 * want, (n, r, got, want)
+            if want > 1e-300:
+                assert abs(got - oracle.pearson_p_from_r(float(r), n)) <= 1e-10 + 1e-8 * want
+        assert mt.mt_pearson_p_tab(1.0, ptr, N, df) == 0.0 and mt.mt_pearson_p_tab(-1.0, ptr, N, df) == 0.0
