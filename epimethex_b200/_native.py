@@ -248,8 +248,20 @@ class Session:
         _check(lib().epx_session_result_device_ptr(self._h, which, C.byref(p), C.byref(n), b, len(b)), b)
         return p.value, n.value
 
-    def _alloc_result(self, full: bool):
+    def _alloc_result(self, full: bool, pinned: bool = False):
         Np, G, n = self.n_pairs, self.n_genes, self.n_samples
+        if pinned and not full:
+            key = (Np, G)
+            if getattr(self, "_pinned_key", None) != key:
+                self._pinned = (pinned_empty((Np, PAIR_COLS)), pinned_empty((Np,), np.uint16),
+                                pinned_empty((G, GENE_COLS)), pinned_empty((G,), np.uint16))
+                self._pinned_key = key
+            pr, pn, gn, gm = self._pinned
+            res = Result(pair=pr, pair_na=pn, pair_stat=np.empty((0, 3)), ks_dnum=np.empty((0, 3), np.int32), gene=gn,
+                         gene_na=gm, gene_ks_dnum=np.empty((0, 3), np.int32), perm=np.empty((0, n), np.uint16))
+            r = _Result()
+            r.pair, r.pair_na, r.gene, r.gene_na = pr.ctypes.data, pn.ctypes.data, gn.ctypes.data, gm.ctypes.data
+            return res, r
         res = Result(pair=np.empty((Np, PAIR_COLS)), pair_na=np.zeros(Np, np.uint16),
                      pair_stat=np.empty((Np, 3)) if full else np.empty((0, 3)),
                      ks_dnum=np.empty((Np, 3), np.int32) if full else np.empty((0, 3), np.int32),
@@ -272,14 +284,17 @@ class Session:
         res.timing = self.timing()
         return res
 
-    def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True) -> Result:
-        """One blocking epx_analyze call with host buffers (what the R `.Call` shim does)."""
+    def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True,
+                pinned_results: bool = False) -> Result:
+        """One blocking epx_analyze call with host buffers (what the R `.Call` shim does).
+        pinned_results: write the result tables into page-locked buffers owned by the session (reused by the next
+        call: copy what you keep)."""
         expr = np.ascontiguousarray(expr, np.float64)
         row_ptr = np.ascontiguousarray(row_ptr, np.int64)
         probe_idx = np.ascontiguousarray(probe_idx, np.int32)
         self.n_genes, self.n_samples = expr.shape
         self.n_pairs = int(row_ptr[-1])
-        res, r = self._alloc_result(full)
+        res, r = self._alloc_result(full, pinned_results)
         opt = options if options is not None else make_options()
         b = _errbuf()
         _check(lib().epx_analyze(self._h, expr.ctypes.data, expr.shape[0], expr.shape[1], row_ptr.ctypes.data,

@@ -197,8 +197,28 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
     EPX_CUDA(cudaSetDevice(s->device));
     const int64_t dld = round_up(n_samples, 4); /* 32-byte aligned rows */
     EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
-    EPX_CUDA(cudaMemcpy2DAsync(s->meth_own.p, (size_t)dld * 8, rows, (size_t)ld * 8, (size_t)n_samples * 8,
-                               (size_t)n_probes, cudaMemcpyHostToDevice, s->stream));
+    if (ld == dld) {
+        EPX_CUDA(cudaMemcpyAsync(s->meth_own.p, rows, (size_t)(n_probes * dld) * 8, cudaMemcpyHostToDevice, s->stream));
+    } else if (ld == n_samples) {
+        /* contiguous host matrix: flat copies at full PCIe rate into a staging buffer, rows re-spaced on the
+         * device (a 2-D copy with 3.7 KB rows runs at a fraction of the link rate) */
+        const int64_t chunk_rows = (64ll << 20) / (n_samples * 8) > 0 ? (64ll << 20) / (n_samples * 8) : 1;
+        DevBuf<double> stage;
+        EPX_CUDA(stage.reserve((size_t)(chunk_rows * n_samples)));
+        for (int64_t r0 = 0; r0 < n_probes; r0 += chunk_rows) {
+            const int64_t nr = (n_probes - r0) < chunk_rows ? (n_probes - r0) : chunk_rows;
+            cudaError_t e = cudaMemcpyAsync(stage.p, rows + r0 * n_samples, (size_t)(nr * n_samples) * 8,
+                                            cudaMemcpyHostToDevice, s->stream);
+            if (e == cudaSuccess) e = launch_respace_rows(stage.p, s->meth_own.p + r0 * dld, nr, n_samples, dld, s->stream);
+            if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); stage.release(); return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e)); }
+        }
+        cudaError_t e = cudaStreamSynchronize(s->stream);
+        stage.release();
+        if (e != cudaSuccess) return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e));
+    } else {
+        EPX_CUDA(cudaMemcpy2DAsync(s->meth_own.p, (size_t)dld * 8, rows, (size_t)ld * 8, (size_t)n_samples * 8,
+                                   (size_t)n_probes, cudaMemcpyHostToDevice, s->stream));
+    }
     EPX_CUDA(cudaStreamSynchronize(s->stream));
     s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
     s->G_index = -1; /* slots refer to the previous matrix */

@@ -97,6 +97,8 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
 /* dst[p*ld + s0 + j] = src[j*P + p], j < ns : sample-major chunk -> probe-major rows */
 cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,
                                   cudaStream_t st);
+/* dst[r*ld + j] = src[r*n + j]: re-space contiguous rows to the padded leading dimension */
+cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, cudaStream_t st);
 /* one-time kernel attribute setup (dynamic shared memory opt-in) */
 cudaError_t kernels_init();
 

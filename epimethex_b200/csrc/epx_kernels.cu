@@ -877,7 +877,25 @@ __global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict
     }
 }
 
+__global__ void __launch_bounds__(256) k_respace_rows(const double *__restrict__ src, double *__restrict__ dst, int64_t rows,
+                                                      int n, int64_t ld)
+{
+    const int64_t total = rows * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n;
+        dst[r * ld + (i - r * n)] = src[i];
+    }
+}
+
 /* ============================================================ launchers */
+
+cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, cudaStream_t st)
+{
+    if (rows <= 0) return cudaSuccess;
+    k_respace_rows<<<148 * 8, 256, 0, st>>>(src, dst, rows, (int)n, ld);
+    return cudaGetLastError();
+}
+
 
 static size_t sort_smem(int npad) { return (size_t)npad * 10; }
 
