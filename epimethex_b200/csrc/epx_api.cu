@@ -70,7 +70,7 @@ struct epx_session {
     DevBuf<double> expr;
     int64_t G = 0, n = 0;
     /* index */
-    DevBuf<int32_t> probe_idx, pair_slot, uniq_probe;
+    DevBuf<int32_t> probe_idx, pair_slot, uniq_probe, pair_gene;
     DevBuf<Item> items;
     int64_t Np = 0, U = 0, n_items = 0, G_index = -1;
     /* per-gene and per-probe intermediates */
@@ -170,7 +170,7 @@ void epx_session_destroy(epx_session *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->meth_own.release(); s->expr.release(); s->probe_idx.release(); s->pair_slot.release();
-    s->uniq_probe.release(); s->items.release(); s->perm.release(); s->ord.release(); s->lab8.release();
+    s->uniq_probe.release(); s->items.release(); s->pair_gene.release(); s->perm.release(); s->ord.release(); s->lab8.release();
     s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->nuniq.release(); s->scal.release();
     s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
     s->pair_dnum.release(); s->gene_dnum.release();
@@ -296,13 +296,14 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     if (Np > 0 && !probe_idx) return fail(err, errlen, EPX_EINVAL, "probe_idx is NULL");
     EPX_CUDA(cudaSetDevice(s->device));
 
-    std::vector<int32_t> slot_of((size_t)s->P, -1), pair_slot((size_t)Np), uniq;
+    std::vector<int32_t> slot_of((size_t)s->P, -1), pair_slot((size_t)Np), pair_gene((size_t)Np), uniq;
     std::vector<Item> items;
     for (int64_t g = 0; g < n_genes; g++) {
         const int64_t b = row_ptr[g], e = row_ptr[g + 1];
         if (e < b || e > Np) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)g);
         for (int64_t j = b; j < e; j++) {
             const int32_t pi = probe_idx[j];
+            pair_gene[(size_t)j] = (int32_t)g;
             if (pi >= s->P) return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d >= n_probes %lld", (long long)j, pi, (long long)s->P);
             if (pi < 0) { pair_slot[(size_t)j] = -1; continue; }
             if (slot_of[(size_t)pi] < 0) { slot_of[(size_t)pi] = (int32_t)uniq.size(); uniq.push_back(pi); }
@@ -317,11 +318,13 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     }
     EPX_CUDA(s->probe_idx.reserve((size_t)Np));
     EPX_CUDA(s->pair_slot.reserve((size_t)Np));
+    EPX_CUDA(s->pair_gene.reserve((size_t)Np));
     EPX_CUDA(s->uniq_probe.reserve(uniq.size()));
     EPX_CUDA(s->items.reserve(items.size()));
     if (Np) {
         EPX_CUDA(cudaMemcpyAsync(s->probe_idx.p, probe_idx, (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
         EPX_CUDA(cudaMemcpyAsync(s->pair_slot.p, pair_slot.data(), (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(cudaMemcpyAsync(s->pair_gene.p, pair_gene.data(), (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
     }
     if (!uniq.empty())
         EPX_CUDA(cudaMemcpyAsync(s->uniq_probe.p, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, s->stream));
@@ -378,8 +381,6 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     const int n = (int)s->n;
     if (opt.strict_n3 && n % 3 != 0)
         return fail(err, errlen, EPX_ESTRICT, "arguments imply differing number of rows: %d, %d", n, 3 * (n / 3));
-    if (n > MAX_WARP_SAMPLES && s->Np > 0)
-        return fail(err, errlen, EPX_EINVAL, "n_samples %d > %d is not supported by the pair kernel yet", n, MAX_WARP_SAMPLES);
     EPX_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     const int m = n / 3;
@@ -421,7 +422,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;
     pp.pair_slot = s->pair_slot.p; pp.xc = s->xc.p; pp.ldx = s->ldx; pp.lab8 = s->lab8.p; pp.ldl = s->ldl;
-    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items;
+    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items; pp.pair_gene = s->pair_gene.p; pp.n_pairs = (int)Np;
     pp.n = n; pp.m = m; pp.test_t = opt.test_meth_t;
     pp.exact_ok = ((double)m * (double)m < 10000.0) ? 1 : 0;
     pp.warp_smem = 0;

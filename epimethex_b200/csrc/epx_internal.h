@@ -75,6 +75,8 @@ struct PairParams {
     const double *gene_aux;
     const Item *items;
     int n_items;
+    const int32_t *pair_gene; /* [Np] gene of each pair (CTA-per-pair kernel) */
+    int n_pairs;
     int n, m;
     int test_t;
     int exact_ok;           /* m*m < 10000: exact KS p-value unless the two groups hold ties */

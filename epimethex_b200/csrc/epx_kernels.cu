@@ -855,6 +855,191 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
     }
 }
 
+
+/* ============================================================ k_pair_stats_cta (CTA per pair, n > 1024) */
+
+/* Same statistics as k_pair_stats2 for rows too long for one warp (pan-cancer: n = 9,000). One CTA per pair:
+ * row, labels and the probe's order are staged in shared memory (11n bytes); the gene's centred expression is
+ * read from global memory (it stays in L2 across the gene's probes). Correct and general (n <= 16,384), not yet
+ * tuned: no bulk-copy pipeline, one pair per CTA at a time. */
+constexpr int BIG_THREADS = 256;
+
+__device__ __forceinline__ int block_max_i(int v, int *red)
+{
+    v = warp_max_i(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = max(r, red[w]);
+    return r;
+}
+
+template <bool TMODE>
+__global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = p.n, m = p.m, tid = threadIdx.x, nt = blockDim.x;
+    double *s_row = (double *)smem;
+    unsigned short *s_ord = (unsigned short *)(s_row + ((n + 1) & ~1));
+    uint8_t *s_lab = (uint8_t *)(s_ord + ((n + 7) & ~7));
+    __shared__ double red[40];
+    __shared__ int ired[8];
+    __shared__ int s_cnt[BIG_THREADS][3];
+    __shared__ double s_med[8];
+    __shared__ int s_flag;
+    const double dm = (double)m, dn_ = (double)n;
+    const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
+
+    for (int j = blockIdx.x; j < p.n_pairs; j += gridDim.x) {
+        const int pi = p.probe_idx[j];
+        const int gene = p.pair_gene[j];
+        if (pi < 0) {
+            if (tid < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + tid] = EPX_NAN;
+            if (tid < 3) { p.pair_stat[(int64_t)j * 3 + tid] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + tid] = -1; }
+            if (tid == 0) p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+            continue;
+        }
+        const double *row = p.meth + (int64_t)pi * p.ld;
+        const uint16_t *ord = p.ord + (int64_t)p.pair_slot[j] * p.ldo;
+        const double *xc = p.xc + (int64_t)gene * p.ldx;
+        const uint8_t *lab = p.lab8 + (int64_t)gene * p.ldl;
+        const uint16_t *perm_g = p.perm + (int64_t)gene * n;
+        const double *ga = p.gene_aux + 4 * (int64_t)gene;
+        __syncthreads(); /* previous pair is done with the staging buffers */
+        const double K = __ldg(row);
+        double sd = 0, sdd = 0, sxd = 0, g0 = 0, g1 = 0, g2 = 0, q0 = 0, q1 = 0, q2 = 0;
+        for (int s = tid; s < n; s += nt) {
+            const double v = __ldg(row + s);
+            const unsigned l = lab[s];
+            s_row[s] = v; s_lab[s] = (uint8_t)l; s_ord[s] = ord[s];
+            const double d = v - K;
+            sd += d; sdd = fma(d, d, sdd); sxd = fma(xc[s], d, sxd);
+            if (TMODE) {
+                if (l == 0) { g0 += d; q0 = fma(d, d, q0); } else if (l == 1) { g1 += d; q1 = fma(d, d, q1); }
+                else if (l == 2) { g2 += d; q2 = fma(d, d, q2); }
+            }
+        }
+        if (tid == 0) s_flag = 0;
+        sd = block_sum(sd, red); sdd = block_sum(sdd, red); sxd = block_sum(sxd, red);
+        double syy = sdd - sd * sd / dn_, sxy = sxd - (sd / dn_) * ga[2];
+        double mg0 = 0, mg1 = 0, mg2 = 0, ss0 = 0, ss1 = 0, ss2 = 0;
+        bool redo = sdd > 0.0 && syy < 1e-7 * sdd;
+        if (TMODE) {
+            g0 = block_sum(g0, red); g1 = block_sum(g1, red); g2 = block_sum(g2, red);
+            q0 = block_sum(q0, red); q1 = block_sum(q1, red); q2 = block_sum(q2, red);
+            ss0 = q0 - g0 * g0 / dm; ss1 = q1 - g1 * g1 / dm; ss2 = q2 - g2 * g2 / dm;
+            mg0 = K + g0 / dm; mg1 = K + g1 / dm; mg2 = K + g2 / dm;
+            redo = redo || (q0 > 0.0 && ss0 < 1e-7 * q0) || (q1 > 0.0 && ss1 < 1e-7 * q1) || (q2 > 0.0 && ss2 < 1e-7 * q2);
+        }
+        if (sdd == 0.0) syy = 0.0;
+        if (redo) {
+            const double mean_all = K + sd / dn_;
+            double a0 = 0, a1 = 0, b0 = 0, b1 = 0, b2 = 0;
+            for (int s = tid; s < n; s += nt) {
+                const double yv = s_row[s], d = yv - mean_all;
+                a0 = fma(d, d, a0); a1 = fma(xc[s], d, a1);
+                if (TMODE) {
+                    const unsigned l = s_lab[s];
+                    const double dg = yv - (l == 0 ? mg0 : (l == 1 ? mg1 : mg2));
+                    if (l == 0) b0 = fma(dg, dg, b0); else if (l == 1) b1 = fma(dg, dg, b1); else if (l == 2) b2 = fma(dg, dg, b2);
+                }
+            }
+            syy = block_sum(a0, red); sxy = block_sum(a1, red);
+            if (TMODE) { ss0 = block_sum(b0, red); ss1 = block_sum(b1, red); ss2 = block_sum(b2, red); }
+        }
+        __syncthreads();
+
+        /* sorted walk: thread t owns positions [t*chunk, (t+1)*chunk) */
+        const int chunk = (n + nt - 1) / nt;
+        const int k0 = min(tid * chunk, n), k1 = min(k0 + chunk, n);
+        int c0 = 0, c1 = 0, c2 = 0;
+        for (int k = k0; k < k1; k++) {
+            const unsigned l = s_lab[s_ord[k] & 0x7fffu];
+            c0 += l == 0; c1 += l == 1; c2 += l == 2;
+        }
+        s_cnt[tid][0] = c0; s_cnt[tid][1] = c1; s_cnt[tid][2] = c2;
+        __syncthreads();
+        if (tid < 3) { /* exclusive scan of one label's per-thread totals */
+            int run = 0;
+            for (int t = 0; t < nt; t++) { const int v = s_cnt[t][tid]; s_cnt[t][tid] = run; run += v; }
+        }
+        __syncthreads();
+        c0 = s_cnt[tid][0]; c1 = s_cnt[tid][1]; c2 = s_cnt[tid][2];
+        int d01 = 0, d02 = 0, d12 = 0;
+        for (int k = k0; k < k1; k++) {
+            const unsigned short o = s_ord[k];
+            const int s = o & 0x7fffu;
+            const unsigned l = s_lab[s];
+            int c = -1;
+            if (l == 0) c = ++c0; else if (l == 1) c = ++c1; else if (l == 2) c = ++c2;
+            if (c == t1) s_med[l * 2] = s_row[s];
+            if (c == t2) s_med[l * 2 + 1] = s_row[s];
+            if (!TMODE && !(o & 0x8000u)) {
+                d01 = max(d01, abs(c0 - c1)); d02 = max(d02, abs(c0 - c2)); d12 = max(d12, abs(c1 - c2));
+            }
+        }
+        if (!TMODE) { d01 = block_max_i(d01, ired); d02 = block_max_i(d02, ired); d12 = block_max_i(d12, ired); }
+        __syncthreads();
+        const double medUP = (s_med[0] + s_med[1]) * 0.5, medMID = (s_med[2] + s_med[3]) * 0.5,
+                     medDOWN = (s_med[4] + s_med[5]) * 0.5;
+
+        /* guard (R/Functions.R:193) */
+        int guard[3] = { -1, -1, -1 };
+        if (m >= 2) {
+            const int offA[3] = { 0, 0, m }, offB[3] = { m, 2 * m, 2 * m };
+            for (int c = 0; c < 3; c++) {
+                const double dd = s_row[perm_g[offA[c]]] - s_row[perm_g[offB[c]]];
+                int differs = 0;
+                if (s_row[perm_g[offA[c] + 1]] - s_row[perm_g[offB[c] + 1]] != dd) differs = 1;
+                else
+                    for (int i = 2 + tid; i < m; i += nt)
+                        if (s_row[perm_g[offA[c] + i]] - s_row[perm_g[offB[c] + i]] != dd) differs = 1;
+                guard[c] = __syncthreads_or(differs) ? 1 : 0;
+            }
+        }
+
+        if (tid == 0) {
+            double out[PAIR_COLS], stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+            int dnum[3] = { -1, -1, -1 };
+            unsigned na = 0;
+            double r = EPX_NAN, pr = EPX_NAN;
+            if (ga[0] != 0.0 && syy != 0.0 && n >= 3) {
+                r = sxy * ga[3] * rsqrt(syy);
+                r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+                pr = epx_pearson_p_tab(r, p.pt_tab, p.pt_n, dn_ - 2.0);
+            } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
+            if (TMODE) {
+                const double mg[3] = { mg0, mg1, mg2 };
+                const double vg[3] = { ss0 / (dm - 1.0), ss1 / (dm - 1.0), ss2 / (dm - 1.0) };
+                const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
+                for (int c = 0; c < 3; c++) {
+                    double df = EPX_NAN;
+                    bool ok = false;
+                    if (guard[c] == 1) ok = epx_welch(mg[ga_[c]], vg[ga_[c]], dm, mg[gb_[c]], vg[gb_[c]], dm, &stat[c], &df) == 0;
+                    if (ok) pv[c] = epx_t_two_sided_p(stat[c], df);
+                    else { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
+                }
+            } else {
+                const int dd[3] = { d01, d02, d12 };
+                for (int c = 0; c < 3; c++) {
+                    if (guard[c] != 0) {
+                        dnum[c] = dd[c] * m;
+                        stat[c] = (double)dnum[c] / (dm * dm);
+                        pv[c] = p.lut_asym[dd[c]]; /* m > 341: n.x*n.y >= 10000, always asymptotic */
+                    } else na |= 1u << (EPX_P_UP_MID + c);
+                }
+            }
+            out[0] = medDOWN; out[1] = medMID; out[2] = medUP;
+            out[3] = medUP - medMID; out[4] = medUP - medDOWN; out[5] = medMID - medDOWN;
+            out[6] = pv[0]; out[7] = pv[1]; out[8] = pv[2]; out[9] = r; out[10] = pr;
+            for (int c = 0; c < PAIR_COLS; c++) p.pair[(int64_t)j * PAIR_COLS + c] = out[c];
+            for (int c = 0; c < 3; c++) { p.pair_stat[(int64_t)j * 3 + c] = stat[c]; p.pair_dnum[(int64_t)j * 3 + c] = dnum[c]; }
+            p.pair_na[j] = (uint16_t)na;
+        }
+    }
+}
+
 /* ============================================================ transpose (sample-major upload) */
 
 __global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict__ src, double *__restrict__ dst,
@@ -929,6 +1114,8 @@ cudaError_t kernels_init()
     if ((e = allow_max_dynamic_smem(k_pair_stats<L, W, false>)) != cudaSuccess) return e;
     EPX_FOR_PAIR_VARIANTS(EPX_PAIR_ATTR)
 #undef EPX_PAIR_ATTR
+    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<true>)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<false>)) != cudaSuccess) return e;
 #define EPX_PAIR2_ATTR(E)                                                                 \
     if ((e = allow_max_dynamic_smem(k_pair_stats2<E, true>)) != cudaSuccess) return e;    \
     if ((e = allow_max_dynamic_smem(k_pair_stats2<E, false>)) != cudaSuccess) return e;
@@ -1042,6 +1229,17 @@ static cudaError_t launch_pair2(PairParams p, int sm_count, cudaStream_t st)
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st)
 {
     if (p.n_items <= 0) return cudaSuccess;
+    if (p.n > MAX_WARP_SAMPLES) {
+        const size_t smem = (size_t)((p.n + 1) & ~1) * 8 + (size_t)((p.n + 7) & ~7) * 2 + (size_t)((p.n + 15) & ~15);
+        int per_sm = (int)((220 * 1024) / (smem + 8192));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        int grid = sm_count * per_sm;
+        if (grid > p.n_pairs) grid = p.n_pairs;
+        if (p.test_t) k_pair_stats_cta<true><<<grid, BIG_THREADS, smem, st>>>(p);
+        else k_pair_stats_cta<false><<<grid, BIG_THREADS, smem, st>>>(p);
+        return cudaGetLastError();
+    }
     const int epl = (p.n + 31) / 32;
     /* bulk-copy path: rows and order rows must be 16-byte aligned with a 16-byte multiple length */
     const bool aligned = (((uintptr_t)p.meth) & 15) == 0 && (p.ld & 1) == 0 && (((uintptr_t)p.ord) & 15) == 0 && (p.ldo & 7) == 0;

@@ -20,53 +20,65 @@ template <int EPS> struct WarpSort {
     static constexpr unsigned IDXM = (1u << IDXB) - 1u;
     static_assert(EPS == 1 || EPS == 2 || EPS == 4 || EPS == 8 || EPS == 16 || EPS == 32, "EPS must be a power of two <= 32");
 
-    /* ascending sort of the 32*EPS words held as v[r] by 32 lanes; on return position k = lane*EPS + r */
+    /* in-thread half-cleaners with strides EPS/2 .. 1 (static register indices) */
+    __device__ __forceinline__ static void thread_tail(unsigned (&v)[EPS], int from)
+    {
+#pragma unroll
+        for (int j = EPS / 2; j >= 1; j >>= 1) {
+            if (j <= from) {
+#pragma unroll
+                for (int r = 0; r < EPS; r++) {
+                    if ((r & j) == 0) {
+                        const unsigned a = v[r], b = v[r | j];
+                        v[r] = min(a, b);
+                        v[r | j] = max(a, b);
+                    }
+                }
+            }
+        }
+    }
+
+    /* ascending sort of the 32*EPS words held as v[r] by 32 lanes; on return position k = lane*EPS + r.
+     * Direction-free bitonic network: every merge phase starts with a mirror step (i <-> i ^ (k-1), the lower
+     * index keeps the minimum) followed by half-cleaners (i <-> i ^ j). Phases that fit a thread are unrolled;
+     * the five cross-lane phases run as a loop (same code for every phase: the body stays in the instruction
+     * cache) with the lane masks as run-time values. */
     __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane)
     {
 #pragma unroll
-        for (int k = 2; k <= N; k <<= 1) {
-            /* mirror step: i <-> i ^ (k-1), the lower index keeps the minimum */
-            if (k <= EPS) {
+        for (int k = 2; k <= EPS; k <<= 1) {
 #pragma unroll
-                for (int r = 0; r < EPS; r++) {
-                    const int q = r ^ (k - 1);
-                    if (r < q) {
-                        const unsigned a = v[r], b = v[q];
-                        v[r] = min(a, b);
-                        v[q] = max(a, b);
-                    }
+            for (int r = 0; r < EPS; r++) {
+                const int q = r ^ (k - 1);
+                if (r < q) {
+                    const unsigned a = v[r], b = v[q];
+                    v[r] = min(a, b);
+                    v[q] = max(a, b);
                 }
-            } else {
-                const int lm = k / EPS - 1;
-                const bool lower = (lane & (k / EPS / 2)) == 0;
+            }
+            thread_tail(v, k / 4);
+        }
+#pragma unroll 1
+        for (int q = 1; q < 32; q <<= 1) { /* phase k = 2*EPS*q */
+            {
+                const int lm = 2 * q - 1;
+                const bool lower = (lane & q) == 0;
                 unsigned t[EPS];
 #pragma unroll
                 for (int r = 0; r < EPS; r++) t[r] = __shfl_xor_sync(FULL, v[r ^ (EPS - 1)], lm);
 #pragma unroll
                 for (int r = 0; r < EPS; r++) v[r] = lower ? min(v[r], t[r]) : max(v[r], t[r]);
             }
-            /* half-cleaners: i <-> i ^ j */
+#pragma unroll 1
+            for (int j = q >> 1; j >= 1; j >>= 1) {
+                const bool lower = (lane & j) == 0;
 #pragma unroll
-            for (int j = k / 4; j >= 1; j >>= 1) {
-                if (j < EPS) {
-#pragma unroll
-                    for (int r = 0; r < EPS; r++) {
-                        if ((r & j) == 0) {
-                            const unsigned a = v[r], b = v[r | j];
-                            v[r] = min(a, b);
-                            v[r | j] = max(a, b);
-                        }
-                    }
-                } else {
-                    const int lm = j / EPS;
-                    const bool lower = (lane & lm) == 0;
-#pragma unroll
-                    for (int r = 0; r < EPS; r++) {
-                        const unsigned t = __shfl_xor_sync(FULL, v[r], lm);
-                        v[r] = lower ? min(v[r], t) : max(v[r], t);
-                    }
+                for (int r = 0; r < EPS; r++) {
+                    const unsigned t = __shfl_xor_sync(FULL, v[r], j);
+                    v[r] = lower ? min(v[r], t) : max(v[r], t);
                 }
             }
+            thread_tail(v, EPS / 2);
         }
     }
 

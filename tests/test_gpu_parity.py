@@ -104,6 +104,15 @@ def test_missing_probes_constant_rows_and_guard(sess):
         assert (ref.pair_na == 0x7FF).any() and ((ref.pair_na & 0x1C0) != 0).any()
 
 
+@pytest.mark.parametrize("n,decimals", [(1500, None), (2001, 3)])
+def test_long_rows_use_the_cta_per_pair_kernel(sess, n, decimals):
+    """n > 1024 (towards the 9,000-sample pan-cancer shape): CTA-per-row sort + CTA-per-pair statistics"""
+    x, y, idx = _synth(40, n, 600, decimals=decimals)
+    for te, tm in ((True, False), (False, True)):
+        got = run_gpu(sess, x, y, idx, te=te, tm=tm)
+        assert_parity(got, run_oracle(x, y, idx, te=te, tm=tm), f"n={n} te={te} tm={tm}")
+
+
 def test_log_fold_change_and_means_variant(sess):
     x, y, idx = _synth(200, 60, 1000, ties=False)
     for linear, fcm in ((False, False), (True, True), (False, True)):
