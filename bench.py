@@ -104,10 +104,11 @@ def make_workload(name: str, rank: int):
     ann = synth.annotation(P, dims["n_genes"])
     idx = synth.probe_index(ann, g0, g1)
     expr = synth.expression(g1 - g0, n, g0=g0, seed=synth.SEED_EXPR + rank)
+    pinned = True
     try:
         meth = _native.pinned_empty((P, n))
     except Exception:
-        meth = np.empty((P, n))
+        meth, pinned = np.empty((P, n)), False
     threads = max(1, min(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     # only rows some pair references are ever read; generate those, zero the rest
     used = np.unique(idx.probe_idx[idx.probe_idx >= 0])
@@ -121,7 +122,7 @@ def make_workload(name: str, rank: int):
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(work, chunks))
     return dict(w=w, n=n, P=P, G=g1 - g0, ann=ann, idx=idx, expr=np.ascontiguousarray(expr), meth=meth,
-                gen_s=time.time() - t0, n_unique=int(used.size))
+                gen_s=time.time() - t0, n_unique=int(used.size), pinned=pinned)
 
 
 def cpu_baseline(wl, target_s: float, threads: int):
@@ -258,10 +259,12 @@ def main():
     ms = ev0.elapsed_time(ev1)
     # per-kernel CUDA-event times of the last step (events recorded by the library on the same stream)
     tim = sess.timing()
-    # average the per-kernel times over a few more steps, each read back right after it ran
+    # per-kernel times: a few more steps with the kernels serialised (no overlap of the gene kernels with the probe
+    # ranking), each read back right after it ran
     reps = min(5, args.steps)
+    opts_serial = _native.make_options(True, wl["w"]["te"], wl["w"]["tm"], serialize=True)
     for _ in range(reps):
-        sess.run(opts, stream)
+        sess.run(opts_serial, stream)
         t = sess.timing()
         for k in kern:
             kern[k] += t[k] / reps
@@ -320,7 +323,8 @@ def main():
                          "frac": kernels[dom[:-3]]["frac"], "traffic": None, "peak_source": peak_src},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_t, "steps": len(e2e_ms)},
+                    "ms_per_step": e2e_t, "steps": len(e2e_ms), "pinned_host_buffers": bool(wl["pinned"]),
+                    "h2d_gbs": round(h2d / (e2e_t * 1e-3) / 1e9, 1) if e2e_t == e2e_t else None},
             "gpu_launches": int(tim["kernel_launches"]) * args.steps,
             "clocks": clocks,
             "setup_s": round(wl["gen_s"], 1),

@@ -128,11 +128,12 @@ def device_info(device: int = 0) -> dict:
 
 
 def make_options(data_linear=True, test_expr_t=True, test_meth_t=False, fc_from_means=False,
-                 strict_n3=False) -> Options:
+                 strict_n3=False, serialize=False) -> Options:
     o = Options()
     lib().epx_options_default(C.byref(o))
     o.data_linear, o.test_expr_t, o.test_meth_t = int(data_linear), int(test_expr_t), int(test_meth_t)
     o.fc_from_means, o.strict_n3 = int(fc_from_means), int(strict_n3)
+    o.reserved[0] = 1 if serialize else 0   # profiling aid: no overlap of the gene kernels with the probe ranking
     return o
 
 

@@ -86,7 +86,8 @@ struct epx_session {
     DevBuf<uint16_t> pair_na, gene_na;
     DevBuf<int32_t> pair_dnum, gene_dnum;
     /* timing */
-    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t side = nullptr; /* gene-level kernels run here, concurrently with the probe ranking */
     bool ran = false;
     int launches = 0;
     void *staging = nullptr; /* pinned */
@@ -154,7 +155,8 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = s->scal.reserve(8);
     if (e != cudaSuccess) {
         epx_session_destroy(s);
@@ -174,7 +176,8 @@ void epx_session_destroy(epx_session *s)
     s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->nuniq.release(); s->scal.release();
     s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
     s->pair_dnum.release(); s->gene_dnum.release();
-    for (int i = 0; i < 6; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < 8; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->side) cudaStreamDestroy(s->side);
     if (s->staging) cudaFreeHost(s->staging);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -430,15 +433,25 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     pp.lut_exact = s->lut.p; pp.lut_asym = s->lut.p + (m + 1);
     pp.pair = s->pair.p; pp.pair_na = s->pair_na.p; pp.pair_stat = s->pair_stat.p; pp.pair_dnum = s->pair_dnum.p;
 
+    /* The gene-level kernels depend on the expression matrix only and the probe ranking on the methylation
+     * matrix only: they run concurrently (side stream / main stream) and join before the pair kernel.
+     * options.reserved[0] & 1 serialises them (clean per-kernel timings for profiling). */
+    const bool overlap = !(opt.reserved[0] & 1);
+    cudaStream_t gs = overlap ? s->side : st;
     s->launches = 0;
     EPX_CUDA(cudaEventRecord(s->ev[0], st));
-    EPX_CUDA(launch_gene_sort(gp, s->sm_count, st)); s->launches++;
-    EPX_CUDA(cudaEventRecord(s->ev[1], st));
-    EPX_CUDA(launch_pick_reference(tp, st)); s->launches++;
-    EPX_CUDA(launch_gene_tests(tp, s->sm_count, st)); s->launches++;
-    EPX_CUDA(cudaEventRecord(s->ev[2], st));
+    if (overlap) EPX_CUDA(cudaStreamWaitEvent(gs, s->ev[0], 0));
+    EPX_CUDA(cudaEventRecord(s->ev[5], gs));
+    EPX_CUDA(launch_gene_sort(gp, s->sm_count, gs)); s->launches++;
+    EPX_CUDA(cudaEventRecord(s->ev[1], gs));
+    EPX_CUDA(launch_pick_reference(tp, gs)); s->launches++;
+    EPX_CUDA(launch_gene_tests(tp, s->sm_count, gs)); s->launches++;
+    EPX_CUDA(cudaEventRecord(s->ev[2], gs));
+    EPX_CUDA(cudaEventRecord(s->ev[6], st));
     if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[3], st));
+    if (overlap) EPX_CUDA(cudaStreamWaitEvent(st, s->ev[2], 0));
+    EPX_CUDA(cudaEventRecord(s->ev[7], st));
     if (s->n_items > 0) { EPX_CUDA(launch_pair_stats(pp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[4], st));
     s->ran = true;
@@ -478,10 +491,10 @@ int epx_session_timing(epx_session *s, epx_timing *out, char *err, size_t errlen
     EPX_CUDA(cudaEventSynchronize(s->ev[4]));
     memset(out, 0, sizeof(*out));
     EPX_CUDA(cudaEventElapsedTime(&out->total_ms, s->ev[0], s->ev[4]));
-    EPX_CUDA(cudaEventElapsedTime(&out->gene_sort_ms, s->ev[0], s->ev[1]));
+    EPX_CUDA(cudaEventElapsedTime(&out->gene_sort_ms, s->ev[5], s->ev[1]));
     EPX_CUDA(cudaEventElapsedTime(&out->gene_tests_ms, s->ev[1], s->ev[2]));
-    EPX_CUDA(cudaEventElapsedTime(&out->probe_rank_ms, s->ev[2], s->ev[3]));
-    EPX_CUDA(cudaEventElapsedTime(&out->pair_stats_ms, s->ev[3], s->ev[4]));
+    EPX_CUDA(cudaEventElapsedTime(&out->probe_rank_ms, s->ev[6], s->ev[3]));
+    EPX_CUDA(cudaEventElapsedTime(&out->pair_stats_ms, s->ev[7], s->ev[4]));
     out->n_pairs = s->Np; out->n_unique_probes = s->U; out->n_genes = s->G; out->n_samples = s->n;
     out->algorithmic_bytes = s->Np * (8 * s->n + 88) + s->G * (10 * s->n + 48);
     out->kernel_launches = s->launches;

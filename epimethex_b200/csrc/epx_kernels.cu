@@ -301,7 +301,7 @@ constexpr int SORT_WARPS = 8;
 
 /* k_gene_sort, one warp per gene */
 template <int EPS>
-__global__ void __launch_bounds__(SORT_WARPS * 32, 2) k_gene_sort_w(GeneParams p)
+__global__ void __launch_bounds__(SORT_WARPS * 32, 3) k_gene_sort_w(GeneParams p)
 {
     __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
@@ -313,14 +313,15 @@ __global__ void __launch_bounds__(SORT_WARPS * 32, 2) k_gene_sort_w(GeneParams p
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
             const int s = lane + 32 * e;
-            const double v = s < n ? __ldg(x + s) : 0.0;
+            const double v = __ldg(x + min(s, n - 1));
             key_halves(v, khi[e], klo[e]);
             khi[e] = ~khi[e]; klo[e] = ~klo[e]; /* descending by value */
-            sum += v;
+            sum += s < n ? v : 0.0;
         }
         const double mean = warp_sum(sum) / (double)n;
         unsigned short out[EPS];
-        WarpSort<EPS>::order(khi, klo, n, lane, s_ord[warp], [&](int i) { return ~key_of(__ldg(x + i)); }, out);
+        WarpSort<EPS>::template order<true>(khi, klo, n, lane, s_ord[warp], [&](int i) { return __ldg(x + i); },
+                                            (unsigned short)0xffffu, out);
         int ties = 0;
         uint16_t *perm = p.perm + (int64_t)g * n;
         uint8_t *lab8 = p.lab8 + (int64_t)g * p.ldl;
@@ -436,8 +437,13 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
             const int L = la > lb ? la : lb;
             if (la > 0 && lb > 0 && L >= 2) {
                 const double d0 = A[0] - B[0];
-                for (int i = 1 + lane; i < L; i += 32)
-                    if (A[i % la] - B[i % lb] != d0) differs[c] = 1;
+                if (la == lb) {
+                    for (int i = 1 + lane; i < L; i += 32)
+                        if (A[i] - B[i] != d0) differs[c] = 1;
+                } else {
+                    for (int i = 1 + lane; i < L; i += 32)
+                        if (A[i % la] - B[i % lb] != d0) differs[c] = 1;
+                }
             }
             guard[c] = (la == 0 || lb == 0 || L < 2) ? -1 : (__any_sync(FULL, differs[c]) ? 1 : 0);
         }
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
 
 /* k_probe_rank, one warp per referenced probe */
 template <int EPS>
-__global__ void __launch_bounds__(SORT_WARPS * 32) k_probe_rank_w(RankParams p)
+__global__ void __launch_bounds__(SORT_WARPS * 32, 3) k_probe_rank_w(RankParams p)
 {
     __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
@@ -521,16 +527,12 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) k_probe_rank_w(RankParams p)
         const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
         unsigned khi[EPS], klo[EPS];
 #pragma unroll
-        for (int e = 0; e < EPS; e++) {
-            const int s = lane + 32 * e;
-            key_halves(s < n ? __ldg(row + s) : 0.0, khi[e], klo[e]);
-        }
+        for (int e = 0; e < EPS; e++) key_halves(__ldg(row + min(lane + 32 * e, n - 1)), khi[e], klo[e]);
         unsigned short out[EPS];
-        WarpSort<EPS>::order(khi, klo, n, lane, s_ord[warp], [&](int i) { return key_of(__ldg(row + i)); }, out);
+        /* pad positions (k >= n) carry index n: the pair kernel's inert table entry */
+        WarpSort<EPS>::template order<false>(khi, klo, n, lane, s_ord[warp], [&](int i) { return __ldg(row + i); },
+                                             (unsigned short)n, out);
         uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
-#pragma unroll
-        for (int r = 0; r < EPS; r++)
-            if (lane * EPS + r >= n) out[r] = (unsigned short)n; /* pad: the pair kernel's inert table entry */
         if (EPS >= 8) {
 #pragma unroll
             for (int c = 0; c < EPS / 8; c++) {
@@ -1138,8 +1140,8 @@ cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
         k_gene_sort<<<p.G, 256, sort_smem(p.npad), st>>>(p);
         return cudaGetLastError();
     }
-    int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS;
-    if (grid > sm_count * 8) grid = sm_count * 8;
+    int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS; /* one gene per warp: G is small, favour parallelism */
+    (void)sm_count;
     switch (sort_eps(p.n)) {
 #define EPX_CASE(E) case E: k_gene_sort_w<E><<<grid, SORT_WARPS * 32, 0, st>>>(p); break;
         EPX_FOR_SORT_VARIANTS(EPX_CASE)
@@ -1162,8 +1164,8 @@ cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_
         k_gene_tests<<<p.G, 128, (size_t)(p.n + 2) * sizeof(double), st>>>(p);
         return cudaGetLastError();
     }
-    int grid = (p.G + GT_WARPS - 1) / GT_WARPS;
-    if (grid > sm_count * 8) grid = sm_count * 8;
+    int grid = (p.G + GT_WARPS - 1) / GT_WARPS; /* one gene per warp */
+    (void)sm_count;
     const int eps = sort_eps(p.n);
     const size_t smem = (size_t)GT_WARPS * (32 * eps + 2) * sizeof(double);
     switch (eps) {

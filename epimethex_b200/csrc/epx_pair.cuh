@@ -71,7 +71,7 @@ __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t
 __host__ __device__ inline size_t pair2_warp_smem(int n, int64_t ld, int64_t ldo, bool tmode)
 {
     return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 4) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
-                   (tmode ? (size_t)ITEM_PAIRS * 6 * 8 : 0));
+                   (tmode ? (size_t)ITEM_PAIRS * 6 * 8 + (size_t)ITEM_PAIRS * 4 : 0));
 }
 
 template <int EPL, bool TMODE>
@@ -91,8 +91,9 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     double *s_out = (double *)((unsigned char *)tab + round16((size_t)(n + 1) * 4));
     double *s_med = s_out + 16;
     double *s_r = s_med + 8;
-    double *s_t = s_r + ITEM_PAIRS;
-    double *s_df = s_t + 3 * ITEM_PAIRS;
+    double *s_mg = s_r + ITEM_PAIRS;          /* t mode: group means [ITEM_PAIRS][3] */
+    double *s_va = s_mg + 3 * ITEM_PAIRS;     /* t mode: var_g / m   [ITEM_PAIRS][3] */
+    int *s_ok = (int *)(s_va + 3 * ITEM_PAIRS); /* t mode: bit c = Welch test c is defined */
 
     if (lane == 0) {
         mbar_init(&bar[0], 1);
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
     const unsigned T1P = (unsigned)t1 * 0x00100401u, T2P = (unsigned)t2 * 0x00100401u;
     const bool m_even = (m & 1) == 0;
+    const bool has_unl = 3 * m != n; /* n mod 3 != 0: the lowest-expression samples carry no label */
 
     int fill = 0, use = 0;
     uint32_t ph0 = 0, ph1 = 0;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 if (lane == 0) {
                     p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
                     s_r[jj] = EPX_NAN;
-                    if (TMODE) { s_t[jj * 3] = EPX_NAN; s_t[jj * 3 + 1] = EPX_NAN; s_t[jj * 3 + 2] = EPX_NAN; }
+                    if (TMODE) s_ok[jj] = 0;
                 }
                 continue;
             }
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             /* ---- pass A: pivot-shifted moments, sample-major (conflict-free LDS.64) ---- */
             const double K = row[0];
             double sd = 0.0, sdd = 0.0, sxd = 0.0;
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, g3 = 0.0, q3 = 0.0;
 #pragma unroll
             for (int e = 0; e < EPL; e++) {
                 const int s = lane + 32 * e;
@@ -216,10 +218,12 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 sdd = fma(d, d, sdd);
                 sxd = fma(xc_r[e], d, sxd);
                 if (TMODE) {
+                    /* groups 0 and 1 (and the <= 2 unlabelled samples) explicitly, group 2 by subtraction */
                     const unsigned l = EPL <= 16 ? (labs >> (2 * e)) & 3u : (unsigned)(labs64 >> (2 * e)) & 3u;
-                    if (l == 0) { g0 += d; q0 = fma(d, d, q0); }
-                    else if (l == 1) { g1 += d; q1 = fma(d, d, q1); }
-                    else if (l == 2) { g2 += d; q2 = fma(d, d, q2); }
+                    const double d0 = l == 0 ? d : 0.0, d1 = l == 1 ? d : 0.0;
+                    g0 += d0; q0 = fma(d0, d0, q0);
+                    g1 += d1; q1 = fma(d1, d1, q1);
+                    if (has_unl) { const double d3 = (l == 3 && (e < EPL - 1 || s < n)) ? d : 0.0; g3 += d3; q3 = fma(d3, d3, q3); }
                 }
             }
             sd = warp_sum(sd); sdd = warp_sum(sdd); sxd = warp_sum(sxd);
@@ -228,8 +232,9 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             double mg0 = 0, mg1 = 0, mg2 = 0, ss0 = 0, ss1 = 0, ss2 = 0;
             bool redo = sdd > 0.0 && syy < 1e-7 * sdd;
             if (TMODE) {
-                g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
-                q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2);
+                g0 = warp_sum(g0); g1 = warp_sum(g1); q0 = warp_sum(q0); q1 = warp_sum(q1);
+                if (has_unl) { g3 = warp_sum(g3); q3 = warp_sum(q3); }
+                g2 = sd - g0 - g1 - g3; q2 = sdd - q0 - q1 - q3;
                 ss0 = q0 - g0 * g0 * inv_m; ss1 = q1 - g1 * g1 * inv_m; ss2 = q2 - g2 * g2 * inv_m;
                 mg0 = K + g0 * inv_m; mg1 = K + g1 * inv_m; mg2 = K + g2 * inv_m;
                 redo = redo || (q0 > 0.0 && ss0 < 1e-7 * q0) || (q1 > 0.0 && ss1 < 1e-7 * q1) || (q2 > 0.0 && ss2 < 1e-7 * q2);
@@ -363,21 +368,24 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
             } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
             if (TMODE) {
+                /* Welch t, df and p are computed in the deferred pass (one comparison per lane); here only what
+                 * decides NA: the guard, at least two observations, and t.test's "data are essentially constant" */
+                const double sc = 1.0 / (dm * (dm - 1.0));
                 const double mg[3] = { mg0, mg1, mg2 };
-                const double vg[3] = { ss0 / (dm - 1.0), ss1 / (dm - 1.0), ss2 / (dm - 1.0) };
+                const double va[3] = { ss0 * sc, ss1 * sc, ss2 * sc }; /* var_g / m */
                 const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
-                double df[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+                int okbits = 0;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    bool ok = false;
-                    if (guard[c] == 1)
-                        ok = epx_welch(mg[ga_[c]], vg[ga_[c]], dm, mg[gb_[c]], vg[gb_[c]], dm, &stat[c], &df[c]) == 0;
-                    if (!ok) { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
+                    const double thr = 10.0 * 2.220446049250313e-16 * fmax(fabs(mg[ga_[c]]), fabs(mg[gb_[c]]));
+                    const bool ok = guard[c] == 1 && m >= 2 && !(va[ga_[c]] + va[gb_[c]] < thr * thr);
+                    if (ok) okbits |= 1 << c; else na |= 1u << (EPX_P_UP_MID + c);
                 }
                 if (lane < 3) {
-                    s_t[jj * 3 + lane] = lane == 0 ? stat[0] : (lane == 1 ? stat[1] : stat[2]);
-                    s_df[jj * 3 + lane] = lane == 0 ? df[0] : (lane == 1 ? df[1] : df[2]);
+                    s_mg[jj * 3 + lane] = lane == 0 ? mg0 : (lane == 1 ? mg1 : mg2);
+                    s_va[jj * 3 + lane] = lane == 0 ? va[0] : (lane == 1 ? va[1] : va[2]);
                 }
+                if (lane == 3) s_ok[jj] = okbits;
             } else {
                 int ties[3] = { 0, 0, 0 };
                 if (p.exact_ok && anytie) {
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             __syncwarp();
             /* columns 6-8 (t mode) and 10 are written by the deferred pass */
             if (lane < PAIR_COLS - 1 && !(TMODE && lane >= 6 && lane <= 8)) p.pair[(int64_t)j * PAIR_COLS + lane] = s_out[lane];
-            if (lane >= 11 && lane < 14) p.pair_stat[(int64_t)j * 3 + (lane - 11)] = s_out[lane];
+            if (!TMODE && lane >= 11 && lane < 14) p.pair_stat[(int64_t)j * 3 + (lane - 11)] = s_out[lane];
             if (lane >= 14 && lane < 17) p.pair_dnum[(int64_t)j * 3 + (lane - 14)] = lane == 14 ? dnum[0] : (lane == 15 ? dnum[1] : dnum[2]);
             if (lane == 17) p.pair_na[j] = (uint16_t)na;
         }
@@ -435,8 +443,16 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             double pq = EPX_NAN;
             int col = EPX_PEARSON_P;
             if (TMODE && slot < 3) {
-                const double t = s_t[jj * 3 + slot];
-                if (!isnan(t)) pq = epx_t_two_sided_p(t, s_df[jj * 3 + slot]);
+                /* stats::t.test(var.equal = FALSE): se^2 = vx/nx + vy/ny, Welch-Satterthwaite df */
+                const int ga = slot == 2 ? 1 : 0, gb = slot == 0 ? 1 : 2;
+                double t = EPX_NAN;
+                if ((s_ok[jj] >> slot) & 1) {
+                    const double A = s_va[jj * 3 + ga], B = s_va[jj * 3 + gb], se2 = A + B;
+                    t = (s_mg[jj * 3 + ga] - s_mg[jj * 3 + gb]) / sqrt(se2);
+                    const double df = se2 * se2 * (dm - 1.0) / (A * A + B * B);
+                    pq = epx_t_two_sided_p(t, df);
+                }
+                p.pair_stat[(int64_t)(item.begin + jj) * 3 + slot] = t;
                 col = EPX_P_UP_MID + slot;
             } else {
                 const double rr = s_r[jj];

@@ -65,9 +65,9 @@ template <int EPS> struct WarpSort {
                 const bool lower = (lane & q) == 0;
                 unsigned t[EPS];
 #pragma unroll
-                for (int r = 0; r < EPS; r++) t[r] = __shfl_xor_sync(FULL, v[r ^ (EPS - 1)], lm);
+                for (int r = 0; r < EPS; r++) t[r] = __shfl_xor_sync(FULL, v[r], lm);
 #pragma unroll
-                for (int r = 0; r < EPS; r++) v[r] = lower ? min(v[r], t[r]) : max(v[r], t[r]);
+                for (int r = 0; r < EPS; r++) v[r] = lower ? min(v[r], t[r ^ (EPS - 1)]) : max(v[r], t[r ^ (EPS - 1)]);
             }
 #pragma unroll 1
             for (int j = q >> 1; j >= 1; j >>= 1) {
@@ -83,26 +83,26 @@ template <int EPS> struct WarpSort {
     }
 
     /*
-     * Orders one row. (khi[e], klo[e]) = the full 64-bit key (key_hi/key_lo below) of the element with sample
-     * index lane + 32*e (any value for indices >= n). Ascending by (key, index). Returns in out[r] the sample
-     * index at sorted position lane*EPS + r, with bit 15 set when the NEXT position holds an equal key (tie
-     * mark); positions >= n hold 0xffff. s_ord: N uint16 of per-warp shared scratch. fullkey(idx) must return
-     * the 64-bit key of a sample (only called on the exact path).
+     * Orders one row. (khi[e], klo[e]) = key_halves() of the element with sample index min(lane + 32*e, n-1)
+     * (callers clamp the load index, so every slot holds a real key and nothing here needs a validity test
+     * until the words are packed). Ascending by (key, index); pass complemented halves and DESC = true for a
+     * descending order. Returns in out[r] the sample index at sorted position lane*EPS + r, with bit 15 set when
+     * the NEXT position holds an equal value (tie mark); positions >= n hold `padval`. s_ord: N uint16 of
+     * per-warp shared scratch; value(idx) returns the double of a sample (only called for positions whose
+     * neighbour shares their coarse key).
      */
-    template <typename KeyOf>
+    template <bool DESC, typename ValueOf>
     __device__ __forceinline__ static void order(const unsigned (&khi)[EPS], const unsigned (&klo)[EPS], const int n,
-                                                 const int lane, unsigned short *s_ord, KeyOf fullkey,
-                                                 unsigned short (&out)[EPS])
+                                                 const int lane, unsigned short *s_ord, ValueOf value,
+                                                 const unsigned short padval, unsigned short (&out)[EPS])
     {
         /* bits shared by all keys: OR of (key ^ key0) tells where they start to differ */
         const unsigned h0 = __shfl_sync(FULL, khi[0], 0), l0 = __shfl_sync(FULL, klo[0], 0);
         unsigned dhi = 0, dlo = 0;
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
-            if (lane + 32 * e < n) {
-                dhi |= khi[e] ^ h0;
-                dlo |= klo[e] ^ l0;
-            }
+            dhi |= khi[e] ^ h0;
+            dlo |= klo[e] ^ l0;
         }
         dhi = __reduce_or_sync(FULL, dhi);
         dlo = __reduce_or_sync(FULL, dlo);
@@ -126,46 +126,44 @@ template <int EPS> struct WarpSort {
         sort(v, lane);
 
         /* Neighbours that share a coarse key are either exact ties (common: rounded or clipped data) or
-         * values closer than the coarse resolution (rare). Fetch the full keys of just those positions:
+         * values closer than the coarse resolution (rare). Fetch the values of just those positions:
          * equal -> tie mark (the packed index already orders ties by sample index); inverted -> the rare
          * transposition pass below. */
-        bool eqn[EPS];
-        bool anyeq = false;
+        const int nv = n - lane * EPS; /* positions r < nv of this lane are real */
+        unsigned eqm = 0;
         const unsigned nx0 = __shfl_down_sync(FULL, v[0], 1);
 #pragma unroll
         for (int r = 0; r < EPS; r++) {
             const unsigned nxt = r + 1 < EPS ? v[r + 1] : nx0;
-            eqn[r] = ((v[r] ^ nxt) & ~IDXM) == 0 && lane * EPS + r + 1 < n && (r + 1 < EPS || lane < 31);
-            anyeq = anyeq || eqn[r];
+            if (((v[r] ^ nxt) & ~IDXM) == 0 && r + 1 < nv) eqm |= 1u << r;
         }
-        if (!__any_sync(FULL, anyeq)) {
+        if (lane == 31) eqm &= ~(1u << (EPS - 1));
+        if (!__any_sync(FULL, eqm != 0)) {
 #pragma unroll
-            for (int r = 0; r < EPS; r++) out[r] = (lane * EPS + r < n) ? (unsigned short)(v[r] & IDXM) : (unsigned short)0xffffu;
+            for (int r = 0; r < EPS; r++) out[r] = r < nv ? (unsigned short)(v[r] & IDXM) : padval;
             return;
         }
         {
-            const bool prev_eq = __shfl_up_sync(FULL, (int)eqn[EPS - 1], 1) != 0 && lane > 0;
-            unsigned long long fk[EPS];
+            const unsigned prev = __shfl_up_sync(FULL, eqm >> (EPS - 1), 1);
+            const unsigned inv = eqm | (eqm << 1) | (lane > 0 ? (prev & 1u) : 0u); /* positions whose value is needed */
+            double fv[EPS];
 #pragma unroll
-            for (int r = 0; r < EPS; r++) {
-                const bool involved = eqn[r] || (r > 0 ? eqn[r - 1] : prev_eq);
-                fk[r] = involved ? fullkey((int)(v[r] & IDXM)) : 0ull;
-            }
-            const unsigned long long fnx = __shfl_down_sync(FULL, fk[0], 1);
+            for (int r = 0; r < EPS; r++) fv[r] = ((inv >> r) & 1u) ? value((int)(v[r] & IDXM)) : 0.0;
+            const double fnx = __shfl_down_sync(FULL, fv[0], 1);
             bool bad = false;
             unsigned ties = 0;
 #pragma unroll
             for (int r = 0; r < EPS; r++) {
-                const unsigned long long fn = r + 1 < EPS ? fk[r + 1] : fnx;
-                if (eqn[r]) {
-                    bad = bad || fk[r] > fn;
-                    ties |= (fk[r] == fn ? 1u : 0u) << r;
+                const double fn = r + 1 < EPS ? fv[r + 1] : fnx;
+                if ((eqm >> r) & 1u) {
+                    bad = bad || (DESC ? fv[r] < fn : fv[r] > fn);
+                    ties |= (fv[r] == fn ? 1u : 0u) << r;
                 }
             }
             if (!__any_sync(FULL, bad)) {
 #pragma unroll
                 for (int r = 0; r < EPS; r++)
-                    out[r] = (lane * EPS + r < n) ? (unsigned short)((v[r] & IDXM) | (((ties >> r) & 1u) << 15)) : (unsigned short)0xffffu;
+                    out[r] = r < nv ? (unsigned short)((v[r] & IDXM) | (((ties >> r) & 1u) << 15)) : padval;
                 return;
             }
         }
@@ -184,8 +182,8 @@ template <int EPS> struct WarpSort {
             for (int parity = 0; parity < 2; parity++) {
                 for (int k = 2 * lane + parity; k + 1 < n; k += 64) {
                     const unsigned short ia = s_ord[k], ib = s_ord[k + 1];
-                    const unsigned long long ka = fullkey(ia), kb = fullkey(ib);
-                    if (ka > kb || (ka == kb && ia > ib)) {
+                    const double ka = value(ia), kb = value(ib);
+                    if ((DESC ? ka < kb : ka > kb) || (ka == kb && ia > ib)) {
                         /* only possible inside a run of equal coarse keys */
                         s_ord[k] = ib; s_ord[k + 1] = ia;
                         swapped = 1;
@@ -198,10 +196,10 @@ template <int EPS> struct WarpSort {
 #pragma unroll
         for (int r = 0; r < EPS; r++) {
             const int k = lane * EPS + r;
-            unsigned short o = 0xffffu;
+            unsigned short o = padval;
             if (k < n) {
                 o = s_ord[k];
-                if (k + 1 < n && fullkey(o) == fullkey(s_ord[k + 1])) o |= 0x8000u;
+                if (k + 1 < n && value(o) == value(s_ord[k + 1])) o |= 0x8000u;
             }
             out[r] = o;
         }
