@@ -410,7 +410,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     GeneParams gp;
     gp.expr = s->expr.p; gp.n = n; gp.G = (int)G; gp.npad = next_pow2(n); gp.m = m;
     gp.perm = s->perm.p; gp.lab8 = s->lab8.p; gp.ldl = s->ldl; gp.xc = s->xc.p; gp.ldx = s->ldx;
-    gp.gene_aux = s->gene_aux.p; gp.nuniq = s->nuniq.p;
+    gp.gene_aux = s->gene_aux.p; gp.nuniq = s->nuniq.p; gp.one = 1u;
 
     GeneTestParams tp;
     tp.expr = s->expr.p; tp.perm = s->perm.p; tp.n = n; tp.G = (int)G; tp.nuniq = s->nuniq.p;
@@ -420,7 +420,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
 
     RankParams rp;
     rp.meth = s->meth; rp.ld = s->ld; rp.uniq_probe = s->uniq_probe.p; rp.U = s->U; rp.n = n; rp.npad = next_pow2(n);
-    rp.ord = s->ord.p; rp.ldo = s->ldo;
+    rp.ord = s->ord.p; rp.ldo = s->ldo; rp.one = 1u;
 
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;

@@ -34,6 +34,7 @@ struct GeneParams {
     int64_t ldx;
     double *gene_aux;       /* [G][4]    {sxx = sum (x-mean)^2 (0 for a constant gene), mean, sum (x-mean), 1/sqrt(sxx)} */
     int32_t *nuniq;         /* [G] */
+    unsigned one;           /* = 1, opaque to the compiler (see ce_fma) */
 };
 
 struct GeneTestParams {
@@ -58,6 +59,7 @@ struct RankParams {
     int n, npad;
     uint16_t *ord;          /* [U][ldo]: sample index of the k-th smallest value | 0x8000 when equal to the next */
     int64_t ldo;
+    unsigned one;           /* = 1, opaque to the compiler (see ce_fma) */
 };
 
 struct PairParams {

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32, 3) k_gene_sort_w(GeneParams p
         const double mean = warp_sum(sum) / (double)n;
         unsigned short out[EPS];
         WarpSort<EPS>::template order<true>(khi, klo, n, lane, s_ord[warp], [&](int i) { return __ldg(x + i); },
-                                            (unsigned short)0xffffu, out);
+                                            (unsigned short)0xffffu, p.one, out);
         int ties = 0;
         uint16_t *perm = p.perm + (int64_t)g * n;
         uint8_t *lab8 = p.lab8 + (int64_t)g * p.ldl;
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32, 3) k_probe_rank_w(RankParams 
         unsigned short out[EPS];
         /* pad positions (k >= n) carry index n: the pair kernel's inert table entry */
         WarpSort<EPS>::template order<false>(khi, klo, n, lane, s_ord[warp], [&](int i) { return __ldg(row + i); },
-                                             (unsigned short)n, out);
+                                             (unsigned short)n, p.one, out);
         uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
         if (EPS >= 8) {
 #pragma unroll

@@ -14,14 +14,28 @@
 
 namespace epx {
 
+/* Compare-exchange with the maximum computed on the FMA pipe: max = a + b - min as two IMADs whose multipliers
+ * (+1, -1) are run-time values, so ptxas cannot fold them back into integer-ALU adds. The sort kernels are bound
+ * by the integer ALU pipe (VIMNMX); moving ~40 % of the max() halves there balances the two pipes. */
+__device__ __forceinline__ void ce_fma(unsigned &a, unsigned &b, const unsigned one, const unsigned minus1)
+{
+    const unsigned mn = min(a, b);
+    unsigned s, mx;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(a), "r"(one), "r"(b));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(mx) : "r"(mn), "r"(minus1), "r"(s));
+    a = mn;
+    b = mx;
+}
+
 template <int EPS> struct WarpSort {
     static constexpr int N = 32 * EPS;
     static constexpr int IDXB = (EPS == 1 ? 5 : EPS == 2 ? 6 : EPS == 4 ? 7 : EPS == 8 ? 8 : EPS == 16 ? 9 : 10);
     static constexpr unsigned IDXM = (1u << IDXB) - 1u;
+    static constexpr int FMA_CE_OF_5 = 4; /* of every 5 in-thread compare-exchanges, this many use ce_fma */
     static_assert(EPS == 1 || EPS == 2 || EPS == 4 || EPS == 8 || EPS == 16 || EPS == 32, "EPS must be a power of two <= 32");
 
     /* in-thread half-cleaners with strides EPS/2 .. 1 (static register indices) */
-    __device__ __forceinline__ static void thread_tail(unsigned (&v)[EPS], int from)
+    __device__ __forceinline__ static void thread_tail(unsigned (&v)[EPS], int from, const unsigned one, const unsigned minus1)
     {
 #pragma unroll
         for (int j = EPS / 2; j >= 1; j >>= 1) {
@@ -29,9 +43,12 @@ template <int EPS> struct WarpSort {
 #pragma unroll
                 for (int r = 0; r < EPS; r++) {
                     if ((r & j) == 0) {
-                        const unsigned a = v[r], b = v[r | j];
-                        v[r] = min(a, b);
-                        v[r | j] = max(a, b);
+                        if (FMA_CE_OF_5 > 0 && (r % 5) < FMA_CE_OF_5) ce_fma(v[r], v[r | j], one, minus1);
+                        else {
+                            const unsigned a = v[r], b = v[r | j];
+                            v[r] = min(a, b);
+                            v[r | j] = max(a, b);
+                        }
                     }
                 }
             }
@@ -43,7 +60,7 @@ template <int EPS> struct WarpSort {
      * index keeps the minimum) followed by half-cleaners (i <-> i ^ j). Phases that fit a thread are unrolled;
      * the five cross-lane phases run as a loop (same code for every phase: the body stays in the instruction
      * cache) with the lane masks as run-time values. */
-    __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane)
+    __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane, const unsigned one, const unsigned minus1)
     {
 #pragma unroll
         for (int k = 2; k <= EPS; k <<= 1) {
@@ -56,7 +73,7 @@ template <int EPS> struct WarpSort {
                     v[q] = max(a, b);
                 }
             }
-            thread_tail(v, k / 4);
+            thread_tail(v, k / 4, one, minus1);
         }
 #pragma unroll 1
         for (int q = 1; q < 32; q <<= 1) { /* phase k = 2*EPS*q */
@@ -78,7 +95,7 @@ template <int EPS> struct WarpSort {
                     v[r] = lower ? min(v[r], t) : max(v[r], t);
                 }
             }
-            thread_tail(v, EPS / 2);
+            thread_tail(v, EPS / 2, one, minus1);
         }
     }
 
@@ -94,7 +111,8 @@ template <int EPS> struct WarpSort {
     template <bool DESC, typename ValueOf>
     __device__ __forceinline__ static void order(const unsigned (&khi)[EPS], const unsigned (&klo)[EPS], const int n,
                                                  const int lane, unsigned short *s_ord, ValueOf value,
-                                                 const unsigned short padval, unsigned short (&out)[EPS])
+                                                 const unsigned short padval, const unsigned one,
+                                                 unsigned short (&out)[EPS])
     {
         /* bits shared by all keys: OR of (key ^ key0) tells where they start to differ */
         const unsigned h0 = __shfl_sync(FULL, khi[0], 0), l0 = __shfl_sync(FULL, klo[0], 0);
@@ -123,7 +141,7 @@ template <int EPS> struct WarpSort {
                 v[e] = s < n ? ((w & ~IDXM) | (unsigned)s) : 0xffffffffu;
             }
         }
-        sort(v, lane);
+        sort(v, lane, one, 0u - one);
 
         /* Neighbours that share a coarse key are either exact ties (common: rounded or clipped data) or
          * values closer than the coarse resolution (rare). Fetch the values of just those positions:
