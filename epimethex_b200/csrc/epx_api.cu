@@ -156,7 +156,11 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     s->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0; /* the side stream (gene kernels: little work, long latency chains) gets the highest priority */
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = s->scal.reserve(8);
     if (e != cudaSuccess) {
         epx_session_destroy(s);
