@@ -43,6 +43,10 @@ WORKLOADS = {
                          desc="SKCM full genome at 474 samples (nearest multiple of 3: the reference's defined case)"),
     "epic": dict(shape="epic", genes=(0, 20531), te=False, tm=False,
                  desc="synthetic EPIC-array shape: 866k probes x 1,000 samples, KS on both"),
+    # BASELINE.json configs[4] at single-GPU scale: 9,000 samples, a 2,000-gene slice (the full 35 GB matrix is an
+    # 8-GPU job); only the rows the slice references are generated
+    "pancan_slice": dict(shape="pancan", genes=(0, 2000), te=True, tm=False,
+                         desc="synthetic pan-cancer shape, 9,000 samples, gene range 1-2000 of 20,531, 485,577 probes"),
     "tiny": dict(shape=None, genes=(0, 300), te=True, tm=False, n_samples=99, n_probes=6000, n_genes=300,
                  desc="tiny self-test workload"),
 }

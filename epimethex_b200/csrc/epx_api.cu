@@ -156,11 +156,7 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     s->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
-    if (e == cudaSuccess) {
-        int lo = 0, hi = 0; /* the side stream (gene kernels: little work, long latency chains) gets the highest priority */
-        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, hi);
-    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = s->scal.reserve(8);
     if (e != cudaSuccess) {
         epx_session_destroy(s);
@@ -305,6 +301,11 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
 
     std::vector<int32_t> slot_of((size_t)s->P, -1), pair_slot((size_t)Np), pair_gene((size_t)Np), uniq;
     std::vector<Item> items;
+    /* work items of the pair kernel: up to ITEM_PAIRS consecutive pairs of one gene. Small jobs (a 1000-gene
+     * range is ~23 k pairs for ~2400 resident warps) get smaller items so that every warp has several. */
+    int64_t item_pairs = Np / ((int64_t)s->sm_count * 16 * 4);
+    if (item_pairs < 4) item_pairs = 4;
+    if (item_pairs > ITEM_PAIRS) item_pairs = ITEM_PAIRS;
     for (int64_t g = 0; g < n_genes; g++) {
         const int64_t b = row_ptr[g], e = row_ptr[g + 1];
         if (e < b || e > Np) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)g);
@@ -316,10 +317,10 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
             if (slot_of[(size_t)pi] < 0) { slot_of[(size_t)pi] = (int32_t)uniq.size(); uniq.push_back(pi); }
             pair_slot[(size_t)j] = slot_of[(size_t)pi];
         }
-        for (int64_t j = b; j < e; j += ITEM_PAIRS) {
+        for (int64_t j = b; j < e; j += item_pairs) {
             Item it;
             it.gene = (int32_t)g; it.begin = (int32_t)j;
-            it.count = (int32_t)((e - j) < ITEM_PAIRS ? (e - j) : ITEM_PAIRS); it.pad = 0;
+            it.count = (int32_t)((e - j) < item_pairs ? (e - j) : item_pairs); it.pad = 0;
             items.push_back(it);
         }
     }

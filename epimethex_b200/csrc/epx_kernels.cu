@@ -301,7 +301,7 @@ constexpr int SORT_WARPS = 8;
 
 /* k_gene_sort, one warp per gene */
 template <int EPS>
-__global__ void __launch_bounds__(SORT_WARPS * 32, 3) k_gene_sort_w(GeneParams p)
+__global__ void __launch_bounds__(SORT_WARPS * 32, (EPS <= 16 ? 3 : 2)) k_gene_sort_w(GeneParams p)
 {
     __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
 
 /* k_probe_rank, one warp per referenced probe */
 template <int EPS>
-__global__ void __launch_bounds__(SORT_WARPS * 32, 3) k_probe_rank_w(RankParams p)
+__global__ void __launch_bounds__(SORT_WARPS * 32, (EPS <= 16 ? 3 : 2)) k_probe_rank_w(RankParams p)
 {
     __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
