@@ -1,0 +1,85 @@
+/*
+ * epx_ctasort.cuh — one CTA (8 warps) orders one long row (1024 < n <= 16384 values, e.g. the 9,000-sample
+ * pan-cancer shape) held in shared memory: every warp sorts 1024-value chunks with the register bitonic sort of
+ * epx_warpsort.cuh, then log2(chunks) merge passes (merge path: each thread produces a contiguous slice of the
+ * output after a binary search for its split point) combine them. Exact and stable: equal values keep ascending
+ * sample index, because chunks are contiguous index ranges and merges prefer the left run on ties.
+ */
+#pragma once
+#include "epx_warpsort.cuh"
+
+namespace epx {
+
+constexpr int CTASORT_THREADS = 256;
+constexpr int CTASORT_CHUNK = 1024;
+
+/* entries of each of the two index buffers: a whole number of chunks, so that the second buffer can double as
+ * the warp sorts' scratch (1024 entries per chunk being sorted) while the first one is being filled */
+__host__ __device__ inline int ctasort_entries(int n) { return (n + CTASORT_CHUNK - 1) / CTASORT_CHUNK * CTASORT_CHUNK; }
+
+/* shared memory needed besides the row itself */
+__host__ __device__ inline size_t ctasort_smem(int n) { return (size_t)ctasort_entries(n) * 2 * 2; }
+
+template <bool DESC> __device__ __forceinline__ bool comes_before(double a, double b) { return DESC ? a > b : a < b; }
+
+/* s_val: the row (n doubles, shared); s_a, s_b: ctasort_entries(n) uint16 each. All threads of the CTA must call.
+ * Returns the buffer (s_a or s_b) that holds the sample indices in sorted order. */
+template <bool DESC>
+__device__ unsigned short *cta_sort_row(const double *s_val, const int n, unsigned short *s_a, unsigned short *s_b,
+                                        const unsigned one)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nchunks = (n + CTASORT_CHUNK - 1) / CTASORT_CHUNK;
+    for (int c = warp; c < nchunks; c += nwarps) {
+        const int base = c * CTASORT_CHUNK;
+        const int nc = min(CTASORT_CHUNK, n - base);
+        unsigned khi[32], klo[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            key_halves(s_val[base + min(lane + 32 * e, nc - 1)], khi[e], klo[e]);
+            if (DESC) { khi[e] = ~khi[e]; klo[e] = ~klo[e]; }
+        }
+        unsigned short out[32];
+        WarpSort<32>::template order<DESC>(khi, klo, nc, lane, s_b + c * CTASORT_CHUNK,
+                                           [&](int i) { return s_val[base + i]; }, (unsigned short)0xffffu, one, out);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const int k = lane * 32 + r;
+            if (k < nc) s_a[base + k] = (unsigned short)(base + (out[r] & 0x7fff));
+        }
+    }
+    __syncthreads();
+
+    unsigned short *src = s_a, *dst = s_b;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    for (int len = CTASORT_CHUNK; len < n; len <<= 1) {
+        int o = min((int)threadIdx.x * per, n);
+        const int o_end = min(o + per, n);
+        while (o < o_end) {
+            const int pbase = (o / (2 * len)) * (2 * len);
+            const int la = min(len, n - pbase), lb = min(len, n - pbase - la);
+            const unsigned short *A = src + pbase, *B = src + pbase + la;
+            const int seg_end = min(o_end, pbase + la + lb);
+            const int d = o - pbase;
+            /* merge path: i = how many of the first d outputs come from A (A wins ties) */
+            int lo = max(0, d - lb), hi = min(d, la);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (!comes_before<DESC>(s_val[B[d - 1 - mid]], s_val[A[mid]])) lo = mid + 1; else hi = mid;
+            }
+            int i = lo, j = d - lo;
+            double va = i < la ? s_val[A[i]] : 0.0, vb = j < lb ? s_val[B[j]] : 0.0;
+            for (int k = o; k < seg_end; k++) {
+                const bool take_a = i < la && (j >= lb || !comes_before<DESC>(vb, va));
+                if (take_a) { dst[k] = A[i]; i++; va = i < la ? s_val[A[i]] : 0.0; }
+                else { dst[k] = B[j]; j++; vb = j < lb ? s_val[B[j]] : 0.0; }
+            }
+            o = seg_end;
+        }
+        __syncthreads();
+        unsigned short *t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+} // namespace epx

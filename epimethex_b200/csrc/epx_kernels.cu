@@ -14,52 +14,49 @@
 #include "epx_device.cuh"
 #include "epx_internal.h"
 #include "epx_warpsort.cuh"
+#include "epx_ctasort.cuh"
 #include "epx_pair.cuh"
 
 namespace epx {
 
 /* ============================================================ k_gene_sort */
 
-__global__ void __launch_bounds__(256) k_gene_sort(GeneParams p)
+__global__ void __launch_bounds__(CTASORT_THREADS) k_gene_sort(GeneParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *keys = (unsigned long long *)smem;
-    unsigned short *idx = (unsigned short *)(keys + p.npad);
+    const int g = blockIdx.x, n = p.n;
+    double *s_val = (double *)smem;
+    unsigned short *s_a = (unsigned short *)(s_val + ((n + 1) & ~1));
+    unsigned short *s_b = s_a + ctasort_entries(n);
     __shared__ double red[40];
     __shared__ int s_uniq;
 
-    const int g = blockIdx.x, n = p.n;
     const double *x = p.expr + (int64_t)g * n;
     if (threadIdx.x == 0) s_uniq = 1;
     double sum = 0.0;
-    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
-        if (i < n) {
-            double v = x[i];
-            keys[i] = ~key_of(v); /* descending by value */
-            idx[i] = (unsigned short)i;
-            sum += v;
-        } else {
-            keys[i] = ~0ull;
-            idx[i] = 0xffffu;
-        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = x[i];
+        s_val[i] = v;
+        sum += v;
     }
     __syncthreads();
-    block_bitonic_sort(keys, idx, p.npad); /* (key, idx) ascending = value descending, ties by sample index */
+    /* value descending, ties by sample index */
+    const unsigned short *ord = cta_sort_row<true>(s_val, n, s_a, s_b, p.one);
 
     int uniq = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int s = idx[i];
+        const int s = ord[i];
         p.perm[(int64_t)g * n + i] = (uint16_t)s;
-        int lab = i / p.m;
+        const int lab = i / p.m;
         p.lab8[(int64_t)g * p.ldl + s] = (uint8_t)(lab > 3 ? 3 : lab);
-        if (i > 0 && keys[i] != keys[i - 1]) uniq++;
+        if (i > 0 && s_val[s] != s_val[ord[i - 1]]) uniq++;
     }
     if (uniq) atomicAdd(&s_uniq, uniq);
 
     double mean = block_sum(sum, red) / (double)n;
     double sxx = 0.0, sxc = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double d = x[i] - mean;
+        double d = s_val[i] - mean;
         p.xc[(int64_t)g * p.ldx + i] = d;
         sxx += d * d;
         sxc += d;
@@ -269,31 +266,30 @@ __global__ void __launch_bounds__(128) k_gene_tests(GeneTestParams p)
 
 /* ============================================================ k_probe_rank */
 
-__global__ void __launch_bounds__(256) k_probe_rank(RankParams p)
+__global__ void __launch_bounds__(CTASORT_THREADS, 2) k_probe_rank(RankParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *keys = (unsigned long long *)smem;
-    unsigned short *idx = (unsigned short *)(keys + p.npad);
-    const int64_t slot = blockIdx.x;
     const int n = p.n;
-    const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
-    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
-        if (i < n) { keys[i] = key_of(row[i]); idx[i] = (unsigned short)i; }
-        else { keys[i] = ~0ull; idx[i] = 0xffffu; }
-    }
-    __syncthreads();
-    block_bitonic_sort(keys, idx, p.npad);
-    uint16_t *o = p.ord + slot * p.ldo;
-    for (int k = threadIdx.x; k < p.ldo; k += blockDim.x) {
-        unsigned short v = (unsigned short)n; /* pad */
-        if (k < n) {
-            v = idx[k];
-            if (k + 1 < n && keys[k] == keys[k + 1]) v |= 0x8000u;
+    double *s_val = (double *)smem;
+    unsigned short *s_a = (unsigned short *)(s_val + ((n + 1) & ~1));
+    unsigned short *s_b = s_a + ctasort_entries(n);
+    for (int64_t slot = blockIdx.x; slot < p.U; slot += gridDim.x) {
+        const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
+        __syncthreads(); /* the previous row is done with the buffers */
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
+        __syncthreads();
+        const unsigned short *ord = cta_sort_row<false>(s_val, n, s_a, s_b, p.one);
+        uint16_t *o = p.ord + slot * p.ldo;
+        for (int k = threadIdx.x; k < p.ldo; k += blockDim.x) {
+            unsigned short v = (unsigned short)n; /* pad */
+            if (k < n) {
+                v = ord[k];
+                if (k + 1 < n && s_val[v] == s_val[ord[k + 1]]) v |= 0x8000u;
+            }
+            o[k] = v;
         }
-        o[k] = v;
     }
 }
-
 
 /* ============================================================ warp-per-row variants (n <= 1024) */
 
@@ -1084,7 +1080,7 @@ cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, in
 }
 
 
-static size_t sort_smem(int npad) { return (size_t)npad * 10; }
+static size_t sort_smem(int n) { return (size_t)((n + 1) & ~1) * 8 + ctasort_smem(n); }
 
 template <typename F> static cudaError_t allow_max_dynamic_smem(F *func)
 {
@@ -1137,7 +1133,7 @@ cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
 {
     if (p.G <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
-        k_gene_sort<<<p.G, 256, sort_smem(p.npad), st>>>(p);
+        k_gene_sort<<<p.G, CTASORT_THREADS, sort_smem(p.n), st>>>(p);
         return cudaGetLastError();
     }
     int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS; /* one gene per warp: G is small, favour parallelism */
@@ -1181,7 +1177,15 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
 {
     if (p.U <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
-        k_probe_rank<<<(unsigned)p.U, 256, sort_smem(p.npad), st>>>(p);
+        {
+            const size_t smem = sort_smem(p.n);
+            int per_sm = (int)((226 * 1024) / (smem + 1024));
+            if (per_sm > 2) per_sm = 2;
+            if (per_sm < 1) per_sm = 1;
+            int64_t grid = (int64_t)sm_count * per_sm;
+            if (grid > p.U) grid = p.U;
+            k_probe_rank<<<(unsigned)grid, CTASORT_THREADS, smem, st>>>(p);
+        }
         return cudaGetLastError();
     }
     int64_t grid = (p.U + SORT_WARPS - 1) / SORT_WARPS;

@@ -104,7 +104,7 @@ def test_missing_probes_constant_rows_and_guard(sess):
         assert (ref.pair_na == 0x7FF).any() and ((ref.pair_na & 0x1C0) != 0).any()
 
 
-@pytest.mark.parametrize("n,decimals", [(1500, None), (2001, 3)])
+@pytest.mark.parametrize("n,decimals", [(1500, None), (2001, 3), (4500, 2)])
 def test_long_rows_use_the_cta_per_pair_kernel(sess, n, decimals):
     """n > 1024 (towards the 9,000-sample pan-cancer shape): CTA-per-row sort + CTA-per-pair statistics"""
     x, y, idx = _synth(40, n, 600, decimals=decimals)
