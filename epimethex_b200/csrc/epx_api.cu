@@ -267,6 +267,8 @@ int epx_session_set_methylation_device(epx_session *s, const double *d_rows, int
     if (!s || !d_rows || n_probes < 1 || ld < n_samples) return fail(err, errlen, EPX_EINVAL, "bad methylation arguments");
     int rc = check_samples(s, n_samples, err, errlen);
     if (rc) return rc;
+    if ((((uintptr_t)d_rows) & 15) != 0 || (ld & 1) != 0)
+        return fail(err, errlen, EPX_EINVAL, "device methylation rows must be 16-byte aligned with an even leading dimension (bulk copies)");
     s->meth_own.release();
     s->meth = d_rows; s->P = n_probes; s->n_meth = n_samples; s->ld = ld;
     s->G_index = -1;

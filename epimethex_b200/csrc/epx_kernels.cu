@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
  * row, labels and the probe's order are staged in shared memory (11n bytes); the gene's centred expression is
  * read from global memory (it stays in L2 across the gene's probes). Correct and general (n <= 16,384), not yet
  * tuned: no bulk-copy pipeline, one pair per CTA at a time. */
-constexpr int BIG_THREADS = 256;
+constexpr int BIG_THREADS = 512;
 
 __device__ __forceinline__ int block_max_i(int v, int *red)
 {
@@ -873,52 +873,80 @@ __device__ __forceinline__ int block_max_i(int v, int *red)
     return r;
 }
 
-template <bool TMODE>
+/* bytes of one stage: row (ld doubles) + order (ldo uint16) */
+__host__ __device__ inline size_t big_stage_bytes(int64_t ld, int64_t ldo) { return (size_t)ld * 8 + (size_t)ldo * 2; }
+
+/* STAGES = 2: the next pair's row and order are bulk-copied (cp.async.bulk + mbarrier) while this pair is
+ * computed; STAGES = 1 when two stages do not fit in shared memory (n > ~11,000). */
+template <bool TMODE, int STAGES>
 __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int n = p.n, m = p.m, tid = threadIdx.x, nt = blockDim.x;
-    double *s_row = (double *)smem;
-    unsigned short *s_ord = (unsigned short *)(s_row + ((n + 1) & ~1));
-    uint8_t *s_lab = (uint8_t *)(s_ord + ((n + 7) & ~7));
+    const uint32_t rowb = (uint32_t)p.ld * 8u, ordb = (uint32_t)p.ldo * 2u, stageb = rowb + ordb;
+    uint8_t *s_lab = (uint8_t *)(smem + (size_t)STAGES * stageb);
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ double red[40];
-    __shared__ int ired[8];
-    __shared__ int s_cnt[BIG_THREADS][3];
+    __shared__ int ired[BIG_THREADS / 32];
+    __shared__ int s_wtot[BIG_THREADS / 32][3];
     __shared__ double s_med[8];
-    __shared__ int s_flag;
     const double dm = (double)m, dn_ = (double)n;
     const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
+    const int lane = tid & 31, warp = tid >> 5;
 
-    for (int j = blockIdx.x; j < p.n_pairs; j += gridDim.x) {
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    __syncthreads();
+    uint32_t ph[2] = { 0, 0 };
+    auto issue = [&](int j, int stage) { /* thread 0 only */
+        const int pi = p.probe_idx[j];
+        if (pi < 0) return;
+        unsigned char *dst = smem + (size_t)stage * stageb;
+        mbar_expect_tx(&bar[stage], stageb);
+        bulk_g2s(dst, p.meth + (int64_t)pi * p.ld, rowb, &bar[stage]);
+        bulk_g2s(dst + rowb, p.ord + (int64_t)p.pair_slot[j] * p.ldo, ordb, &bar[stage]);
+    };
+    int cur_gene = -1;
+    if (tid == 0 && (int)blockIdx.x < p.n_pairs) issue(blockIdx.x, 0);
+
+    int it = 0;
+    for (int j = blockIdx.x; j < p.n_pairs; j += gridDim.x, it++) {
+        const int stage = STAGES == 2 ? (it & 1) : 0;
         const int pi = p.probe_idx[j];
         const int gene = p.pair_gene[j];
+        __syncthreads(); /* everybody is done with the other stage (and with s_lab / s_med of the previous pair) */
+        if (STAGES == 2 && tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, stage ^ 1);
         if (pi < 0) {
             if (tid < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + tid] = EPX_NAN;
             if (tid < 3) { p.pair_stat[(int64_t)j * 3 + tid] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + tid] = -1; }
             if (tid == 0) p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+            if (STAGES == 1 && tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, 0);
             continue;
         }
-        const double *row = p.meth + (int64_t)pi * p.ld;
-        const uint16_t *ord = p.ord + (int64_t)p.pair_slot[j] * p.ldo;
+        const double *s_row = (const double *)(smem + (size_t)stage * stageb);
+        const unsigned short *s_ord = (const unsigned short *)(smem + (size_t)stage * stageb + rowb);
         const double *xc = p.xc + (int64_t)gene * p.ldx;
-        const uint8_t *lab = p.lab8 + (int64_t)gene * p.ldl;
         const uint16_t *perm_g = p.perm + (int64_t)gene * n;
         const double *ga = p.gene_aux + 4 * (int64_t)gene;
-        __syncthreads(); /* previous pair is done with the staging buffers */
-        const double K = __ldg(row);
+        if (gene != cur_gene) { /* uniform: labels of the gene, reused by its following probes */
+            const uint8_t *lab = p.lab8 + (int64_t)gene * p.ldl;
+            for (int s = tid; s < n; s += nt) s_lab[s] = lab[s];
+            cur_gene = gene;
+        }
+        mbar_wait(&bar[stage], ph[stage]);
+        ph[stage] ^= 1;
+        __syncthreads();
+
+        const double K = s_row[0];
         double sd = 0, sdd = 0, sxd = 0, g0 = 0, g1 = 0, g2 = 0, q0 = 0, q1 = 0, q2 = 0;
         for (int s = tid; s < n; s += nt) {
-            const double v = __ldg(row + s);
-            const unsigned l = lab[s];
-            s_row[s] = v; s_lab[s] = (uint8_t)l; s_ord[s] = ord[s];
-            const double d = v - K;
-            sd += d; sdd = fma(d, d, sdd); sxd = fma(xc[s], d, sxd);
+            const double d = s_row[s] - K;
+            sd += d; sdd = fma(d, d, sdd); sxd = fma(__ldg(xc + s), d, sxd);
             if (TMODE) {
+                const unsigned l = s_lab[s];
                 if (l == 0) { g0 += d; q0 = fma(d, d, q0); } else if (l == 1) { g1 += d; q1 = fma(d, d, q1); }
                 else if (l == 2) { g2 += d; q2 = fma(d, d, q2); }
             }
         }
-        if (tid == 0) s_flag = 0;
         sd = block_sum(sd, red); sdd = block_sum(sdd, red); sxd = block_sum(sxd, red);
         double syy = sdd - sd * sd / dn_, sxy = sxd - (sd / dn_) * ga[2];
         double mg0 = 0, mg1 = 0, mg2 = 0, ss0 = 0, ss1 = 0, ss2 = 0;
@@ -936,7 +964,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             double a0 = 0, a1 = 0, b0 = 0, b1 = 0, b2 = 0;
             for (int s = tid; s < n; s += nt) {
                 const double yv = s_row[s], d = yv - mean_all;
-                a0 = fma(d, d, a0); a1 = fma(xc[s], d, a1);
+                a0 = fma(d, d, a0); a1 = fma(__ldg(xc + s), d, a1);
                 if (TMODE) {
                     const unsigned l = s_lab[s];
                     const double dg = yv - (l == 0 ? mg0 : (l == 1 ? mg1 : mg2));
@@ -946,9 +974,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             syy = block_sum(a0, red); sxy = block_sum(a1, red);
             if (TMODE) { ss0 = block_sum(b0, red); ss1 = block_sum(b1, red); ss2 = block_sum(b2, red); }
         }
-        __syncthreads();
 
-        /* sorted walk: thread t owns positions [t*chunk, (t+1)*chunk) */
+        /* sorted walk: thread t owns positions [t*chunk, (t+1)*chunk); label counts by warp scan + warp totals */
         const int chunk = (n + nt - 1) / nt;
         const int k0 = min(tid * chunk, n), k1 = min(k0 + chunk, n);
         int c0 = 0, c1 = 0, c2 = 0;
@@ -956,14 +983,18 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             const unsigned l = s_lab[s_ord[k] & 0x7fffu];
             c0 += l == 0; c1 += l == 1; c2 += l == 2;
         }
-        s_cnt[tid][0] = c0; s_cnt[tid][1] = c1; s_cnt[tid][2] = c2;
-        __syncthreads();
-        if (tid < 3) { /* exclusive scan of one label's per-thread totals */
-            int run = 0;
-            for (int t = 0; t < nt; t++) { const int v = s_cnt[t][tid]; s_cnt[t][tid] = run; run += v; }
+        int i0 = c0, i1 = c1, i2 = c2; /* inclusive scan inside the warp */
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a0 = __shfl_up_sync(FULL, i0, d), a1 = __shfl_up_sync(FULL, i1, d), a2 = __shfl_up_sync(FULL, i2, d);
+            if (lane >= d) { i0 += a0; i1 += a1; i2 += a2; }
         }
+        __syncthreads(); /* s_wtot of the previous pair has been consumed */
+        if (lane == 31) { s_wtot[warp][0] = i0; s_wtot[warp][1] = i1; s_wtot[warp][2] = i2; }
         __syncthreads();
-        c0 = s_cnt[tid][0]; c1 = s_cnt[tid][1]; c2 = s_cnt[tid][2];
+        int b0_ = 0, b1_ = 0, b2_ = 0;
+        for (int w = 0; w < warp; w++) { b0_ += s_wtot[w][0]; b1_ += s_wtot[w][1]; b2_ += s_wtot[w][2]; }
+        c0 = b0_ + i0 - c0; c1 = b1_ + i1 - c1; c2 = b2_ + i2 - c2; /* exclusive prefix of this thread */
         int d01 = 0, d02 = 0, d12 = 0;
         for (int k = k0; k < k1; k++) {
             const unsigned short o = s_ord[k];
@@ -1034,6 +1065,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             for (int c = 0; c < PAIR_COLS; c++) p.pair[(int64_t)j * PAIR_COLS + c] = out[c];
             for (int c = 0; c < 3; c++) { p.pair_stat[(int64_t)j * 3 + c] = stat[c]; p.pair_dnum[(int64_t)j * 3 + c] = dnum[c]; }
             p.pair_na[j] = (uint16_t)na;
+        }
+        if (STAGES == 1) {
+            __syncthreads();
+            if (tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, 0);
         }
     }
 }
@@ -1112,8 +1147,10 @@ cudaError_t kernels_init()
     if ((e = allow_max_dynamic_smem(k_pair_stats<L, W, false>)) != cudaSuccess) return e;
     EPX_FOR_PAIR_VARIANTS(EPX_PAIR_ATTR)
 #undef EPX_PAIR_ATTR
-    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<true>)) != cudaSuccess) return e;
-    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<false>)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<true, 1>)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<false, 1>)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<true, 2>)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_pair_stats_cta<false, 2>)) != cudaSuccess) return e;
 #define EPX_PAIR2_ATTR(E)                                                                 \
     if ((e = allow_max_dynamic_smem(k_pair_stats2<E, true>)) != cudaSuccess) return e;    \
     if ((e = allow_max_dynamic_smem(k_pair_stats2<E, false>)) != cudaSuccess) return e;
@@ -1236,14 +1273,18 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
 {
     if (p.n_items <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
-        const size_t smem = (size_t)((p.n + 1) & ~1) * 8 + (size_t)((p.n + 7) & ~7) * 2 + (size_t)((p.n + 15) & ~15);
-        int per_sm = (int)((220 * 1024) / (smem + 8192));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
-        int grid = sm_count * per_sm;
+        const size_t stage = big_stage_bytes(p.ld, p.ldo), labb = (size_t)((p.n + 15) & ~15);
+        const bool two = 2 * stage + labb + 4096 <= 227 * 1024;
+        const size_t smem = (two ? 2 : 1) * stage + labb;
+        int grid = sm_count; /* one 512-thread CTA per SM, persistent */
         if (grid > p.n_pairs) grid = p.n_pairs;
-        if (p.test_t) k_pair_stats_cta<true><<<grid, BIG_THREADS, smem, st>>>(p);
-        else k_pair_stats_cta<false><<<grid, BIG_THREADS, smem, st>>>(p);
+        if (two) {
+            if (p.test_t) k_pair_stats_cta<true, 2><<<grid, BIG_THREADS, smem, st>>>(p);
+            else k_pair_stats_cta<false, 2><<<grid, BIG_THREADS, smem, st>>>(p);
+        } else {
+            if (p.test_t) k_pair_stats_cta<true, 1><<<grid, BIG_THREADS, smem, st>>>(p);
+            else k_pair_stats_cta<false, 1><<<grid, BIG_THREADS, smem, st>>>(p);
+        }
         return cudaGetLastError();
     }
     const int epl = (p.n + 31) / 32;
