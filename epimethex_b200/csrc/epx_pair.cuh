@@ -297,20 +297,31 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
              * field < 512, so adding 511 sets a field's bit 9 iff it is non-zero); KS at tie-run ends */
             unsigned cnt = incl - tot;
             unsigned hw1 = 0, hw2 = 0; /* per group: 1 + position (inside this lane) of the t1-th / t2-th member */
+            unsigned ce = 0;           /* counts at the last tie-run end seen (0 = nothing evaluated yet: all differences 0) */
             int mx01 = 0, mn01 = 0, mx02 = 0, mn02 = 0, mx12 = 0, mn12 = 0;
 #pragma unroll
             for (int e = 0; e < EPW; e++) {
                 cnt += inc[e];
                 hw1 += ((~((cnt ^ T1P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
-                if (m_even) hw2 += ((~((cnt ^ T2P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
                 if (!TMODE) {
+                    /* evaluate the ECDF differences only at the end of a tie run: inside a run re-evaluate the
+                     * previous run end (idempotent under max/min) */
                     const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
-                    const int keep = (int)((h >> 15) & 1u) - 1; /* 0 inside a tie run, -1 at its end */
-                    const int c0 = cnt & 1023, c1 = (cnt >> 10) & 1023, c2 = cnt >> 20;
-                    const int d01 = (c0 - c1) & keep, d02 = (c0 - c2) & keep, d12 = (c1 - c2) & keep;
+                    const unsigned tie = 0u - ((h >> 15) & 1u); /* all ones inside a tie run */
+                    ce = (ce & tie) | (cnt & ~tie);
+                    const int c0 = ce & 1023, c1 = (ce >> 10) & 1023, c2 = ce >> 20;
+                    const int d01 = c0 - c1, d02 = c0 - c2, d12 = c1 - c2;
                     mx01 = max(mx01, d01); mn01 = min(mn01, d01);
                     mx02 = max(mx02, d02); mn02 = min(mn02, d02);
                     mx12 = max(mx12, d12); mn12 = min(mn12, d12);
+                }
+            }
+            if (m_even) { /* warp-uniform: the upper middle element is a different one only for even group sizes */
+                unsigned c2nd = incl - tot;
+#pragma unroll
+                for (int e = 0; e < EPW; e++) {
+                    c2nd += inc[e];
+                    hw2 += ((~((c2nd ^ T2P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
                 }
             }
             if (!m_even) hw2 = hw1;
