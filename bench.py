@@ -179,6 +179,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL's version banner goes to stdout)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,37 +233,57 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    # result gather (the path's only exchange step): per-rank pair/gene tables -> rank 0 over NCCL
-    gather_bufs = None
+    # Result gather (the path's only exchange step): per-rank pair/gene tables -> rank 0 over NCCL, on a second
+    # stream. The gather of step i overlaps the gene kernels and the probe ranking of step i+1 (they do not touch
+    # the pair table); the pair kernel of step i+1 waits for it. The timed region ends only when the last gather
+    # has landed.
+    gather_plan = None
+    gstream = torch.cuda.Stream() if world > 1 else None
 
     def step():
-        sess.run(opts, stream)
-        if world > 1:
-            nonlocal gather_bufs
-            if gather_bufs is None:
-                gather_bufs = {}
-                for which, cols, count in ((0, 11, Np), (4, 15, G)):
-                    ptr, nbytes = sess.result_device_ptr(which)
-                    # view the library's device table as a torch tensor (no copy)
-                    t = torch.as_tensor(_DevArray(ptr, (count, cols)), device="cuda")
-                    dst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-                    gather_bufs[which] = (t, dst)
-            for t, dst in gather_bufs.values():
-                dist.gather(t, dst, dst=0)
+        nonlocal gather_plan
+        if world == 1:
+            sess.run(opts, stream)
+            return
+        if gather_plan is not None:
+            tstream.wait_event(gather_plan[4])    # the previous gene-table gather (small) has read the gene table
+        sess.run_prepare(opts, stream)
+        if gather_plan is None:
+            ptr, _ = sess.result_device_ptr(0)
+            pair_t = torch.as_tensor(_DevArray(ptr, (Np, 11)), device="cuda")   # the library's table, no copy
+            gptr, _ = sess.result_device_ptr(4)
+            gene_t = torch.as_tensor(_DevArray(gptr, (G, 15)), device="cuda")
+            pdst = [torch.empty_like(pair_t) for _ in range(world)] if rank == 0 else None
+            gdst = [torch.empty_like(gene_t) for _ in range(world)] if rank == 0 else None
+            gather_plan = (pair_t, pdst, gene_t, gdst, torch.cuda.Event())
+        pair_t, pdst, gene_t, gdst, ev_gene = gather_plan
+        tstream.wait_stream(gstream)              # previous pair-table gather done before the table is overwritten
+        sess.run_pairs(0, 1, stream)
+        gstream.wait_stream(tstream)
+        with torch.cuda.stream(gstream):
+            dist.gather(gene_t, gdst, dst=0)
+            ev_gene.record(gstream)
+            dist.gather(pair_t, pdst, dst=0)
 
+    def finish():
+        if world > 1:
+            tstream.wait_stream(gstream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
+    finish()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {"gene_sort_ms": 0.0, "gene_tests_ms": 0.0, "probe_rank_ms": 0.0, "pair_stats_ms": 0.0}
     torch.cuda.synchronize()
     ev0.record()
     for _ in range(args.steps):
         step()
+    finish()
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:

@@ -24,7 +24,8 @@ EXPORTS = [
     "epx_abi_version", "epx_device_count", "epx_device_info", "epx_options_default", "epx_host_alloc",
     "epx_host_free", "epx_session_create", "epx_session_destroy", "epx_session_set_methylation_rows",
     "epx_session_set_methylation_cols", "epx_session_set_methylation_device", "epx_session_set_expression",
-    "epx_session_set_index", "epx_session_run", "epx_session_fetch", "epx_session_timing",
+    "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
+    "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze",
 ]
 
@@ -93,6 +94,9 @@ def lib():
     L.epx_session_set_expression.argtypes = [vp, vp, i64, i64, C.c_int] + e
     L.epx_session_set_index.argtypes = [vp, vp, vp, i64] + e
     L.epx_session_run.argtypes = [vp, C.POINTER(Options), vp] + e
+    L.epx_session_run_prepare.argtypes = [vp, C.POINTER(Options), vp] + e
+    L.epx_session_run_pairs.argtypes = [vp, C.c_int, C.c_int, vp] + e
+    L.epx_session_pairs_chunk.argtypes = [vp, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)] + e
     L.epx_session_fetch.argtypes = [vp, C.POINTER(_Result), vp] + e
     L.epx_session_timing.argtypes = [vp, C.POINTER(Timing)] + e
     L.epx_session_result_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)] + e
@@ -238,6 +242,20 @@ class Session:
         b = _errbuf()
         opt = options if options is not None else make_options()
         _check(lib().epx_session_run(self._h, C.byref(opt), C.c_void_p(stream or 0), b, len(b)), b)
+
+    def run_prepare(self, options: Options | None = None, stream: int | None = None):
+        b = _errbuf()
+        opt = options if options is not None else make_options()
+        _check(lib().epx_session_run_prepare(self._h, C.byref(opt), C.c_void_p(stream or 0), b, len(b)), b)
+
+    def run_pairs(self, chunk: int, n_chunks: int, stream: int | None = None):
+        b = _errbuf()
+        _check(lib().epx_session_run_pairs(self._h, chunk, n_chunks, C.c_void_p(stream or 0), b, len(b)), b)
+
+    def pairs_chunk(self, chunk: int, n_chunks: int):
+        first, count, b = C.c_int64(), C.c_int64(), _errbuf()
+        _check(lib().epx_session_pairs_chunk(self._h, chunk, n_chunks, C.byref(first), C.byref(count), b, len(b)), b)
+        return first.value, count.value
 
     def timing(self) -> dict:
         t, b = Timing(), _errbuf()

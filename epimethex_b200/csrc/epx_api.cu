@@ -88,8 +88,10 @@ struct epx_session {
     /* timing */
     cudaEvent_t ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     cudaStream_t side = nullptr; /* gene-level kernels run here, concurrently with the probe ranking */
-    bool ran = false;
+    bool ran = false, prepared = false;
     int launches = 0;
+    PairParams pp;                      /* parameters of the pair kernel, valid after run_prepare */
+    std::vector<int32_t> item_begin;    /* host copy: first pair of every work item, plus the total as a sentinel */
     void *staging = nullptr; /* pinned */
     size_t staging_bytes = 0;
 };
@@ -341,6 +343,10 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     if (!items.empty())
         EPX_CUDA(cudaMemcpyAsync(s->items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, s->stream));
     EPX_CUDA(cudaStreamSynchronize(s->stream)); /* the vectors die with this scope */
+    s->item_begin.resize(items.size() + 1);
+    for (size_t i = 0; i < items.size(); i++) s->item_begin[i] = items[i].begin;
+    s->item_begin[items.size()] = (int32_t)Np;
+    s->prepared = false;
     s->Np = Np; s->U = (int64_t)uniq.size(); s->n_items = (int64_t)items.size(); s->G_index = n_genes;
     return EPX_OK;
 }
@@ -376,7 +382,7 @@ static int build_ks_lut(epx_session *s, int n, int m, cudaStream_t st, char *err
     return EPX_OK;
 }
 
-int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, char *err, size_t errlen)
+int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *stream, char *err, size_t errlen)
 {
     if (!s) return fail(err, errlen, EPX_EINVAL, "session is NULL");
     epx_options opt;
@@ -432,7 +438,7 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;
     pp.pair_slot = s->pair_slot.p; pp.xc = s->xc.p; pp.ldx = s->ldx; pp.lab8 = s->lab8.p; pp.ldl = s->ldl;
-    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items; pp.pair_gene = s->pair_gene.p; pp.n_pairs = (int)Np;
+    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items; pp.pair_gene = s->pair_gene.p; pp.n_pairs = (int)Np; pp.pair_begin = 0;
     pp.n = n; pp.m = m; pp.test_t = opt.test_meth_t;
     pp.exact_ok = ((double)m * (double)m < 10000.0) ? 1 : 0;
     pp.warp_smem = 0;
@@ -458,11 +464,61 @@ int epx_session_run(epx_session *s, const epx_options *opt_in, void *stream, cha
     if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[3], st));
     if (overlap) EPX_CUDA(cudaStreamWaitEvent(st, s->ev[2], 0));
-    EPX_CUDA(cudaEventRecord(s->ev[7], st));
-    if (s->n_items > 0) { EPX_CUDA(launch_pair_stats(pp, s->sm_count, st)); s->launches++; }
-    EPX_CUDA(cudaEventRecord(s->ev[4], st));
-    s->ran = true;
+    s->pp = pp;
+    s->prepared = true;
+    s->ran = false;
     return EPX_OK;
+}
+
+static void chunk_items(const epx_session *s, int chunk, int n_chunks, int64_t *i0, int64_t *i1)
+{
+    *i0 = s->n_items * chunk / n_chunks;
+    *i1 = s->n_items * (chunk + 1) / n_chunks;
+}
+
+int epx_session_pairs_chunk(epx_session *s, int chunk, int n_chunks, int64_t *first_pair, int64_t *n_pairs, char *err,
+                            size_t errlen)
+{
+    if (!s || n_chunks < 1 || chunk < 0 || chunk >= n_chunks) return fail(err, errlen, EPX_EINVAL, "bad chunk %d of %d", chunk, n_chunks);
+    if (s->G_index < 0) return fail(err, errlen, EPX_ESTATE, "no index");
+    int64_t i0, i1;
+    chunk_items(s, chunk, n_chunks, &i0, &i1);
+    const int64_t b = s->n_items ? s->item_begin[(size_t)i0] : 0, e = s->n_items ? s->item_begin[(size_t)i1] : 0;
+    if (first_pair) *first_pair = b;
+    if (n_pairs) *n_pairs = e - b;
+    return EPX_OK;
+}
+
+int epx_session_run_pairs(epx_session *s, int chunk, int n_chunks, void *stream, char *err, size_t errlen)
+{
+    if (!s || n_chunks < 1 || chunk < 0 || chunk >= n_chunks) return fail(err, errlen, EPX_EINVAL, "bad chunk %d of %d", chunk, n_chunks);
+    if (!s->prepared) return fail(err, errlen, EPX_ESTATE, "run_pairs before run_prepare");
+    EPX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    int64_t i0, i1;
+    chunk_items(s, chunk, n_chunks, &i0, &i1);
+    if (chunk == 0) EPX_CUDA(cudaEventRecord(s->ev[7], st));
+    if (i1 > i0) {
+        PairParams pp = s->pp;
+        pp.items = s->pp.items + i0;
+        pp.n_items = (int)(i1 - i0);
+        pp.pair_begin = s->item_begin[(size_t)i0];
+        pp.n_pairs = s->item_begin[(size_t)i1];
+        EPX_CUDA(launch_pair_stats(pp, s->sm_count, st));
+        s->launches++;
+    }
+    if (chunk == n_chunks - 1) {
+        EPX_CUDA(cudaEventRecord(s->ev[4], st));
+        s->ran = true;
+    }
+    return EPX_OK;
+}
+
+int epx_session_run(epx_session *s, const epx_options *opt, void *stream, char *err, size_t errlen)
+{
+    int rc = epx_session_run_prepare(s, opt, stream, err, errlen);
+    if (rc) return rc;
+    return epx_session_run_pairs(s, 0, 1, stream, err, errlen);
 }
 
 int epx_session_fetch(epx_session *s, epx_result *out, void *stream, char *err, size_t errlen)
@@ -511,7 +567,7 @@ int epx_session_timing(epx_session *s, epx_timing *out, char *err, size_t errlen
 int epx_session_result_device_ptr(epx_session *s, int which, void **ptr, int64_t *bytes, char *err, size_t errlen)
 {
     if (!s || !ptr) return fail(err, errlen, EPX_EINVAL, "NULL argument");
-    if (!s->ran) return fail(err, errlen, EPX_ESTATE, "no results yet");
+    if (!s->ran && !s->prepared) return fail(err, errlen, EPX_ESTATE, "no results yet");
     const int64_t Np = s->Np, G = s->G, n = s->n;
     void *p = nullptr; int64_t b = 0;
     switch (which) {

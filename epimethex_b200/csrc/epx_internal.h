@@ -78,7 +78,7 @@ struct PairParams {
     const Item *items;
     int n_items;
     const int32_t *pair_gene; /* [Np] gene of each pair (CTA-per-pair kernel) */
-    int n_pairs;
+    int pair_begin, n_pairs;  /* CTA-per-pair kernel: pairs [pair_begin, n_pairs) */
     int n, m;
     int test_t;
     int exact_ok;           /* m*m < 10000: exact KS p-value unless the two groups hold ties */

@@ -906,10 +906,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
         bulk_g2s(dst + rowb, p.ord + (int64_t)p.pair_slot[j] * p.ldo, ordb, &bar[stage]);
     };
     int cur_gene = -1;
-    if (tid == 0 && (int)blockIdx.x < p.n_pairs) issue(blockIdx.x, 0);
+    if (tid == 0 && p.pair_begin + (int)blockIdx.x < p.n_pairs) issue(p.pair_begin + blockIdx.x, 0);
 
     int it = 0;
-    for (int j = blockIdx.x; j < p.n_pairs; j += gridDim.x, it++) {
+    for (int j = p.pair_begin + blockIdx.x; j < p.n_pairs; j += gridDim.x, it++) {
         const int stage = STAGES == 2 ? (it & 1) : 0;
         const int pi = p.probe_idx[j];
         const int gene = p.pair_gene[j];
@@ -1277,7 +1277,8 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
         const bool two = 2 * stage + labb + 4096 <= 227 * 1024;
         const size_t smem = (two ? 2 : 1) * stage + labb;
         int grid = sm_count; /* one 512-thread CTA per SM, persistent */
-        if (grid > p.n_pairs) grid = p.n_pairs;
+        if (grid > p.n_pairs - p.pair_begin) grid = p.n_pairs - p.pair_begin;
+        if (grid < 1) return cudaSuccess;
         if (two) {
             if (p.test_t) k_pair_stats_cta<true, 2><<<grid, BIG_THREADS, smem, st>>>(p);
             else k_pair_stats_cta<false, 2><<<grid, BIG_THREADS, smem, st>>>(p);

@@ -13,7 +13,7 @@
  *   epx_session_set_methylation_*   R/EpimethexAnalysis.R:267-296  (methylation frame -> lookup table)
  *   epx_session_set_expression      R/EpimethexAnalysis.R:103-108  (transpose to samples x genes)
  *   epx_session_set_index           R/EpimethexAnalysis.R:287-291  (dfCGunique as a CSR gene->probe index)
- *   epx_session_run                 R/EpimethexAnalysis.R:117-206  (order/quantiles/bin.var/FC/gene tests),
+ *   epx_session_run (_prepare/_pairs) R/EpimethexAnalysis.R:117-206  (order/quantiles/bin.var/FC/gene tests),
  *                                   :299-311 (gather), :351-453 (Loop A: Analysis + corr.test),
  *                                   R/Functions.R:2-22,26-80,85-132,192-220
  *   epx_session_fetch               the `.combine = cbind` fold of foreach (R/EpimethexAnalysis.R:352)
@@ -155,6 +155,14 @@ int  epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t
 /* Launch the whole device pipeline asynchronously on `stream` (a cudaStream_t; NULL = the session's own
  * stream). No host<->device copies, no host synchronisation. */
 int  epx_session_run(epx_session *s, const epx_options *opt, void *stream, char *err, size_t errlen);
+/* The same pipeline in two phases, for callers that overlap the result gather with the computation (multi-GPU):
+ * run_prepare launches everything but the pair kernel; run_pairs(chunk, n_chunks) launches the pair kernel for
+ * the chunk-th of n_chunks contiguous slices of the pairs; pairs_chunk tells which rows of the pair tables that
+ * slice writes. epx_session_run == run_prepare + run_pairs(0, 1). */
+int  epx_session_run_prepare(epx_session *s, const epx_options *opt, void *stream, char *err, size_t errlen);
+int  epx_session_run_pairs(epx_session *s, int chunk, int n_chunks, void *stream, char *err, size_t errlen);
+int  epx_session_pairs_chunk(epx_session *s, int chunk, int n_chunks, int64_t *first_pair, int64_t *n_pairs,
+                             char *err, size_t errlen);
 /* Wait for `stream` and copy the result tables to the host. */
 int  epx_session_fetch(epx_session *s, epx_result *out, void *stream, char *err, size_t errlen);
 /* Timing of the last run (synchronises the events). */
