@@ -317,14 +317,17 @@ def main():
     h2d = P * n * 8 + G * n * 8 + (G + 1) * 8 + Np * 4
     d2h = Np * (11 * 8 + 2) + G * (15 * 8 + 2)
     e2e_ms = []
+    e2e_upload_ms = []
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         sess.set_methylation(wl["meth"])
+        t1 = time.perf_counter()
         sess.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts, full=False, pinned_results=True)
         dt = time.perf_counter() - t0
         if i > 0:
             e2e_ms.append(dt * 1e3)
+            e2e_upload_ms.append((t1 - t0) * 1e3)
     e2e_t = float(np.median(e2e_ms)) if e2e_ms else float("nan")  # median: host-side outliers (page faults, PCIe neighbours)
     if args.e2e_steps <= 0:
         e2e_t = float("nan")
@@ -360,7 +363,8 @@ def main():
                          "traffic_source": "ncu --set full, profiles/traffic_r01.json" if traffic else None},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_t, "steps": len(e2e_ms), "ms_each": [round(v, 2) for v in e2e_ms], "pinned_host_buffers": bool(wl["pinned"]),
+                    "ms_per_step": e2e_t, "steps": len(e2e_ms), "ms_each": [round(v, 2) for v in e2e_ms],
+                    "methylation_upload_ms": round(float(np.median(e2e_upload_ms)), 2) if e2e_upload_ms else None, "pinned_host_buffers": bool(wl["pinned"]),
                     "h2d_gbs": round(h2d / (e2e_t * 1e-3) / 1e9, 1) if e2e_t == e2e_t else None},
             "gpu_launches": int(tim["kernel_launches"]) * args.steps,
             "clocks": clocks,

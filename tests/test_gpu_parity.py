@@ -177,3 +177,43 @@ def test_full_size_properties_skcm_slice(sess):
     ref = run_oracle(x[sel], y, sub)
     got = run_gpu(sess, x[sel], y, sub, upload=False)
     assert_parity(got, ref, "skcm slice sample")
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 8])
+def test_tiny_sample_counts(sess, n):
+    """m = 1 or 2: the guard is NA (sd of one difference) -> KS still runs, Welch is NA; exact KS with m*m < 10000"""
+    x, y, idx = _synth(30, n, 200, ties=False)
+    for te, tm in ((True, False), (False, True), (False, False)):
+        got = run_gpu(sess, x, y, idx, te=te, tm=tm)
+        assert_parity(got, run_oracle(x, y, idx, te=te, tm=tm), f"n={n} te={te} tm={tm}")
+
+
+def test_degenerate_index_shapes(sess):
+    """one gene; genes without any pair; a probe listed twice in one gene; no pairs at all"""
+    rng = np.random.default_rng(11)
+    y = rng.random((12, 21))
+    x = rng.normal(5, 2, (4, 21))
+    x[2] = 7.0                                            # constant gene: sd 0 -> Pearson NA, tests NA
+    Idx = type(synth.probe_index(synth.annotation(10, 2), 0, 2))
+    def mk(row_ptr, pi):
+        return Idx(np.asarray(row_ptr, np.int64), np.asarray(pi, np.int32), None, None, None, None, None)
+    for name, xx, idx in (("one gene", x[:1], mk([0, 3], [0, 5, 5])),
+                          ("empty genes", x, mk([0, 0, 4, 6, 6], [1, 2, 3, -1, 7, 8])),
+                          ("no pairs", x, mk([0, 0, 0, 0, 0], []))):
+        got = run_gpu(sess, xx, y, idx)
+        assert_parity(got, run_oracle(xx, y, idx), name)
+
+
+def test_heavily_tied_expression(sess):
+    """RNA-seq style zeros: the Medium/Down boundary falls inside a run of ties (stable order by sample index);
+    expression-side KS with pooled ties"""
+    ann = synth.annotation(3000, 200)
+    y = synth.methylation(3000, 60, ann, threads=4)
+    idx = synth.probe_index(ann, 0, 200)
+    x = synth.expression(200, 60)
+    x[x < 4.0] = 0.0                                       # most genes now have long zero runs
+    x[:, :3] += np.arange(3)[None, :] * 1e-3 + 9.0         # keep every gene non-constant and one gene tie-free enough
+    x[0] = np.linspace(1, 60, 60)                          # a reference gene without ties (bin.var needs unique breaks)
+    for te in (True, False):
+        got = run_gpu(sess, x, y, idx, te=te)
+        assert_parity(got, run_oracle(x, y, idx, te=te), f"tied expression te={te}")

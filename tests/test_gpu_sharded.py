@@ -1,0 +1,55 @@
+"""Genes sharded over 2 GPUs of one box with the NCCL gather of the pair tables (epimethex_b200.distributed).
+Skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from epimethex_b200 import _native, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+
+    from epimethex_b200 import distributed
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ann = synth.annotation(4000, 240)
+        x = synth.expression(240, 99)
+        y = synth.methylation(4000, 99, ann, threads=2)
+        idx = synth.probe_index(ann, 0, 240)
+        sess = _native.Session(rank)
+        sess.set_methylation(y)
+        res = distributed.analyze_sharded(sess, x, idx, _native.make_options(True, True, False))
+        if rank == 0:
+            np.savez(out_path, pair=res.pair, pair_na=res.pair_na, ks_dnum=res.ks_dnum, gene=res.gene)
+        sess.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_shards_equal_one_gpu(tmp_path):
+    if _native.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "r0.npz")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    ann = synth.annotation(4000, 240)
+    x = synth.expression(240, 99); y = synth.methylation(4000, 99, ann, threads=2)
+    idx = synth.probe_index(ann, 0, 240)
+    with _native.Session(0) as sess:
+        sess.set_methylation(y)
+        one = sess.analyze(x, idx.row_ptr, idx.probe_idx, _native.make_options(True, True, False))
+    assert np.array_equal(got["pair"], one.pair, equal_nan=True)     # same kernels, same inputs: bit-identical
+    assert np.array_equal(got["pair_na"], one.pair_na) and np.array_equal(got["ks_dnum"], one.ks_dnum)
+    assert np.array_equal(got["gene"], one.gene, equal_nan=True)

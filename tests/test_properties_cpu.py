@@ -1,0 +1,66 @@
+"""Property tests of the oracle's statistics: hypothesis-generated inputs, CPU only."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+import oracle
+
+vals = st.floats(min_value=-50, max_value=50, allow_nan=False, allow_infinity=False, width=64)
+vec = lambda lo, hi: st.lists(vals, min_size=lo, max_size=hi).map(lambda v: np.array(v, dtype=np.float64))
+
+
+@settings(max_examples=150, deadline=None)
+@given(vec(1, 40), vec(1, 40))
+def test_ks_numerator_is_symmetric_and_bounded(a, b):
+    rc1, d1, p1, e1 = oracle.ks(a, b)
+    rc2, d2, p2, e2 = oracle.ks(b, a)
+    assert rc1 == rc2 == 0 and d1 == d2 and e1 == e2
+    assert 0 <= d1 <= a.size * b.size and 0.0 <= p1 <= 1.0
+    assert abs(p1 - p2) <= 1e-12
+    # invariance under a strictly increasing map of both samples
+    rc3, d3, p3, e3 = oracle.ks(3.0 * a + 1.0, 3.0 * b + 1.0)
+    if np.unique(np.concatenate([3.0 * a + 1.0, 3.0 * b + 1.0])).size == np.unique(np.concatenate([a, b])).size:
+        assert d3 == d1
+
+
+@settings(max_examples=150, deadline=None)
+@given(vec(2, 40), vec(2, 40))
+def test_welch_is_antisymmetric(a, b):
+    rc1, t1, df1, p1 = oracle.welch(a, b)
+    rc2, t2, df2, p2 = oracle.welch(b, a)
+    assert rc1 == rc2
+    if rc1 == 0:
+        assert t1 == -t2 and df1 == df2 and p1 == p2 and 0.0 <= p1 <= 1.0
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(vals, vals), min_size=3, max_size=60))
+def test_pearson_is_affine_invariant_and_bounded(xy):
+    x = np.array([p[0] for p in xy]); y = np.array([p[1] for p in xy])
+    rc, r, p = oracle.pearson(x, y)
+    if rc == 0:
+        assert -1.0 <= r <= 1.0 and 0.0 <= p <= 1.0
+        rc2, r2, p2 = oracle.pearson(2.0 * x - 3.0, -0.5 * y + 1.0)
+        if rc2 == 0 and np.ptp(x) > 1e-6 and np.ptp(y) > 1e-6:
+            assert abs(r2 + r) < 1e-7
+
+
+@settings(max_examples=100, deadline=None)
+@given(vec(3, 120))
+def test_order_is_a_stable_descending_permutation(x):
+    perm = oracle.order_desc(x)
+    assert sorted(perm.tolist()) == list(range(x.size))
+    xs = x[perm]
+    assert np.all(xs[:-1] >= xs[1:])
+    ties = xs[:-1] == xs[1:]
+    assert np.all(perm[:-1][ties] < perm[1:][ties])            # ties keep the original sample order
+    m = x.size // 3
+    groups = [set(perm[:m]), set(perm[m:2 * m]), set(perm[2 * m:3 * m])]
+    assert sum(len(g) for g in groups) == 3 * m and not (groups[0] & groups[1]) and not (groups[1] & groups[2])
+
+
+@settings(max_examples=100, deadline=None)
+@given(vec(2, 60), vec(2, 60))
+def test_guard_matches_sd_of_recycled_differences(a, b):
+    L = max(a.size, b.size)
+    d = np.array([a[i % a.size] - b[i % b.size] for i in range(L)])
+    assert oracle.guard(a, b) == (0 if np.all(d == d[0]) else 1)
