@@ -62,6 +62,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (spin > (1u << 26)) __trap();
 }
 
+/* out of line on purpose: the continued fraction + lgamma code is big, and inlining it into the pair loop pushes
+ * the kernel past the instruction cache */
+__device__ __noinline__ double t_two_sided_p_call(double t, double df) { return epx_t_two_sided_p(t, df); }
+
 constexpr int PAIR2_WARPS = 4;
 
 __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                     const double A = s_va[jj * 3 + ga], B = s_va[jj * 3 + gb], se2 = A + B;
                     t = (s_mg[jj * 3 + ga] - s_mg[jj * 3 + gb]) / sqrt(se2);
                     const double df = se2 * se2 * (dm - 1.0) / (A * A + B * B);
-                    pq = epx_t_two_sided_p(t, df);
+                    pq = t_two_sided_p_call(t, df);
                 }
                 p.pair_stat[(int64_t)(item.begin + jj) * 3 + slot] = t;
                 col = EPX_P_UP_MID + slot;
