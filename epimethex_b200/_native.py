@@ -26,7 +26,8 @@ EXPORTS = [
     "epx_session_set_methylation_cols", "epx_session_set_methylation_device", "epx_session_set_expression",
     "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
     "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
-    "epx_session_result_device_ptr", "epx_analyze",
+    "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
+    "epx_multi_set_methylation_rows", "epx_multi_analyze",
 ]
 
 ERRORS = {-1: "EPX_EINVAL", -2: "EPX_ECUDA", -3: "EPX_ENOMEM", -4: "EPX_ESTATE", -5: "EPX_EBREAKS",
@@ -101,6 +102,11 @@ def lib():
     L.epx_session_timing.argtypes = [vp, C.POINTER(Timing)] + e
     L.epx_session_result_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)] + e
     L.epx_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
+    L.epx_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)] + e
+    L.epx_multi_destroy.argtypes = [vp]
+    L.epx_multi_destroy.restype = None
+    L.epx_multi_set_methylation_rows.argtypes = [vp, vp, i64, i64, i64] + e
+    L.epx_multi_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("epx_abi_version",):
@@ -320,4 +326,55 @@ class Session:
                                  probe_idx.ctypes.data, C.byref(opt), C.byref(r), b, len(b)), b)
         res.counts, res.ref_gene = tuple(r.counts), r.ref_gene
         res.timing = self.timing()
+        return res
+
+
+class MultiSession:
+    """Several GPUs driven from this one process (what the R shim would use): genes are split by pair count,
+    every device computes its pairs and writes them straight into the host result tables."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        b = _errbuf()
+        _check(lib().epx_multi_create(devs, len(devices), C.byref(self._h), b, len(b)), b)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().epx_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_methylation(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, np.float64)
+        b = _errbuf()
+        _check(lib().epx_multi_set_methylation_rows(self._h, rows.ctypes.data, rows.shape[0], rows.shape[1],
+                                                    rows.shape[1], b, len(b)), b)
+
+    def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None) -> Result:
+        expr = np.ascontiguousarray(expr, np.float64)
+        row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        probe_idx = np.ascontiguousarray(probe_idx, np.int32)
+        G, n = expr.shape
+        Np = int(row_ptr[-1])
+        res = Result(pair=np.empty((Np, PAIR_COLS)), pair_na=np.zeros(Np, np.uint16), pair_stat=np.empty((Np, 3)),
+                     ks_dnum=np.empty((Np, 3), np.int32), gene=np.empty((G, GENE_COLS)), gene_na=np.zeros(G, np.uint16),
+                     gene_ks_dnum=np.empty((G, 3), np.int32), perm=np.empty((G, n), np.uint16))
+        r = _Result()
+        r.pair, r.pair_na, r.pair_stat, r.pair_ks_dnum = (res.pair.ctypes.data, res.pair_na.ctypes.data,
+                                                          res.pair_stat.ctypes.data, res.ks_dnum.ctypes.data)
+        r.gene, r.gene_na, r.gene_ks_dnum, r.perm = (res.gene.ctypes.data, res.gene_na.ctypes.data,
+                                                     res.gene_ks_dnum.ctypes.data, res.perm.ctypes.data)
+        opt = options if options is not None else make_options()
+        b = _errbuf()
+        _check(lib().epx_multi_analyze(self._h, expr.ctypes.data, G, n, row_ptr.ctypes.data, probe_idx.ctypes.data,
+                                       C.byref(opt), C.byref(r), b, len(b)), b)
+        res.counts, res.ref_gene = tuple(r.counts), r.ref_gene
         return res

@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "epx_internal.h"
@@ -95,6 +97,30 @@ struct epx_session {
     void *staging = nullptr; /* pinned */
     size_t staging_bytes = 0;
 };
+
+struct epx_multi {
+    std::vector<epx_session *> sess;
+};
+
+/* run fn(i) for every device on its own thread; first failure wins */
+template <typename F> static int for_each_device(epx_multi *m, F fn, char *err, size_t errlen)
+{
+    const size_t n = m->sess.size();
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; i++)
+        th.emplace_back([&, i]() {
+            char buf[512] = "";
+            rc[i] = fn((int)i, buf, sizeof buf);
+            msg[i] = buf;
+        });
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (rc[i]) return fail(err, errlen, rc[i], "device %d: %s", m->sess[i]->device, msg[i].c_str());
+    return EPX_OK;
+}
+
 
 extern "C" {
 
@@ -596,6 +622,80 @@ int epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_s
     rc = epx_session_run(s, opt, nullptr, err, errlen);
     if (rc) return rc;
     return epx_session_fetch(s, out, nullptr, err, errlen);
+}
+
+
+/* ---------------------------------------------------------------- several GPUs, one process */
+
+
+int epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *err, size_t errlen)
+{
+    if (!out || !devices || n_devices < 1) return fail(err, errlen, EPX_EINVAL, "bad device list");
+    *out = nullptr;
+    epx_multi *m = new (std::nothrow) epx_multi();
+    if (!m) return fail(err, errlen, EPX_ENOMEM, "out of host memory");
+    for (int i = 0; i < n_devices; i++) {
+        epx_session *s = nullptr;
+        int rc = epx_session_create(devices[i], &s, err, errlen);
+        if (rc) { epx_multi_destroy(m); return rc; }
+        m->sess.push_back(s);
+    }
+    *out = m;
+    return EPX_OK;
+}
+
+void epx_multi_destroy(epx_multi *m)
+{
+    if (!m) return;
+    for (epx_session *s : m->sess) epx_session_destroy(s);
+    delete m;
+}
+
+int epx_multi_set_methylation_rows(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples, int64_t ld,
+                                   char *err, size_t errlen)
+{
+    if (!m) return fail(err, errlen, EPX_EINVAL, "NULL handle");
+    return for_each_device(m, [&](int i, char *e, size_t el) {
+        return epx_session_set_methylation_rows(m->sess[(size_t)i], rows, n_probes, n_samples, ld, e, el);
+    }, err, errlen);
+}
+
+int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t n_samples, const int64_t *row_ptr,
+                      const int32_t *probe_idx, const epx_options *opt, epx_result *out, char *err, size_t errlen)
+{
+    if (!m || !expr || !row_ptr || !out || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad arguments");
+    const int W = (int)m->sess.size();
+    const int64_t Np = row_ptr[n_genes];
+    /* contiguous gene ranges with (nearly) equal pair counts */
+    std::vector<int64_t> cut((size_t)W + 1, 0);
+    cut[(size_t)W] = n_genes;
+    for (int r = 1; r < W; r++) {
+        const int64_t target = Np * r / W;
+        int64_t g = cut[(size_t)r - 1];
+        while (g < n_genes && row_ptr[g] < target) g++;
+        cut[(size_t)r] = g;
+    }
+    return for_each_device(m, [&](int i, char *e, size_t el) -> int {
+        epx_session *s = m->sess[(size_t)i];
+        const int64_t g0 = cut[(size_t)i], g1 = cut[(size_t)i + 1];
+        const int64_t lo = row_ptr[g0], hi = row_ptr[g1];
+        std::vector<int64_t> rp((size_t)n_genes + 1);
+        for (int64_t g = 0; g <= n_genes; g++) {
+            int64_t v = row_ptr[g];
+            v = v < lo ? lo : (v > hi ? hi : v);
+            rp[(size_t)g] = v - lo; /* all genes keep a row (gene kernels run everywhere); only [g0,g1) keep pairs */
+        }
+        epx_result r;
+        memset(&r, 0, sizeof r);
+        if (out->pair) r.pair = out->pair + lo * PAIR_COLS;
+        if (out->pair_na) r.pair_na = out->pair_na + lo;
+        if (out->pair_stat) r.pair_stat = out->pair_stat + lo * 3;
+        if (out->pair_ks_dnum) r.pair_ks_dnum = out->pair_ks_dnum + lo * 3;
+        if (i == 0) { r.gene = out->gene; r.gene_na = out->gene_na; r.gene_ks_dnum = out->gene_ks_dnum; r.perm = out->perm; }
+        int rc = epx_analyze(s, expr, n_genes, n_samples, rp.data(), probe_idx ? probe_idx + lo : nullptr, opt, &r, e, el);
+        if (rc == EPX_OK && i == 0) { memcpy(out->counts, r.counts, sizeof r.counts); out->ref_gene = r.ref_gene; }
+        return rc;
+    }, err, errlen);
 }
 
 } /* extern "C" */

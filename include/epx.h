@@ -172,6 +172,22 @@ int  epx_session_timing(epx_session *s, epx_timing *out, char *err, size_t errle
 int  epx_session_result_device_ptr(epx_session *s, int which, void **ptr, int64_t *bytes,
                                    char *err, size_t errlen);
 
+/* ---- several GPUs from ONE process (R is a single process; replaces the PSOCK cluster of
+ * R/EpimethexAnalysis.R:333-352 and its `.combine = cbind`) ----
+ * One session per device, each driven by its own host thread. Genes are cut into contiguous ranges with equal
+ * numbers of pairs; every device holds a replica of the methylation matrix and the whole expression matrix (the
+ * gene-level kernels run everywhere, so the bin.var reference gene needs no exchange) and computes its own pairs,
+ * which are copied straight into the caller's result tables (the destination is host memory, so no device-to-device
+ * gather is needed in this mode; the one-process-per-GPU mode of bench.py gathers over NCCL instead). */
+typedef struct epx_multi epx_multi;
+int  epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *err, size_t errlen);
+void epx_multi_destroy(epx_multi *m);
+int  epx_multi_set_methylation_rows(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples,
+                                    int64_t ld, char *err, size_t errlen);
+int  epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t n_samples,
+                       const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
+                       epx_result *out, char *err, size_t errlen);
+
 /* ---- one-shot: what `.Call(C_epx_analyze, ...)` needs ----
  * Uploads expression + index, runs, fetches. The session must already hold the methylation matrix. */
 int  epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples,

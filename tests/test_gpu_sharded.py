@@ -53,3 +53,24 @@ def test_two_gpu_shards_equal_one_gpu(tmp_path):
     assert np.array_equal(got["pair"], one.pair, equal_nan=True)     # same kernels, same inputs: bit-identical
     assert np.array_equal(got["pair_na"], one.pair_na) and np.array_equal(got["ks_dnum"], one.ks_dnum)
     assert np.array_equal(got["gene"], one.gene, equal_nan=True)
+
+
+def test_one_process_multi_gpu_equals_one_gpu():
+    """epx_multi_*: what the R `.Call` shim uses to drive all GPUs of the box from R's single process"""
+    nd = min(_native.device_count(), 4)
+    if nd < 2:
+        pytest.skip("needs 2 GPUs")
+    ann = synth.annotation(5000, 300)
+    x = synth.expression(300, 99); y = synth.methylation(5000, 99, ann, threads=2)
+    idx = synth.probe_index(ann, 0, 300)
+    with _native.Session(0) as sess:
+        sess.set_methylation(y)
+        one = sess.analyze(x, idx.row_ptr, idx.probe_idx)
+    with _native.MultiSession(list(range(nd))) as ms:
+        ms.set_methylation(y)
+        for _ in range(2):      # twice: the sessions are reused across calls
+            many = ms.analyze(x, idx.row_ptr, idx.probe_idx)
+            assert many.counts == one.counts and many.ref_gene == one.ref_gene
+            assert np.array_equal(many.pair, one.pair, equal_nan=True) and np.array_equal(many.pair_na, one.pair_na)
+            assert np.array_equal(many.ks_dnum, one.ks_dnum) and np.array_equal(many.pair_stat, one.pair_stat, equal_nan=True)
+            assert np.array_equal(many.gene, one.gene, equal_nan=True) and np.array_equal(many.perm, one.perm)
