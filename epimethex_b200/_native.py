@@ -27,7 +27,7 @@ EXPORTS = [
     "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
     "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
-    "epx_multi_set_methylation_rows", "epx_multi_analyze",
+    "epx_multi_set_methylation_rows", "epx_multi_analyze", "epx_session_run_groups", "epx_session_fetch_groups",
 ]
 
 ERRORS = {-1: "EPX_EINVAL", -2: "EPX_ECUDA", -3: "EPX_ENOMEM", -4: "EPX_ESTATE", -5: "EPX_EBREAKS",
@@ -51,6 +51,11 @@ class _Result(C.Structure):
                 ("pair_ks_dnum", C.c_void_p), ("gene", C.c_void_p), ("gene_na", C.c_void_p),
                 ("gene_ks_dnum", C.c_void_p), ("perm", C.c_void_p), ("counts", C.c_int32 * 3),
                 ("ref_gene", C.c_int32)]
+
+
+class _GroupResult(C.Structure):
+    _fields_ = [("group", C.c_void_p), ("group_na", C.c_void_p), ("group_stat", C.c_void_p),
+                ("group_ks_dnum", C.c_void_p)]
 
 
 class Timing(C.Structure):
@@ -107,6 +112,8 @@ def lib():
     L.epx_multi_destroy.restype = None
     L.epx_multi_set_methylation_rows.argtypes = [vp, vp, i64, i64, i64] + e
     L.epx_multi_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
+    L.epx_session_run_groups.argtypes = [vp, vp, vp, i64, vp] + e
+    L.epx_session_fetch_groups.argtypes = [vp, C.POINTER(_GroupResult), vp] + e
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("epx_abi_version",):
@@ -172,6 +179,14 @@ class Result:
     counts: tuple = (0, 0, 0)
     ref_gene: int = -1
     timing: dict = field(default_factory=dict)
+
+
+@dataclass
+class GroupResult:
+    group: np.ndarray        # [n_groups, 11] same columns as Result.pair
+    group_na: np.ndarray     # [n_groups] uint16 NA bit mask
+    group_stat: np.ndarray   # [n_groups, 3] Welch t or KS D
+    group_dnum: np.ndarray   # [n_groups, 3] int64 KS numerator over (k*m)^2
 
 
 class Session:
@@ -308,6 +323,31 @@ class Session:
         res.counts, res.ref_gene = tuple(r.counts), r.ref_gene
         res.timing = self.timing()
         return res
+
+    def run_groups(self, group_ptr, group_pairs, stream: int | None = None):
+        """Pooled analyses of probe groups (CG_of_a_genes / CG_by_position / CG_by_islands rows); asynchronous.
+        Call after run()/run_prepare() of the same expression + index."""
+        group_ptr = np.ascontiguousarray(group_ptr, np.int64)
+        group_pairs = np.ascontiguousarray(group_pairs, np.int32)
+        assert group_ptr.ndim == 1 and group_ptr.size >= 1 and group_pairs.size == int(group_ptr[-1])
+        self.n_groups = group_ptr.size - 1
+        b = _errbuf()
+        _check(lib().epx_session_run_groups(self._h, group_ptr.ctypes.data, group_pairs.ctypes.data, self.n_groups,
+                                            C.c_void_p(stream or 0), b, len(b)), b)
+
+    def fetch_groups(self, stream: int | None = None) -> GroupResult:
+        q = self.n_groups
+        res = GroupResult(group=np.empty((q, 11)), group_na=np.zeros(q, np.uint16), group_stat=np.empty((q, 3)),
+                          group_dnum=np.empty((q, 3), np.int64))
+        r = _GroupResult(res.group.ctypes.data, res.group_na.ctypes.data, res.group_stat.ctypes.data,
+                         res.group_dnum.ctypes.data)
+        b = _errbuf()
+        _check(lib().epx_session_fetch_groups(self._h, C.byref(r), C.c_void_p(stream or 0), b, len(b)), b)
+        return res
+
+    def analyze_groups(self, group_ptr, group_pairs) -> GroupResult:
+        self.run_groups(group_ptr, group_pairs)
+        return self.fetch_groups()
 
     def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True,
                 pinned_results: bool = False) -> Result:

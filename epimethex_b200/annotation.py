@@ -160,3 +160,74 @@ def build_probe_index(dfGpl, gene_names, methylation_ids, coord_numeric=None) ->
         cg_id, gene_rank, coord_key, pos_id, gene_of_rank, probe_row_of_cg, n_genes)
     take = lambda lst: np.asarray(lst, dtype=object)[kept_csr]
     return ProbeIndex(row_ptr, probe_idx, pair_gene, take(cg), take(pos), take(island), output_order)
+
+
+@dataclass
+class GroupIndex:
+    """Probe groups of the pooled outputs, in the reference's column order (genes by sorted name; inside a gene
+    the positions / islands in order of first appearance in ``dfCGunique``)."""
+    group_ptr: np.ndarray     # int64 [Q+1]
+    group_pairs: np.ndarray   # int32: CSR pair indices, only pairs with a data row
+    gene: np.ndarray          # int32 [Q] gene (expression order)
+    key: np.ndarray           # object [Q]: position / island value, None for by="gene"
+
+    @property
+    def n_groups(self) -> int:
+        return int(self.group_ptr.size - 1)
+
+
+def build_groups(idx: ProbeIndex, by: str = "gene") -> GroupIndex:
+    """Which probes are pooled together.
+
+    by="gene": every gene of ``dfCGunique`` (R/EpimethexAnalysis.R:476-545); a gene whose probes all lack data keeps
+    an (empty) group -> NA column (:536-541).
+    by="position" / by="island": (gene, value) sets with MORE THAN ONE data-bearing probe (R/Functions.R:146-153);
+    island values "NA_NA" or starting with "_" are skipped (R/EpimethexAnalysis.R:321).  The reference selects the
+    columns by a name it never assigned ("cg_gene" vs "cg~gene") and stops; here they are selected by
+    index, which is what the loop is written to do.
+    """
+    import re
+
+    if by not in ("gene", "position", "island"):
+        raise ValueError("by must be 'gene', 'position' or 'island'")
+    po = np.asarray(idx.output_order, np.int64)
+    if po.size == 0:
+        return GroupIndex(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, object))
+    g = np.asarray(idx.pair_gene, np.int64)[po]
+    _, first = np.unique(g, return_index=True)
+    gene_order = g[np.sort(first)]                      # genes in output order
+    grank = np.full(int(g.max()) + 1, -1, np.int64)
+    grank[gene_order] = np.arange(gene_order.size)
+    has = np.asarray(idx.probe_idx)[po] >= 0
+    if by == "gene":
+        sel = np.nonzero(has)[0]
+        counts = np.bincount(grank[g[sel]], minlength=gene_order.size)
+        order = sel[np.argsort(grank[g[sel]], kind="stable")]
+        ptr = np.zeros(gene_order.size + 1, np.int64)
+        np.cumsum(counts, out=ptr[1:])
+        return GroupIndex(ptr, po[order].astype(np.int32), gene_order.astype(np.int32),
+                          np.full(gene_order.size, None, object))
+    vals = (idx.position if by == "position" else idx.island)[po]
+    codes, names = {}, []
+    kc = np.empty(po.size, np.int64)
+    for i, v in enumerate(vals.tolist()):
+        c = codes.get(v)
+        if c is None:
+            c = codes[v] = len(names)
+            names.append(v)
+        kc[i] = c
+    valid = np.ones(len(names), bool)
+    if by == "island":
+        valid = np.array([re.search(r"NA_NA|^_", str(v)) is None for v in names], bool)
+    sel = np.nonzero(has & valid[kc])[0]
+    comp = grank[g[sel]] * len(names) + kc[sel]
+    order = sel[np.argsort(comp, kind="stable")]
+    uniq, start, cnt = np.unique(comp[np.argsort(comp, kind="stable")], return_index=True, return_counts=True)
+    keep = cnt > 1
+    pieces = [order[s:s + c] for s, c in zip(start[keep], cnt[keep])]
+    ptr = np.zeros(int(keep.sum()) + 1, np.int64)
+    np.cumsum(cnt[keep], out=ptr[1:])
+    pairs = po[np.concatenate(pieces)] if pieces else np.zeros(0, np.int64)
+    genes = gene_order[uniq[keep] // len(names)].astype(np.int32)
+    keys = np.asarray(names, dtype=object)[uniq[keep] % len(names)] if len(names) else np.zeros(0, object)
+    return GroupIndex(ptr, pairs.astype(np.int32), genes, keys)

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -96,6 +97,17 @@ struct epx_session {
     std::vector<int32_t> item_begin;    /* host copy: first pair of every work item, plus the total as a sentinel */
     void *staging = nullptr; /* pinned */
     size_t staging_bytes = 0;
+    /* pooled probe groups (epx_session_run_groups) */
+    std::vector<int32_t> h_probe_idx, h_pair_gene; /* host copies of the index, to validate group lists */
+    DevBuf<GroupDesc> g_desc;
+    DevBuf<BlockDesc> g_blocks;
+    DevBuf<TileDesc> g_tiles;
+    DevBuf<int32_t> g_pairs, g_guard;
+    DevBuf<double> g_val[2], grp, grp_stat;
+    DevBuf<uint8_t> g_lab[2];
+    DevBuf<uint16_t> grp_na;
+    DevBuf<int64_t> grp_dnum;
+    int64_t n_groups = -1;
 };
 
 struct epx_multi {
@@ -204,6 +216,9 @@ void epx_session_destroy(epx_session *s)
     s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->nuniq.release(); s->scal.release();
     s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
     s->pair_dnum.release(); s->gene_dnum.release();
+    s->g_desc.release(); s->g_blocks.release(); s->g_tiles.release(); s->g_pairs.release(); s->g_guard.release();
+    s->g_val[0].release(); s->g_val[1].release(); s->g_lab[0].release(); s->g_lab[1].release();
+    s->grp.release(); s->grp_stat.release(); s->grp_na.release(); s->grp_dnum.release();
     for (int i = 0; i < 8; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->side) cudaStreamDestroy(s->side);
     if (s->staging) cudaFreeHost(s->staging);
@@ -372,6 +387,9 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     s->item_begin.resize(items.size() + 1);
     for (size_t i = 0; i < items.size(); i++) s->item_begin[i] = items[i].begin;
     s->item_begin[items.size()] = (int32_t)Np;
+    s->h_probe_idx.assign(probe_idx, probe_idx + Np);
+    s->h_pair_gene.swap(pair_gene);
+    s->n_groups = -1;
     s->prepared = false;
     s->Np = Np; s->U = (int64_t)uniq.size(); s->n_items = (int64_t)items.size(); s->G_index = n_genes;
     return EPX_OK;
@@ -609,6 +627,121 @@ int epx_session_result_device_ptr(epx_session *s, int which, void **ptr, int64_t
     }
     *ptr = p;
     if (bytes) *bytes = b;
+    return EPX_OK;
+}
+
+/* ---------------------------------------------------------------- pooled probe groups */
+
+int epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32_t *group_pairs, int64_t n_groups,
+                           void *stream, char *err, size_t errlen)
+{
+    if (!s || !group_ptr || n_groups < 0) return fail(err, errlen, EPX_EINVAL, "bad group arguments");
+    if (!s->prepared && !s->ran) return fail(err, errlen, EPX_ESTATE, "run_groups before run / run_prepare");
+    if (n_groups > 0x7fffffff || group_ptr[0] != 0) return fail(err, errlen, EPX_EINVAL, "bad group_ptr");
+    const int64_t L = group_ptr[n_groups];
+    if (L < 0 || L > 0x7fffffff || (L > 0 && !group_pairs)) return fail(err, errlen, EPX_EINVAL, "bad group pair list");
+    EPX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const int n = (int)s->n, m = n / 3;
+    const int cap = group_block_cap(n), rpb = cap / n > 0 ? cap / n : 1;
+
+    std::vector<GroupDesc> desc((size_t)n_groups);
+    std::vector<BlockDesc> blocks;
+    int64_t elem = 0;
+    int max_blocks = 1;
+    for (int64_t q = 0; q < n_groups; q++) {
+        const int64_t b = group_ptr[q], e = group_ptr[q + 1];
+        if (e < b || e > L) return fail(err, errlen, EPX_EINVAL, "group_ptr is not monotone at group %lld", (long long)q);
+        GroupDesc &d = desc[(size_t)q];
+        d.k = (int32_t)(e - b); d.first = (int32_t)b; d.elem = elem; d.gene = 0; d.nblocks = 0;
+        if (d.k == 0) continue;
+        for (int64_t j = b; j < e; j++) {
+            const int32_t pr = group_pairs[j];
+            if (pr < 0 || pr >= s->Np) return fail(err, errlen, EPX_EINVAL, "group %lld names pair %d outside [0,%lld)", (long long)q, pr, (long long)s->Np);
+            if (s->h_probe_idx[(size_t)pr] < 0) return fail(err, errlen, EPX_EINVAL, "group %lld names pair %d, which has no data row", (long long)q, pr);
+            if (s->h_pair_gene[(size_t)pr] != s->h_pair_gene[(size_t)group_pairs[b]])
+                return fail(err, errlen, EPX_EINVAL, "group %lld mixes genes %d and %d", (long long)q, s->h_pair_gene[(size_t)group_pairs[b]], s->h_pair_gene[(size_t)pr]);
+        }
+        d.gene = s->h_pair_gene[(size_t)group_pairs[b]];
+        d.nblocks = (d.k + rpb - 1) / rpb;
+        if (d.nblocks > max_blocks) max_blocks = d.nblocks;
+        for (int r0 = 0; r0 < d.k; r0 += rpb) {
+            BlockDesc bd;
+            bd.group = (int32_t)q; bd.r0 = r0; bd.runs = d.k - r0 < rpb ? d.k - r0 : rpb; bd.pad = 0;
+            blocks.push_back(bd);
+        }
+        elem += (int64_t)d.k * n;
+    }
+    /* merge tiles, groups with the most runs first: pass p merges the groups with more than 2^p runs = a prefix */
+    std::vector<int32_t> multi;
+    for (int64_t q = 0; q < n_groups; q++) if (desc[(size_t)q].nblocks > 1) multi.push_back((int32_t)q);
+    std::sort(multi.begin(), multi.end(), [&](int32_t a, int32_t b) {
+        return desc[(size_t)a].nblocks != desc[(size_t)b].nblocks ? desc[(size_t)a].nblocks > desc[(size_t)b].nblocks : a < b; });
+    const int64_t tile = 256 * 16; /* MERGE_TILE */
+    std::vector<TileDesc> tiles;
+    int passes = 0;
+    while ((1 << passes) < max_blocks) passes++;
+    std::vector<int64_t> pass_tiles((size_t)passes, 0);
+    for (int32_t q : multi) {
+        const GroupDesc &d = desc[(size_t)q];
+        const int64_t N = (int64_t)d.k * n, nt = (N + tile - 1) / tile;
+        for (int64_t t = 0; t < nt; t++) { TileDesc td; td.group = q; td.tile = (int32_t)t; tiles.push_back(td); }
+        for (int p = 0; p < passes; p++) if (d.nblocks > (1 << p)) pass_tiles[(size_t)p] = (int64_t)tiles.size();
+    }
+    if (tiles.size() > 0x7fffffffu || blocks.size() > 0x7fffffffu) return fail(err, errlen, EPX_EINVAL, "too many group blocks");
+
+    EPX_CUDA(s->g_desc.reserve(desc.size()));
+    EPX_CUDA(s->g_blocks.reserve(blocks.size()));
+    EPX_CUDA(s->g_tiles.reserve(tiles.size()));
+    EPX_CUDA(s->g_pairs.reserve((size_t)L));
+    EPX_CUDA(s->g_guard.reserve((size_t)n_groups * 3));
+    EPX_CUDA(s->grp.reserve((size_t)n_groups * PAIR_COLS));
+    EPX_CUDA(s->grp_stat.reserve((size_t)n_groups * 3));
+    EPX_CUDA(s->grp_na.reserve((size_t)n_groups));
+    EPX_CUDA(s->grp_dnum.reserve((size_t)n_groups * 3));
+    for (int i = 0; i < 2; i++) {
+        if (i == 1 && passes == 0) break;
+        EPX_CUDA(s->g_val[i].reserve((size_t)elem));
+        EPX_CUDA(s->g_lab[i].reserve((size_t)elem));
+    }
+    if (!desc.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_desc.p, desc.data(), desc.size() * sizeof(GroupDesc), cudaMemcpyHostToDevice, st));
+    if (!blocks.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_blocks.p, blocks.data(), blocks.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+    if (!tiles.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    if (L) EPX_CUDA(cudaMemcpyAsync(s->g_pairs.p, group_pairs, (size_t)L * 4, cudaMemcpyHostToDevice, st));
+    EPX_CUDA(cudaStreamSynchronize(st)); /* the vectors die with this scope */
+
+    GroupParams gp;
+    gp.meth = s->meth; gp.ld = s->ld; gp.probe_idx = s->probe_idx.p; gp.group_pairs = s->g_pairs.p;
+    gp.groups = s->g_desc.p; gp.blocks = s->g_blocks.p; gp.tiles = s->g_tiles.p;
+    gp.n_groups = (int)n_groups; gp.n_blocks = (int)blocks.size();
+    gp.n = n; gp.m = m; gp.cap = cap; gp.test_t = s->pp.test_t;
+    gp.perm = s->perm.p; gp.lab8 = s->lab8.p; gp.ldl = s->ldl; gp.xc = s->xc.p; gp.ldx = s->ldx; gp.gene_aux = s->gene_aux.p;
+    gp.val[0] = s->g_val[0].p; gp.val[1] = s->g_val[1].p; gp.lab[0] = s->g_lab[0].p; gp.lab[1] = s->g_lab[1].p;
+    gp.guard = s->g_guard.p; gp.grp = s->grp.p; gp.grp_na = s->grp_na.p; gp.grp_stat = s->grp_stat.p; gp.grp_dnum = s->grp_dnum.p;
+    gp.one = 1u;
+    EPX_CUDA(launch_group_moments(gp, st)); s->launches++;
+    EPX_CUDA(launch_group_blocksort(gp, st)); s->launches++;
+    for (int p = 0; p < passes; p++) {
+        EPX_CUDA(launch_group_merge(gp, p, ((int64_t)rpb * n) << p, (int)pass_tiles[(size_t)p], st));
+        s->launches++;
+    }
+    EPX_CUDA(launch_group_walk(gp, st)); s->launches++;
+    s->n_groups = n_groups;
+    return EPX_OK;
+}
+
+int epx_session_fetch_groups(epx_session *s, epx_group_result *out, void *stream, char *err, size_t errlen)
+{
+    if (!s || !out) return fail(err, errlen, EPX_EINVAL, "NULL argument");
+    if (s->n_groups < 0) return fail(err, errlen, EPX_ESTATE, "fetch_groups before run_groups");
+    EPX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const size_t Q = (size_t)s->n_groups;
+    if (out->group && Q) EPX_CUDA(cudaMemcpyAsync(out->group, s->grp.p, Q * PAIR_COLS * 8, cudaMemcpyDeviceToHost, st));
+    if (out->group_na && Q) EPX_CUDA(cudaMemcpyAsync(out->group_na, s->grp_na.p, Q * 2, cudaMemcpyDeviceToHost, st));
+    if (out->group_stat && Q) EPX_CUDA(cudaMemcpyAsync(out->group_stat, s->grp_stat.p, Q * 24, cudaMemcpyDeviceToHost, st));
+    if (out->group_ks_dnum && Q) EPX_CUDA(cudaMemcpyAsync(out->group_ks_dnum, s->grp_dnum.p, Q * 24, cudaMemcpyDeviceToHost, st));
+    EPX_CUDA(cudaStreamSynchronize(st));
     return EPX_OK;
 }
 

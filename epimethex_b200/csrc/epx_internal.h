@@ -93,6 +93,49 @@ struct PairParams {
     int32_t *pair_dnum;     /* [Np][3] */
 };
 
+/* ---- pooled probe groups (epx_group.cuh) ---- */
+struct GroupDesc {
+    int32_t gene;
+    int32_t k;        /* probes (all with data) */
+    int32_t first;    /* offset of the group's pair list in group_pairs */
+    int32_t nblocks;  /* sorted runs written by k_group_blocksort */
+    int64_t elem;     /* offset of the group's k*n stacked values in the work buffers */
+};
+struct BlockDesc { int32_t group, r0, runs, pad; };   /* probes [r0, r0 + runs) of a group */
+struct TileDesc { int32_t group, tile; };             /* MERGE_TILE outputs of one group */
+
+struct GroupParams {
+    const double *meth;
+    int64_t ld;
+    const int32_t *probe_idx;
+    const int32_t *group_pairs;
+    const GroupDesc *groups;
+    const BlockDesc *blocks;
+    const TileDesc *tiles;
+    int n_groups, n_blocks;
+    int n, m, cap, test_t;
+    const uint16_t *perm;
+    const uint8_t *lab8;
+    int64_t ldl;
+    const double *xc;
+    int64_t ldx;
+    const double *gene_aux;
+    double *val[2];         /* ping-pong: stacked values of every group, ascending inside sorted runs */
+    uint8_t *lab[2];        /* their labels */
+    int32_t *guard;         /* [n_groups][3] calculateTtest guard: 1 differs, 0 all equal, -1 NA */
+    double *grp;            /* [n_groups][11] */
+    uint16_t *grp_na;
+    double *grp_stat;       /* [n_groups][3] */
+    int64_t *grp_dnum;      /* [n_groups][3] */
+    unsigned one;
+};
+
+cudaError_t launch_group_moments(const GroupParams &p, cudaStream_t st);
+cudaError_t launch_group_blocksort(const GroupParams &p, cudaStream_t st);
+cudaError_t launch_group_merge(const GroupParams &p, int pass, int64_t run_len, int n_tiles, cudaStream_t st);
+cudaError_t launch_group_walk(const GroupParams &p, cudaStream_t st);
+int group_block_cap(int n);      /* entries of one k_group_blocksort block */
+
 cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st);
 cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_t st);

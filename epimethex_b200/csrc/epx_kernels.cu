@@ -16,6 +16,7 @@
 #include "epx_warpsort.cuh"
 #include "epx_ctasort.cuh"
 #include "epx_pair.cuh"
+#include "epx_group.cuh"
 
 namespace epx {
 
@@ -1156,7 +1157,36 @@ cudaError_t kernels_init()
     if ((e = allow_max_dynamic_smem(k_pair_stats2<E, false>)) != cudaSuccess) return e;
     EPX_FOR_PAIR2_VARIANTS(EPX_PAIR2_ATTR)
 #undef EPX_PAIR2_ATTR
+    if ((e = allow_max_dynamic_smem(k_group_blocksort)) != cudaSuccess) return e;
     return cudaSuccess;
+}
+
+/* ---- pooled probe groups ---- */
+int group_block_cap(int n) { return n <= 8192 ? 8192 : ctasort_entries(n); }
+
+cudaError_t launch_group_moments(const GroupParams &p, cudaStream_t st)
+{
+    if (p.n_groups <= 0) return cudaSuccess;
+    k_group_moments<<<p.n_groups, GROUP_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_group_blocksort(const GroupParams &p, cudaStream_t st)
+{
+    if (p.n_blocks <= 0) return cudaSuccess;
+    k_group_blocksort<<<p.n_blocks, CTASORT_THREADS, group_sort_smem(p.cap), st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_group_merge(const GroupParams &p, int pass, int64_t run_len, int n_tiles, cudaStream_t st)
+{
+    if (n_tiles <= 0) return cudaSuccess;
+    k_group_merge<<<n_tiles, GROUP_THREADS, 0, st>>>(p, pass, run_len);
+    return cudaGetLastError();
+}
+cudaError_t launch_group_walk(const GroupParams &p, cudaStream_t st)
+{
+    if (p.n_groups <= 0) return cudaSuccess;
+    k_group_walk<<<p.n_groups, GROUP_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
 }
 
 static int sort_eps(int n)

@@ -188,6 +188,25 @@ int  epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_
                        const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
                        epx_result *out, char *err, size_t errlen);
 
+/* ---- pooled probe groups: the rows of CG_of_a_genes.csv, CG_by_position.csv, CG_by_islands.csv ----
+ * Replaces Loops B, C and D of the reference (R/EpimethexAnalysis.R:476-545 and :549-620 with
+ * AnalysisIslands_PositionsCG, R/Functions.R:136-188): the probe columns of a group are stacked, the
+ * stratification is recycled down the stack, then the same Analysis + corr.test as for one probe.
+ * Group q = pairs group_pairs[group_ptr[q] .. group_ptr[q+1]) (indices into the probe_idx of the current
+ * index), all of ONE gene and all with a data row (probe_idx >= 0); an empty group gives an all-NA row
+ * (R/EpimethexAnalysis.R:536-541). Which groups exist (every gene; (gene, position) / (gene, island) with more
+ * than one data-bearing probe, R/Functions.R:153; islands "NA_NA" / "_*" skipped, R/EpimethexAnalysis.R:321) is
+ * decided by the caller. Call after epx_session_run / run_prepare of the same expression + index. */
+typedef struct epx_group_result {
+    double   *group;        /* [n_groups * 11] columns as epx_result.pair */
+    uint16_t *group_na;     /* [n_groups] NA bit mask */
+    double   *group_stat;   /* [n_groups * 3] Welch t or KS D */
+    int64_t  *group_ks_dnum;/* [n_groups * 3] KS numerator over (k*m)^2, -1 when no KS test ran */
+} epx_group_result;
+int  epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32_t *group_pairs,
+                            int64_t n_groups, void *stream, char *err, size_t errlen);
+int  epx_session_fetch_groups(epx_session *s, epx_group_result *out, void *stream, char *err, size_t errlen);
+
 /* ---- one-shot: what `.Call(C_epx_analyze, ...)` needs ----
  * Uploads expression + index, runs, fetches. The session must already hold the methylation matrix. */
 int  epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples,

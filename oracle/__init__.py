@@ -203,3 +203,40 @@ def analyze(expr, meth, row_ptr, probe_idx, *, data_linear=True, test_expr_t=Tru
     res.counts = tuple(int(v) for v in counts)
     res.ref_gene = int(ref.value)
     return res
+
+
+@dataclass
+class GroupResult:
+    group: np.ndarray       # [n_groups, 11] same columns as the pair table
+    group_na: np.ndarray    # [n_groups] uint16 bit mask
+    group_stat: np.ndarray  # [n_groups, 3] Welch t or KS D
+    group_dnum: np.ndarray  # [n_groups, 3] int64 KS numerator over (k*m)^2, -1 = no KS
+
+
+def analyze_groups(expr, meth, row_ptr, probe_idx, group_ptr, group_pairs, *, test_meth_t=False, threads=1) -> GroupResult:
+    """Pooled analyses (CG_of_a_genes / by position / by island): see epo_analyze_groups in epx_oracle.h."""
+    expr = np.ascontiguousarray(expr, np.float64)
+    G, n = expr.shape
+    meth = np.asarray(meth, np.float64)
+    assert meth.ndim == 2 and meth.strides[1] == 8 and meth.shape[1] >= n
+    ld = meth.strides[0] // 8 if meth.shape[0] > 1 else meth.shape[1]
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    probe_idx = np.ascontiguousarray(probe_idx, np.int32)
+    group_ptr = np.ascontiguousarray(group_ptr, np.int64)
+    group_pairs = np.ascontiguousarray(group_pairs, np.int32)
+    ng = group_ptr.size - 1
+    assert group_pairs.size == int(group_ptr[-1])
+    res = GroupResult(group=np.empty((ng, PAIR_COLS)), group_na=np.zeros(ng, np.uint16),
+                      group_stat=np.empty((ng, 3)), group_dnum=np.empty((ng, 3), np.int64))
+    opt = _Options(1, 1, int(test_meth_t), 0, int(threads))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    L = lib()
+    L.epo_analyze_groups.restype = C.c_int
+    L.epo_analyze_groups.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    rc = L.epo_analyze_groups(vp(expr), n, G, vp(meth), ld, vp(row_ptr), vp(probe_idx), C.cast(C.byref(opt), C.c_void_p),
+                              ng, vp(group_ptr), vp(group_pairs), vp(res.group), vp(res.group_na), vp(res.group_stat),
+                              vp(res.group_dnum))
+    if rc != 0:
+        raise ValueError(f"epo_analyze_groups failed with code {rc}")
+    return res

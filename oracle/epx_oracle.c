@@ -546,3 +546,103 @@ int epo_analyze(const double *expr, int64_t n64, int64_t G,
     free(perm); free(xs); free(nuniq);
     return 0;
 }
+
+/* ------------------------------------------------------------------ pooled groups (Loops B, C, D) */
+
+/*
+ * R/EpimethexAnalysis.R:476-545 (CG_of_a_genes: all probes of a gene), :549-620 with R/Functions.R:136-188
+ * (CG_by_position / CG_by_islands: the probes of one gene that share a RefGene group / island relation).
+ * A group is a list of data-bearing pairs of ONE gene.  Their columns, each in the gene's sample order, are
+ * stacked (`stack()`, :504 / R/Functions.R:156) and the n-row stratification frame is recycled down the k*n rows
+ * (`cbind`, :508), so probe j contributes its first m = n/3 ranks to UP, the next m to Medium, the next m to Down;
+ * then Analysis (R/Functions.R:85-132) and psych::corr.test of rep(sorted expression, k) against the stack
+ * (:517-524, R/Functions.R:166-171).
+ */
+int epo_analyze_groups(const double *expr, int64_t n64, int64_t G,
+                       const double *meth, int64_t meth_ld,
+                       const int64_t *row_ptr, const int32_t *probe_idx,
+                       const epo_options *opt,
+                       int64_t n_groups, const int64_t *group_ptr, const int32_t *group_pairs,
+                       double *grp, uint16_t *grp_na, double *grp_stat, int64_t *grp_dnum)
+{
+    if (!expr || !meth || !opt || !row_ptr || !probe_idx || !group_ptr || n64 < 3 || n64 > 32767 || G < 1) return -1;
+    const int n = (int)n64, m = n / 3;
+    int threads = opt->threads > 0 ? opt->threads : 1;
+#ifndef _OPENMP
+    (void)threads;
+#endif
+    int bad = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (int64_t q = 0; q < n_groups; q++) {
+        const int64_t k64 = group_ptr[q + 1] - group_ptr[q];
+        double o[EPO_PAIR_COLS], st[3] = { NAN, NAN, NAN };
+        int64_t dn[3] = { -1, -1, -1 };
+        uint16_t mask = 0;
+        if (k64 <= 0) { /* :536-541: no probe with data -> a column of NA */
+            for (int c = 0; c < EPO_PAIR_COLS; c++) o[c] = NAN;
+            mask = (uint16_t)((1u << EPO_PAIR_COLS) - 1);
+        } else {
+            const int k = (int)k64;
+            const int32_t *pl = group_pairs + group_ptr[q];
+            /* the gene of the group = the CSR row that holds its first pair */
+            int64_t lo = 0, hi = G;
+            while (hi - lo > 1) { int64_t mid = (lo + hi) / 2; if (row_ptr[mid] <= pl[0]) lo = mid; else hi = mid; }
+            const int64_t g = lo;
+            int ok = 1;
+            for (int j = 0; j < k; j++)
+                if (pl[j] < row_ptr[g] || pl[j] >= row_ptr[g + 1] || probe_idx[pl[j]] < 0) ok = 0;
+            if (!ok) {
+#pragma omp atomic write
+                bad = 1;
+                continue;
+            }
+            int32_t *pg = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+            epo_order_desc(expr + g * n, n, pg);
+            const size_t M = (size_t)k * m, N = (size_t)k * n;
+            double *up = (double *)malloc(3 * M * sizeof(double) + 8), *mid = up + M, *down = mid + M;
+            double *xs = (double *)malloc(N * sizeof(double)), *ys = (double *)malloc(N * sizeof(double));
+            for (int j = 0; j < k; j++) {
+                const double *row = meth + (int64_t)probe_idx[pl[j]] * meth_ld;
+                for (int i = 0; i < n; i++) {
+                    const double v = row[pg[i]];
+                    xs[(size_t)j * n + i] = expr[g * n + pg[i]];
+                    ys[(size_t)j * n + i] = v;
+                    if (i < m) up[(size_t)j * m + i] = v;
+                    else if (i < 2 * m) mid[(size_t)j * m + i - m] = v;
+                    else if (i < 3 * m) down[(size_t)j * m + i - 2 * m] = v;
+                }
+            }
+            const int Mi = (int)M;
+            o[EPO_MEDIAN_DOWN] = epo_median(down, Mi);
+            o[EPO_MEDIAN_MEDIUM] = epo_median(mid, Mi);
+            o[EPO_MEDIAN_UP] = epo_median(up, Mi);
+            o[EPO_BD_UP_MID] = o[EPO_MEDIAN_UP] - o[EPO_MEDIAN_MEDIUM];
+            o[EPO_BD_UP_DOWN] = o[EPO_MEDIAN_UP] - o[EPO_MEDIAN_DOWN];
+            o[EPO_BD_MID_DOWN] = o[EPO_MEDIAN_MEDIUM] - o[EPO_MEDIAN_DOWN];
+            int na[3]; int32_t d32;
+            const double *A[3] = { up, up, mid }, *B[3] = { mid, down, down };
+            for (int c = 0; c < 3; c++) {
+                /* calc_test keeps a 32-bit numerator; pooled groups need 64 bits, so KS is called directly */
+                st[c] = NAN; o[EPO_P_UP_MID + c] = NAN; na[c] = 1;
+                const int gd = epo_guard(A[c], Mi, B[c], Mi);
+                if (opt->test_meth_t) {
+                    calc_test(A[c], Mi, B[c], Mi, 1, &st[c], &o[EPO_P_UP_MID + c], &d32, &na[c]);
+                } else if (gd != 0) {
+                    int64_t d; double pv;
+                    if (epo_ks(A[c], Mi, B[c], Mi, &d, &pv, NULL) == 0) {
+                        dn[c] = d; st[c] = (double)d / ((double)Mi * (double)Mi); o[EPO_P_UP_MID + c] = pv; na[c] = 0;
+                    }
+                }
+                if (na[c]) mask |= (uint16_t)(1u << (EPO_P_UP_MID + c));
+            }
+            if (epo_pearson(xs, ys, (int)N, &o[EPO_PEARSON_R], &o[EPO_PEARSON_P]) != 0)
+                mask |= (uint16_t)((1u << EPO_PEARSON_R) | (1u << EPO_PEARSON_P));
+            free(pg); free(up); free(xs); free(ys);
+        }
+        if (grp) memcpy(grp + q * EPO_PAIR_COLS, o, sizeof(o));
+        if (grp_na) grp_na[q] = mask;
+        if (grp_stat) memcpy(grp_stat + q * 3, st, sizeof(st));
+        if (grp_dnum) memcpy(grp_dnum + q * 3, dn, sizeof(dn));
+    }
+    return bad ? -3 : 0;
+}

@@ -122,6 +122,21 @@ int epo_analyze(const double *expr, int64_t n, int64_t G,
                 double *gene, uint16_t *gene_na, int32_t *gene_ks_dnum,
                 int32_t *perm, int32_t counts[3], int32_t *ref_gene);
 
+/*
+ * Pooled analyses of probe groups: CG_of_a_genes (R/EpimethexAnalysis.R:476-545), CG_by_position and
+ * CG_by_islands (:549-620, R/Functions.R:136-188).  Group q = pairs group_pairs[group_ptr[q] .. group_ptr[q+1]),
+ * indices into probe_idx, all of ONE gene and all with a data row (probe_idx >= 0); an empty group yields an
+ * all-NA row.  Output tables like the pair tables: grp [n_groups][11], grp_na, grp_stat [.][3] (Welch t or KS D),
+ * grp_dnum [.][3] (64-bit KS numerator over (k*m)^2).  Returns -3 when a group mixes genes or names a pair
+ * without data.
+ */
+int epo_analyze_groups(const double *expr, int64_t n, int64_t G,
+                       const double *meth, int64_t meth_ld,
+                       const int64_t *row_ptr, const int32_t *probe_idx,
+                       const epo_options *opt,
+                       int64_t n_groups, const int64_t *group_ptr, const int32_t *group_pairs,
+                       double *grp, uint16_t *grp_na, double *grp_stat, int64_t *grp_dnum);
+
 #ifdef __cplusplus
 }
 #endif
