@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pooled", default="", choices=["", "gene", "position", "island"],
+                    help="also time the pooled probe-group pass (CG_of_a_genes / by position / by island rows)")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: seconds for warmup + steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -300,6 +302,39 @@ def main():
         t = sess.timing()
         for k in kern:
             kern[k] += t[k] / reps
+    pooled = None
+    if args.pooled and world == 1:
+        from epimethex_b200.annotation import build_groups
+        gi = build_groups(idx, args.pooled)
+        sess.run(opts, stream)
+        for _ in range(2):
+            sess.run_groups(gi.group_ptr, gi.group_pairs, stream)
+        torch.cuda.synchronize()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        psteps = 5
+        pe0.record()
+        for _ in range(psteps):
+            sess.run_groups(gi.group_ptr, gi.group_pairs, stream)
+        pe1.record()
+        torch.cuda.synchronize()
+        pms = pe0.elapsed_time(pe1) / psteps
+        sizes = np.diff(gi.group_ptr)
+        pooled = {"by": args.pooled, "groups": int(gi.n_groups), "stacked_probes": int(gi.group_pairs.size),
+                  "largest_group": int(sizes.max()) if sizes.size else 0, "ms_per_pass": round(pms, 3),
+                  "stacked_probes_per_s": gi.group_pairs.size / (pms * 1e-3), "includes": "host descriptor build + upload"}
+        if not args.no_cpu_baseline:
+            # the oracle's pooled pass on every s-th group (bounded), all host cores
+            import oracle
+            stride = max(1, int(gi.group_pairs.size // 12000))
+            pick = np.arange(0, gi.n_groups, stride)
+            gp = np.zeros(pick.size + 1, np.int64)
+            np.cumsum(sizes[pick], out=gp[1:])
+            gl = np.concatenate([gi.group_pairs[gi.group_ptr[q]:gi.group_ptr[q + 1]] for q in pick]).astype(np.int32)
+            t0 = time.perf_counter()
+            oracle.analyze_groups(wl["expr"], wl["meth"], idx.row_ptr, idx.probe_idx, gp, gl, test_meth_t=wl["w"]["tm"], threads=cores)
+            dt = time.perf_counter() - t0
+            pooled["cpu_baseline"] = {"value": gl.size / dt, "unit": "stacked probes/s", "cores": cores, "kind": "port",
+                                      "sample": f"every {stride}th group: {pick.size} groups, {gl.size} stacked probes, {dt:.1f} s"}
     clocks = sampler.stop()
     if world > 1:
         tmax = torch.tensor([ms], device="cuda")
@@ -370,6 +405,8 @@ def main():
             "clocks": clocks,
             "setup_s": round(wl["gen_s"], 1),
         }
+        if pooled:
+            line["pooled"] = pooled
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(wl, args.cpu_seconds, cores)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

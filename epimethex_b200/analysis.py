@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _native
-from .annotation import ProbeIndex, build_probe_index
+from .annotation import GroupIndex, ProbeIndex, build_groups, build_probe_index
 
 OUTPUT_COLUMNS = [
     "medianDown", "medianMedium", "medianUP", "bd_UPvsMID", "bd_UPvsDOWN", "bd_MIDvsDOWN",
@@ -105,9 +105,42 @@ def assemble_table(prep: PreparedInputs, res):
     return df
 
 
-def write_csv_like_r(df, path: str) -> None:
+GROUP_TABLES = {  # output file, grouping, column-name prefix rule
+    "genes": ("CG_of_a_genes.csv", "gene"),          # R/EpimethexAnalysis.R:476-545
+    "position": ("CG_by_position.csv", "position"),  # :549-582
+    "islands": ("CG_by_islands.csv", "island"),      # :585-620
+}
+
+
+def assemble_group_table(prep: PreparedInputs, res, gi: GroupIndex, gres, by: str):
+    """The pooled tables: 17 numeric rows per group, transposed (R/EpimethexAnalysis.R:543-545, :573-577). Names:
+    ``CG~gene`` (:529) for the per-gene pool, ``<position>_<gene>`` / ``<island>_<gene>`` (R/Functions.R:181-182)."""
+    import pandas as pd
+
+    grp = gres.group.copy()
+    for c in range(_native.PAIR_COLS):
+        grp[(gres.group_na >> c) & 1 == 1, c] = np.nan
+    gene6 = res.gene[:, :6].copy()
+    for c in range(6):
+        gene6[(res.gene_na >> c) & 1 == 1, c] = np.nan
+    g = gi.gene.astype(np.int64)
+    empty = (gi.group_ptr[1:] - gi.group_ptr[:-1]) == 0
+    tail = gene6[g] if g.size else np.zeros((0, 6))
+    tail[empty] = np.nan   # :536-541: the NA column of a gene without data carries no gene-level rows either
+    table = np.concatenate([grp, tail], axis=1)
+    if by == "gene":
+        names = [f"CG~{prep.gene_names[gi_]}" for gi_ in g]
+    else:
+        names = [f"{k}_{prep.gene_names[gi_]}" for k, gi_ in zip(gi.key, g)]
+    return pd.DataFrame(table, index=names, columns=OUTPUT_COLUMNS[:-1])
+
+
+def write_csv_like_r(df, path: str, numeric: bool = False) -> None:
     """write.csv of a character matrix (the `island` row coerces every column, :463-470): numbers are
-    rendered with 15 significant digits, NA as NA, everything quoted."""
+    rendered with 15 significant digits, NA as NA, everything quoted.  ``numeric=True``: a numeric matrix (the pooled
+    tables), whose numbers write.csv leaves unquoted."""
+    q = '' if numeric else '"'
+
     def fmt(v):
         if isinstance(v, str):
             return '"' + v.replace('"', '""') + '"'
@@ -116,7 +149,7 @@ def write_csv_like_r(df, path: str) -> None:
         s = repr(float(f"{float(v):.15g}"))
         if s.endswith(".0"):
             s = s[:-2]
-        return '"' + s + '"'
+        return q + s + q
 
     with open(path, "w") as f:
         f.write(",".join(['""'] + ['"' + c + '"' for c in df.columns]) + "\n")
@@ -127,7 +160,8 @@ def write_csv_like_r(df, path: str) -> None:
 def epimethex_analysis(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRangeGene, numCores,
                        dataGenesLinear, testExpression, testMethylation, *, device: int = 0, session=None,
                        output_dir: str | None = None, write_csv: bool = True, compat_fc: str = "reference",
-                       strict: bool = False):
+                       strict: bool = False, tables=("individually", "genes", "position", "islands"),
+                       return_all: bool = False):
     """Drop-in for the reference call; returns the ``CG_data_individually`` table as a DataFrame and
     (by default) writes ``<output_dir>/<min>-<max>/CG_data_individually.csv``.
 
@@ -136,6 +170,9 @@ def epimethex_analysis(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRan
     ``compat_fc="reference"`` reproduces the reference's gene fold changes (computed from the
     0.33/0.66/0.99 quantiles); ``"means"`` uses the group means.
     ``strict=True`` raises for sample counts that are not a multiple of 3, like the reference.
+    ``tables``: which of the reference's four outputs to compute: "individually" (always), "genes"
+    (``CG_of_a_genes.csv``), "position" (``CG_by_position.csv``), "islands" (``CG_by_islands.csv``).
+    ``return_all=True`` returns a dict of the computed tables instead of the first one.
     """
     del numCores
     prep = prepare(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRangeGene)
@@ -146,6 +183,14 @@ def epimethex_analysis(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRan
     try:
         sess.set_methylation(prep.meth)
         res = sess.analyze(prep.expr, prep.index.row_ptr, prep.index.probe_idx, opts)
+        pooled = {}
+        for t in tables:
+            if t == "individually":
+                continue
+            if t not in GROUP_TABLES:
+                raise ValueError(f"unknown table {t!r}")
+            gi = build_groups(prep.index, GROUP_TABLES[t][1])
+            pooled[t] = (gi, sess.analyze_groups(gi.group_ptr, gi.group_pairs))
     finally:
         if own:
             sess.close()
@@ -157,4 +202,15 @@ def epimethex_analysis(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRan
         out = os.path.join(output_dir or os.getcwd(), name_fd)
         os.makedirs(out, exist_ok=True)
         write_csv_like_r(df, os.path.join(out, "CG_data_individually.csv"))
-    return df
+    out_tables = {"individually": df}
+    for t, (gi, gres) in pooled.items():
+        fname, by = GROUP_TABLES[t]
+        if gi.n_groups == 0:
+            import warnings
+            warnings.warn(f"{fname} is not generated")     # R/EpimethexAnalysis.R:580, :618
+            continue
+        dft = assemble_group_table(prep, res, gi, gres, by)
+        out_tables[t] = dft
+        if write_csv:
+            write_csv_like_r(dft, os.path.join(out, fname), numeric=True)
+    return out_tables if return_all else df

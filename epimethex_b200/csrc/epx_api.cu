@@ -712,6 +712,7 @@ int epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32
 
     GroupParams gp;
     gp.meth = s->meth; gp.ld = s->ld; gp.probe_idx = s->probe_idx.p; gp.group_pairs = s->g_pairs.p;
+    gp.pair_slot = s->pair_slot.p; gp.ord = s->ord.p; gp.ldo = s->ldo;
     gp.groups = s->g_desc.p; gp.blocks = s->g_blocks.p; gp.tiles = s->g_tiles.p;
     gp.n_groups = (int)n_groups; gp.n_blocks = (int)blocks.size();
     gp.n = n; gp.m = m; gp.cap = cap; gp.test_t = s->pp.test_t;

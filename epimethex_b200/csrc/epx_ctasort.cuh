@@ -22,6 +22,54 @@ __host__ __device__ inline size_t ctasort_smem(int n) { return (size_t)ctasort_e
 
 template <bool DESC> __device__ __forceinline__ bool comes_before(double a, double b) { return DESC ? a > b : a < b; }
 
+/* merge passes: s_a holds sorted runs of run_len entries (the last one may be shorter); every pass merges adjacent
+ * pairs of runs (merge path: each thread produces a contiguous slice of the output after a binary search for its split
+ * point; the left run wins ties). Ends on a __syncthreads(); returns the buffer that holds the result. */
+template <bool DESC>
+__device__ unsigned short *cta_merge_runs(const double *s_val, const int n, const int run_len, unsigned short *s_a,
+                                          unsigned short *s_b)
+{
+    unsigned short *src = s_a, *dst = s_b;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    for (int len = run_len; len < n; len <<= 1) {
+        int o = min((int)threadIdx.x * per, n);
+        const int o_end = min(o + per, n);
+        while (o < o_end) {
+            const int pbase = (o / (2 * len)) * (2 * len);
+            const int la = min(len, n - pbase), lb = min(len, n - pbase - la);
+            const unsigned short *A = src + pbase, *B = src + pbase + la;
+            const int seg_end = min(o_end, pbase + la + lb);
+            const int d = o - pbase;
+            /* merge path: i = how many of the first d outputs come from A (A wins ties) */
+            int lo = max(0, d - lb), hi = min(d, la);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (!comes_before<DESC>(s_val[B[d - 1 - mid]], s_val[A[mid]])) lo = mid + 1; else hi = mid;
+            }
+            /* branch-free sequential merge: pa/pb = next unread entry of A/B, (xa, va)/(xb, vb) = the current heads */
+            int pa = lo, pb = d - lo;
+            /* head of B clamped into the pair of runs; an absent B (odd run out) aliases the last entry of A */
+            auto head_b = [&](int q) { return lb > 0 ? la + min(q, lb - 1) : la - 1; };
+            unsigned short xa = A[min(pa, la - 1)], xb = A[head_b(pb)];
+            double va = s_val[xa], vb = s_val[xb];
+            for (int k = o; k < seg_end; k++) {
+                const bool take_a = pb >= lb || (pa < la && !comes_before<DESC>(vb, va));
+                dst[k] = take_a ? xa : xb;
+                pa += take_a ? 1 : 0;
+                pb += take_a ? 0 : 1;
+                const unsigned short nx = A[take_a ? min(pa, la - 1) : head_b(pb)];
+                const double nv = s_val[nx];
+                xa = take_a ? nx : xa; va = take_a ? nv : va;
+                xb = take_a ? xb : nx; vb = take_a ? vb : nv;
+            }
+            o = seg_end;
+        }
+        __syncthreads();
+        unsigned short *t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
 /* s_val: the row (n doubles, shared); s_a, s_b: ctasort_entries(n) uint16 each. All threads of the CTA must call.
  * Returns the buffer (s_a or s_b) that holds the sample indices in sorted order. */
 template <bool DESC>
@@ -50,36 +98,7 @@ __device__ unsigned short *cta_sort_row(const double *s_val, const int n, unsign
     }
     __syncthreads();
 
-    unsigned short *src = s_a, *dst = s_b;
-    const int per = (n + blockDim.x - 1) / blockDim.x;
-    for (int len = CTASORT_CHUNK; len < n; len <<= 1) {
-        int o = min((int)threadIdx.x * per, n);
-        const int o_end = min(o + per, n);
-        while (o < o_end) {
-            const int pbase = (o / (2 * len)) * (2 * len);
-            const int la = min(len, n - pbase), lb = min(len, n - pbase - la);
-            const unsigned short *A = src + pbase, *B = src + pbase + la;
-            const int seg_end = min(o_end, pbase + la + lb);
-            const int d = o - pbase;
-            /* merge path: i = how many of the first d outputs come from A (A wins ties) */
-            int lo = max(0, d - lb), hi = min(d, la);
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (!comes_before<DESC>(s_val[B[d - 1 - mid]], s_val[A[mid]])) lo = mid + 1; else hi = mid;
-            }
-            int i = lo, j = d - lo;
-            double va = i < la ? s_val[A[i]] : 0.0, vb = j < lb ? s_val[B[j]] : 0.0;
-            for (int k = o; k < seg_end; k++) {
-                const bool take_a = i < la && (j >= lb || !comes_before<DESC>(vb, va));
-                if (take_a) { dst[k] = A[i]; i++; va = i < la ? s_val[A[i]] : 0.0; }
-                else { dst[k] = B[j]; j++; vb = j < lb ? s_val[B[j]] : 0.0; }
-            }
-            o = seg_end;
-        }
-        __syncthreads();
-        unsigned short *t = src; src = dst; dst = t;
-    }
-    return src;
+    return cta_merge_runs<DESC>(s_val, n, CTASORT_CHUNK, s_a, s_b);
 }
 
 } // namespace epx

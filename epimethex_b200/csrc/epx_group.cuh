@@ -11,8 +11,9 @@
  *   k_group_moments    one CTA per group: two-pass centred sums straight from the methylation rows (Pearson r of
  *                      rep(expression, k) against the stack, Welch t from the pooled group moments) and the
  *                      calculateTtest guard over all k*m rank-paired differences
- *   k_group_blocksort  one CTA per block of <= rpb probe rows: gather rows + labels into shared memory, order them
- *                      with cta_sort_row (register bitonic chunks + merge path), write (value, label) runs
+ *   k_group_blocksort  one CTA per block of <= rpb probe rows: rows + labels into shared memory; every row is already
+ *                      ranked (k_probe_rank's order rows), so log2(rpb) merge-path passes in shared memory order
+ *                      the block; write (value, label) runs
  *   k_group_merge      one pass of pairwise merges of adjacent sorted runs of a group in global memory (merge
  *                      path, one contiguous output slice per thread); ceil(log2(blocks)) launches, ping-pong buffers
  *   k_group_walk       one CTA per group: running label counts over the ordered stack -> medians, KS numerators at
@@ -25,6 +26,7 @@
 namespace epx {
 
 constexpr int GROUP_THREADS = 256;
+constexpr int BLOCKSORT_THREADS = 512;
 constexpr int MERGE_SLICE = 16;                         /* outputs per thread of k_group_merge */
 constexpr int MERGE_TILE = GROUP_THREADS * MERGE_SLICE; /* outputs per CTA */
 
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group_moments(GroupParams p)
 }
 
 /* ---------------------------------------------------------------- sorted blocks of <= rpb probe rows */
-__global__ void __launch_bounds__(CTASORT_THREADS) k_group_blocksort(GroupParams p)
+__global__ void __launch_bounds__(BLOCKSORT_THREADS) k_group_blocksort(GroupParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const BlockDesc bd = p.blocks[blockIdx.x];
@@ -162,15 +164,19 @@ __global__ void __launch_bounds__(CTASORT_THREADS) k_group_blocksort(GroupParams
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint8_t *lab = p.lab8 + (int64_t)gd.gene * p.ldl;
     const int32_t *pairs = p.group_pairs + gd.first + bd.r0;
+    /* every probe row was ranked once by k_probe_rank: start from sorted runs of n and only merge */
     for (int j = warp; j < bd.runs; j += nw) {
-        const double *row = p.meth + (int64_t)p.probe_idx[pairs[j]] * p.ld;
+        const int pr = pairs[j];
+        const double *row = p.meth + (int64_t)p.probe_idx[pr] * p.ld;
+        const uint16_t *po = p.ord + (int64_t)p.pair_slot[pr] * p.ldo;
         for (int s = lane; s < n; s += 32) {
             s_val[j * n + s] = row[s];
             s_lab[j * n + s] = lab[s];
+            s_a[j * n + s] = (unsigned short)(j * n + (po[s] & 0x7fffu));
         }
     }
     __syncthreads();
-    const unsigned short *ord = cta_sort_row<false>(s_val, nb, s_a, s_b, p.one);
+    const unsigned short *ord = cta_merge_runs<false>(s_val, nb, n, s_a, s_b);
     double *ov = p.val[0] + gd.elem + (int64_t)bd.r0 * n;
     uint8_t *ol = p.lab[0] + gd.elem + (int64_t)bd.r0 * n;
     for (int t = threadIdx.x; t < nb; t += blockDim.x) {
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group_merge(GroupParams p, in
         const int64_t pbase = (o / (2 * run_len)) * (2 * run_len);
         const int64_t la = min(run_len, N - pbase), lb = min(run_len, N - pbase - la);
         const double *A = sv + pbase, *B = A + la;
-        const uint8_t *LA = sl + pbase, *LB = LA + la;
+        const uint8_t *LA = sl + pbase;
         const int64_t seg_end = min(o_end, pbase + la + lb);
         const int64_t d = o - pbase;
         /* merge path: i = how many of the first d outputs of this pair of runs come from A (A wins ties) */
@@ -205,12 +211,24 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group_merge(GroupParams p, in
             const int64_t mid = (lo + hi) >> 1;
             if (!(B[d - 1 - mid] < A[mid])) lo = mid + 1; else hi = mid;
         }
-        int64_t i = lo, j = d - lo;
-        double va = i < la ? A[i] : 0.0, vb = j < lb ? B[j] : 0.0;
+        /* branch-free sequential merge: pa/pb = next unread entry of A/B, (va, ua)/(vb, ub) = the current heads */
+        int64_t pa = lo, pb = d - lo;
+        const int64_t ca = la - 1, cb = lb - 1;
+        /* index (relative to A; B = A + la) of the head of B, clamped into the pair of runs; an absent B aliases A */
+        auto head_b = [&](int64_t q) { return lb > 0 ? la + min(q, cb) : ca; };
+        double va = A[min(pa, ca)], vb = A[head_b(pb)];
+        unsigned ua = LA[min(pa, ca)], ub = LA[head_b(pb)];
         for (int64_t t = o; t < seg_end; t++) {
-            const bool take_a = i < la && (j >= lb || !(vb < va));
-            if (take_a) { dv[t] = va; dl[t] = LA[i]; i++; va = i < la ? A[i] : 0.0; }
-            else { dv[t] = vb; dl[t] = LB[j]; j++; vb = j < lb ? B[j] : 0.0; }
+            const bool take_a = pb >= lb || (pa < la && !(vb < va));
+            dv[t] = take_a ? va : vb;
+            dl[t] = (uint8_t)(take_a ? ua : ub);
+            pa += take_a ? 1 : 0;
+            pb += take_a ? 0 : 1;
+            const int64_t nx = take_a ? min(pa, ca) : head_b(pb);
+            const double nv = A[nx];
+            const unsigned nl = LA[nx];
+            va = take_a ? nv : va; ua = take_a ? nl : ua;
+            vb = take_a ? vb : nv; ub = take_a ? ub : nl;
         }
         o = seg_end;
     }

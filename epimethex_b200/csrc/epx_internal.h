@@ -109,6 +109,9 @@ struct GroupParams {
     int64_t ld;
     const int32_t *probe_idx;
     const int32_t *group_pairs;
+    const int32_t *pair_slot;   /* order row of each pair's probe (k_probe_rank) */
+    const uint16_t *ord;
+    int64_t ldo;
     const GroupDesc *groups;
     const BlockDesc *blocks;
     const TileDesc *tiles;

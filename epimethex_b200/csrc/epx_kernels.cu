@@ -1173,7 +1173,7 @@ cudaError_t launch_group_moments(const GroupParams &p, cudaStream_t st)
 cudaError_t launch_group_blocksort(const GroupParams &p, cudaStream_t st)
 {
     if (p.n_blocks <= 0) return cudaSuccess;
-    k_group_blocksort<<<p.n_blocks, CTASORT_THREADS, group_sort_smem(p.cap), st>>>(p);
+    k_group_blocksort<<<p.n_blocks, BLOCKSORT_THREADS, group_sort_smem(p.cap), st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_group_merge(const GroupParams &p, int pass, int64_t run_len, int n_tiles, cudaStream_t st)

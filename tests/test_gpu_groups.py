@@ -139,3 +139,25 @@ def test_bad_group_lists_are_rejected(sess):
     g0 = int(idx.row_ptr[1]) - 1
     with pytest.raises(_native.EpxError):
         sess.analyze_groups(np.array([0, 2], np.int64), np.array([g0, int(idx.row_ptr[-1]) - 1], np.int32))
+
+
+def test_public_api_writes_the_pooled_tables(tmp_path):
+    """epimethex.analysis writes four files (R/EpimethexAnalysis.R:470, :545, :577, :615)."""
+    from epimethex_b200 import epimethex_analysis
+    dfe, dfa, dfm, _ = synth.frames(40, 30, 600)
+    out = epimethex_analysis(dfe, dfa, dfm, 1, 40, 2, True, True, False, output_dir=str(tmp_path), return_all=True)
+    d = tmp_path / "1-40"
+    assert set(out) >= {"individually", "genes", "position"}
+    assert (d / "CG_data_individually.csv").exists() and (d / "CG_of_a_genes.csv").exists() and (d / "CG_by_position.csv").exists()
+    genes = out["genes"]
+    assert genes.shape[1] == 17 and all(name.startswith("CG~G") for name in genes.index)
+    head = (d / "CG_of_a_genes.csv").read_text().splitlines()[0]
+    assert head.startswith('"","medianDown","medianMedium","medianUP"') and head.count(",") == 17
+    pos = out["position"]
+    assert all(name.split("_")[0] in synth.GROUPS for name in pos.index)
+    # a gene pooled over all its probes with a single data-bearing probe repeats that probe's row
+    ind = out["individually"]
+    single = [g for g in genes.index if sum(i.endswith("_" + g[3:]) for i in ind.dropna(subset=["medianUP"]).index) == 1]
+    for g in single[:5]:
+        row = ind.dropna(subset=["medianUP"]).filter(like="_" + g[3:], axis=0).iloc[0]
+        np.testing.assert_allclose(genes.loc[g].to_numpy(float), row.to_numpy()[:17].astype(float), rtol=1e-8, atol=1e-10)

@@ -135,3 +135,85 @@ def test_assemble_and_csv(tmp_path, readme_frames):
     assert lines[0].startswith('"","medianDown","medianMedium"') and lines[0].endswith('"island"')
     assert lines[1].split(",")[2] == '"0.142857142857143"'          # 15 significant digits, quoted
     assert "NA" in lines[2].split(",")
+
+
+# ---------------------------------------------------------------- pooled probe groups (host logic + oracle)
+
+def _brute_groups(idx, by):
+    import re
+    po = idx.output_order
+    genes = []
+    for p in po:
+        if idx.pair_gene[p] not in genes:
+            genes.append(idx.pair_gene[p])
+    out = []
+    if by == "gene":
+        return [(g, None, [p for p in po if idx.pair_gene[p] == g and idx.probe_idx[p] >= 0]) for g in genes]
+    vals = idx.position if by == "position" else idx.island
+    keys = []
+    for p in po:
+        if vals[p] not in keys:
+            keys.append(vals[p])
+    if by == "island":
+        keys = [k for k in keys if not re.search("NA_NA|^_", k)]
+    for g in genes:
+        pg = [p for p in po if idx.pair_gene[p] == g]
+        for k in keys:
+            members = [p for p in pg if vals[p] == k and idx.probe_idx[p] >= 0]
+            if len(members) > 1:                       # R/Functions.R:153
+                out.append((g, k, members))
+    return out
+
+
+@pytest.mark.parametrize("by", ["gene", "position", "island"])
+def test_build_groups_follows_the_reference_loops(by):
+    """R/EpimethexAnalysis.R:476-620 / R/Functions.R:136-188: which probes are pooled, and in which column order."""
+    from epimethex_b200 import synth
+    from epimethex_b200.annotation import build_groups
+    ann = synth.annotation(1500, 90)
+    has = np.ones(1500, bool); has[::7] = False
+    idx = synth.probe_index(ann, 0, 90, has)
+    gi = build_groups(idx, by)
+    want = _brute_groups(idx, by)
+    assert gi.n_groups == len(want) > 0
+    for q, (g, k, members) in enumerate(want):
+        assert gi.gene[q] == g and gi.key[q] == k
+        assert gi.group_pairs[gi.group_ptr[q]:gi.group_ptr[q + 1]].tolist() == members
+
+
+def test_oracle_groups_of_one_probe_equal_the_pair_table():
+    import oracle
+    rng = np.random.default_rng(0)
+    G, n, P = 12, 30, 40
+    expr = rng.normal(5, 2, (G, n)); meth = np.round(rng.random((P, n)), 2)
+    row_ptr = np.arange(0, G * 5 + 1, 5, dtype=np.int64)
+    probe_idx = rng.integers(0, P, G * 5).astype(np.int32)
+    for tm in (False, True):
+        res = oracle.analyze(expr, meth, row_ptr, probe_idx, test_meth_t=tm)
+        one = oracle.analyze_groups(expr, meth, row_ptr, probe_idx, np.arange(G * 5 + 1, dtype=np.int64),
+                                    np.arange(G * 5, dtype=np.int32), test_meth_t=tm)
+        assert np.array_equal(one.group, res.pair, equal_nan=True)
+        assert np.array_equal(one.group_na, res.pair_na)
+        assert np.array_equal(one.group_dnum, res.ks_dnum)
+
+
+def test_oracle_pooled_group_by_hand():
+    """two probes pooled: medians, KS numerator and Pearson against a direct numpy/scipy computation"""
+    import oracle
+    from scipy import stats
+    rng = np.random.default_rng(3)
+    n, m = 60, 20
+    expr = rng.normal(5, 2, (1, n)); meth = rng.random((2, n))
+    row_ptr = np.array([0, 2], np.int64); probe_idx = np.array([0, 1], np.int32)
+    r = oracle.analyze_groups(expr, meth, row_ptr, probe_idx, row_ptr, probe_idx)
+    order = np.argsort(-expr[0], kind="stable")
+    y = meth[:, order]
+    up, mid, down = y[:, :m].ravel(), y[:, m:2 * m].ravel(), y[:, 2 * m:].ravel()
+    assert r.group[0, 0] == np.median(down) and r.group[0, 1] == np.median(mid) and r.group[0, 2] == np.median(up)
+    d = stats.ks_2samp(up, mid, method="asymp").statistic
+    assert r.group_dnum[0, 0] == round(d * 40 * 40)
+    pr = stats.pearsonr(np.tile(expr[0][order], 2), y.ravel())
+    np.testing.assert_allclose(r.group[0, 9:11], [pr.statistic, pr.pvalue], rtol=1e-9)
+    with pytest.raises(ValueError):      # a group may not mix genes or name a pair without data
+        oracle.analyze_groups(np.vstack([expr, expr]), meth, np.array([0, 1, 2], np.int64), probe_idx,
+                              np.array([0, 2], np.int64), np.array([0, 1], np.int32))
