@@ -46,5 +46,30 @@ epimethex.analysis <- function(dfExpressions, dfGpl, dfMethylation, minRangeGene
     colnames(tab) <- paste(ann$cg, ann$position, ann$gene, sep = "_")
     out <- rbind(tab, island = ann$island)                       # the character row coerces all, as in :463-467
     utils::write.csv(t(out), file.path(getwd(), nameFD, "CG_data_individually.csv"))
+    # --- pooled tables: Loops B, C, D (R/EpimethexAnalysis.R:476-620, R/Functions.R:136-188) ---
+    csr <- back - 1L                                             # 0-based pair index of every dfCGunique row
+    hasData <- !is.na(probeIdx[back])
+    gfac <- factor(ann$gene)                                     # column order of the reference: sorted gene names
+    pooled <- function(groups, names, file) {                    # groups: list of dfCGunique row numbers with data
+        if (length(groups) == 0) { warning(paste(file, "is not generated")); return(invisible()) }
+        ptr <- c(0, cumsum(lengths(groups)))
+        g <- .Call(C_epx_groups, session, as.numeric(ptr), as.integer(csr[unlist(groups)]))
+        first <- vapply(seq_along(groups), function(i) if (length(groups[[i]])) groups[[i]][1] else NA_integer_, 1L)
+        tail6 <- res$gene[1:6, gi[first], drop = FALSE]
+        tail6[, is.na(first)] <- NA                               # :536-541: a gene without data -> NA column
+        t2 <- rbind(g, tail6); rownames(t2) <- rownames(tab); colnames(t2) <- names
+        utils::write.csv(t(t2), file.path(getwd(), nameFD, file))
+    }
+    rows <- split(seq_len(nrow(ann)), gfac)
+    pooled(lapply(rows, function(r) r[hasData[r]]), paste("CG", levels(gfac), sep = "~"), "CG_of_a_genes.csv")
+    for (spec in list(list("position", unique(ann$position), "CG_by_position.csv"),
+                      list("island", Filter(function(v) !grepl("NA_NA|^_", v), unique(ann$island)), "CG_by_islands.csv"))) {
+        grp <- list(); nms <- character(0)
+        for (gname in levels(gfac)) for (v in spec[[2]]) {       # gene-major, values in order of first appearance
+            r <- rows[[gname]]; r <- r[ann[[spec[[1]]]][r] == v & hasData[r]]
+            if (length(r) > 1) { grp[[length(grp) + 1]] <- r; nms <- c(nms, paste(v, gname, sep = "_")) }
+        }
+        pooled(grp, nms, spec[[3]])
+    }
     invisible(session)
 }

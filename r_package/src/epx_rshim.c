@@ -115,6 +115,36 @@ SEXP C_epx_analyze(SEXP session, SEXP expr, SEXP rowPtr, SEXP probeIdx, SEXP opt
     return out;
 }
 
+/* .Call(C_epx_groups, session, groupPtr, groupPairs): pooled tables (Loops B, C, D of the reference,
+ * R/EpimethexAnalysis.R:476-620). groupPtr: REALSXP Q+1 offsets; groupPairs: INTSXP, 0-based rows of dfCGunique
+ * (same numbering as probeIdx), each group inside one gene and with data. Returns an 11 x Q matrix. */
+SEXP C_epx_groups(SEXP session, SEXP groupPtr, SEXP groupPairs)
+{
+    char err[512] = "";
+    epx_session *s = (epx_session *)R_ExternalPtrAddr(session);
+    if (!s) Rf_error("libepx: the session has been released");
+    const int64_t Q = (int64_t)Rf_xlength(groupPtr) - 1;
+    if (Q < 0) Rf_error("groupPtr must hold at least one offset");
+    int64_t *gp = (int64_t *)malloc((size_t)(Q + 1) * sizeof(int64_t));
+    uint16_t *na = (uint16_t *)malloc((size_t)(Q > 0 ? Q : 1) * 2);
+    if (!gp || !na) { free(gp); free(na); Rf_error("out of memory"); }
+    for (int64_t q = 0; q <= Q; q++) gp[q] = (int64_t)REAL(groupPtr)[q];
+    SEXP grp = PROTECT(Rf_allocMatrix(REALSXP, EPX_PAIR_COLS, (int)Q));
+    epx_group_result r;
+    memset(&r, 0, sizeof r);
+    r.group = REAL(grp); r.group_na = na;
+    int rc = epx_session_run_groups(s, gp, (const int32_t *)INTEGER(groupPairs), Q, NULL, err, sizeof err);
+    if (rc == EPX_OK) rc = epx_session_fetch_groups(s, &r, NULL, err, sizeof err);
+    if (rc == EPX_OK)
+        for (int64_t q = 0; q < Q; q++)
+            for (int c = 0; c < EPX_PAIR_COLS; c++)
+                if ((na[q] >> c) & 1) REAL(grp)[q * EPX_PAIR_COLS + c] = NA_REAL;
+    free(gp); free(na);
+    UNPROTECT(1);
+    if (rc != EPX_OK) Rf_error("libepx: %s", err);
+    return grp;
+}
+
 SEXP C_epx_device_info(void)
 {
     char err[512] = "", name[256] = "";
@@ -129,6 +159,7 @@ SEXP C_epx_device_info(void)
 static const R_CallMethodDef call_methods[] = {
     { "C_epx_upload", (DL_FUNC)&C_epx_upload, 2 },
     { "C_epx_analyze", (DL_FUNC)&C_epx_analyze, 5 },
+    { "C_epx_groups", (DL_FUNC)&C_epx_groups, 3 },
     { "C_epx_device_info", (DL_FUNC)&C_epx_device_info, 0 },
     { NULL, NULL, 0 }
 };
