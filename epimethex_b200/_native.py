@@ -28,6 +28,7 @@ EXPORTS = [
     "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
     "epx_multi_set_methylation_rows", "epx_multi_analyze", "epx_session_run_groups", "epx_session_fetch_groups",
+    "epx_write_csv", "epx_format_real15",
 ]
 
 ERRORS = {-1: "EPX_EINVAL", -2: "EPX_ECUDA", -3: "EPX_ENOMEM", -4: "EPX_ESTATE", -5: "EPX_EBREAKS",
@@ -114,6 +115,9 @@ def lib():
     L.epx_multi_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
     L.epx_session_run_groups.argtypes = [vp, vp, vp, i64, vp] + e
     L.epx_session_fetch_groups.argtypes = [vp, C.POINTER(_GroupResult), vp] + e
+    L.epx_write_csv.argtypes = [C.c_char_p, i64, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp,
+                                C.POINTER(C.c_char_p), C.c_char_p, C.c_int, C.c_int] + e
+    L.epx_format_real15.argtypes = [C.c_double, C.c_char_p, C.c_size_t]
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int and name not in ("epx_abi_version",):
@@ -129,6 +133,27 @@ def _check(rc: int, buf) -> None:
 
 def _errbuf():
     return C.create_string_buffer(512)
+
+
+def format_real15(x: float) -> str:
+    """One double as R prints it with 15 significant digits (as.character / write.csv)."""
+    buf = C.create_string_buffer(64)
+    if lib().epx_format_real15(float(x), buf, len(buf)) != 0:
+        raise ValueError("epx_format_real15 failed")
+    return buf.value.decode()
+
+
+def write_csv(path: str, row_names, col_names, values: np.ndarray, *, text_col=None, text_col_name: str = "",
+              quote_numbers: bool = False, threads: int = 0) -> None:
+    """R's write.csv of a table (epx_write_csv): NaN cells are written as NA."""
+    values = np.ascontiguousarray(values, np.float64)
+    n_rows, n_cols = values.shape if values.ndim == 2 else (len(row_names), 0)
+    enc = lambda seq: (C.c_char_p * len(seq))(*[None if v is None else str(v).encode() for v in seq])
+    rn, cn = enc(list(row_names)), enc(list(col_names))
+    tc = enc(list(text_col)) if text_col is not None else None
+    b = _errbuf()
+    _check(lib().epx_write_csv(os.fsencode(path), n_rows, n_cols, rn, cn, values.ctypes.data, None, tc,
+                               text_col_name.encode(), int(quote_numbers), threads or (os.cpu_count() or 1), b, len(b)), b)
 
 
 def device_count() -> int:

@@ -136,25 +136,23 @@ def assemble_group_table(prep: PreparedInputs, res, gi: GroupIndex, gres, by: st
 
 
 def write_csv_like_r(df, path: str, numeric: bool = False) -> None:
-    """write.csv of a character matrix (the `island` row coerces every column, :463-470): numbers are
-    rendered with 15 significant digits, NA as NA, everything quoted.  ``numeric=True``: a numeric matrix (the pooled
-    tables), whose numbers write.csv leaves unquoted."""
-    q = '' if numeric else '"'
+    """write.csv of the result table through the native writer (epx_write_csv, multithreaded).
+    Default: a character matrix (the `island` row coerces every column, R/EpimethexAnalysis.R:463-470): numbers with
+    15 significant digits as R's as.character renders them, NA as NA, everything quoted.  ``numeric=True``: a numeric
+    matrix (the pooled tables), whose numbers write.csv leaves unquoted."""
+    cols = list(df.columns)
+    text = None
+    import pandas as pd
 
-    def fmt(v):
-        if isinstance(v, str):
-            return '"' + v.replace('"', '""') + '"'
-        if v is None or (isinstance(v, float) and np.isnan(v)):
-            return "NA"
-        s = repr(float(f"{float(v):.15g}"))
-        if s.endswith(".0"):
-            s = s[:-2]
-        return q + s + q
-
-    with open(path, "w") as f:
-        f.write(",".join(['""'] + ['"' + c + '"' for c in df.columns]) + "\n")
-        for name, row in zip(df.index, df.itertuples(index=False, name=None)):
-            f.write(",".join(['"' + str(name) + '"'] + [fmt(v) for v in row]) + "\n")
+    if cols and not pd.api.types.is_numeric_dtype(df[cols[-1]]):
+        text = [None if (v is None or v is pd.NA or (isinstance(v, float) and np.isnan(v))) else str(v)
+                for v in df[cols[-1]].tolist()]
+        num_cols = cols[:-1]
+    else:
+        num_cols = cols
+    values = df[num_cols].to_numpy(dtype=np.float64) if num_cols else np.zeros((len(df), 0))
+    _native.write_csv(path, [str(v) for v in df.index], num_cols, values, text_col=text,
+                      text_col_name=cols[-1] if text is not None else "", quote_numbers=not numeric)
 
 
 def epimethex_analysis(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRangeGene, numCores,

@@ -207,6 +207,17 @@ int  epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int3
                             int64_t n_groups, void *stream, char *err, size_t errlen);
 int  epx_session_fetch_groups(epx_session *s, epx_group_result *out, void *stream, char *err, size_t errlen);
 
+/* ---- result files: R's write.csv, formatted on several host threads (no GPU involved) ----
+ * Replaces write.csv(...) at R/EpimethexAnalysis.R:470, :545, :577, :615. values [n_rows][n_cols] row-major;
+ * na (optional) [n_rows][n_cols] non-zero = NA, NULL = every NaN is NA; text_col (optional) one more, quoted,
+ * column of strings (the `island` row of CG_data_individually, which also makes R quote the numbers:
+ * quote_numbers = 1). Numbers are rendered like R does with 15 significant digits (epx_format_real15). */
+int  epx_write_csv(const char *path, int64_t n_rows, int n_cols, const char *const *row_names,
+                   const char *const *col_names, const double *values, const uint8_t *na,
+                   const char *const *text_col, const char *text_col_name, int quote_numbers, int threads,
+                   char *err, size_t errlen);
+int  epx_format_real15(double x, char *buf, size_t buflen);
+
 /* ---- one-shot: what `.Call(C_epx_analyze, ...)` needs ----
  * Uploads expression + index, runs, fetches. The session must already hold the methylation matrix. */
 int  epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples,

@@ -135,6 +135,28 @@ def test_assemble_and_csv(tmp_path, readme_frames):
     assert lines[0].startswith('"","medianDown","medianMedium"') and lines[0].endswith('"island"')
     assert lines[1].split(",")[2] == '"0.142857142857143"'          # 15 significant digits, quoted
     assert "NA" in lines[2].split(",")
+    analysis.write_csv_like_r(df.iloc[:, :17], str(p), numeric=True)    # the pooled tables: a numeric matrix
+    lines = p.read_text().splitlines()
+    assert lines[1].split(",")[2] == "0.142857142857143" and lines[0].count(",") == 17
+
+
+@pytest.mark.parametrize("x,want", [
+    (0.1, "0.1"), (1e-4, "1e-04"), (100000.0, "1e+05"), (123456.0, "123456"), (0.00012345, "0.00012345"),
+    (1 / 3, "0.333333333333333"), (2 / 3, "0.666666666666667"), (1e15, "1e+15"), (123456789012.0, "123456789012"),
+    (-0.5, "-0.5"), (1e-300, "1e-300"), (0.9841, "0.9841"), (1234567.1, "1234567.1"), (100001.0, "100001"),
+    (3.0, "3"), (1.5e-10, "1.5e-10"), (0.1 + 0.2, "0.3"), (1e22, "1e+22"), (0.0, "0"), (-1e-5, "-1e-05"),
+    (float("inf"), "Inf"), (5.066e-17, "5.066e-17"), (0.05, "0.05"), (0.000123456789012345, "0.000123456789012345")])
+def test_numbers_are_rendered_like_r(x, want):
+    """R's formatReal with digits = 15 on one value (as.character / write.csv): fewest significant digits, fixed
+    notation unless scientific is strictly narrower.  Expected strings are what R prints for these literals."""
+    assert _native.format_real15(x) == want
+
+
+def test_native_csv_writer_quotes_and_escapes(tmp_path):
+    p = tmp_path / "q.csv"
+    _native.write_csv(str(p), ['a"b', "c"], ["x", "y"], np.array([[1.0, np.nan], [2.5, -1e-7]]),
+                      text_col=["i,1", None], text_col_name="island", quote_numbers=True, threads=3)
+    assert p.read_text() == '"","x","y","island"\n"a""b","1",NA,"i,1"\n"c","2.5","-1e-07",NA\n'
 
 
 # ---------------------------------------------------------------- pooled probe groups (host logic + oracle)
