@@ -325,7 +325,7 @@ def main():
         if not args.no_cpu_baseline:
             # the oracle's pooled pass on every s-th group (bounded), all host cores
             import oracle
-            stride = max(1, int(gi.group_pairs.size // 12000))
+            stride = max(1, int(gi.group_pairs.size // 60000))
             pick = np.arange(0, gi.n_groups, stride)
             gp = np.zeros(pick.size + 1, np.int64)
             np.cumsum(sizes[pick], out=gp[1:])

@@ -102,7 +102,7 @@ struct epx_session {
     DevBuf<GroupDesc> g_desc;
     DevBuf<BlockDesc> g_blocks;
     DevBuf<TileDesc> g_tiles;
-    DevBuf<int32_t> g_pairs, g_guard;
+    DevBuf<int32_t> g_pairs, g_guard, g_multi;
     DevBuf<double> g_val[2], grp, grp_stat;
     DevBuf<uint8_t> g_lab[2];
     DevBuf<uint16_t> grp_na;
@@ -216,7 +216,7 @@ void epx_session_destroy(epx_session *s)
     s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->nuniq.release(); s->scal.release();
     s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
     s->pair_dnum.release(); s->gene_dnum.release();
-    s->g_desc.release(); s->g_blocks.release(); s->g_tiles.release(); s->g_pairs.release(); s->g_guard.release();
+    s->g_desc.release(); s->g_blocks.release(); s->g_tiles.release(); s->g_pairs.release(); s->g_guard.release(); s->g_multi.release();
     s->g_val[0].release(); s->g_val[1].release(); s->g_lab[0].release(); s->g_lab[1].release();
     s->grp.release(); s->grp_stat.release(); s->grp_na.release(); s->grp_dnum.release();
     for (int i = 0; i < 8; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -688,12 +688,16 @@ int epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32
         for (int64_t t = 0; t < nt; t++) { TileDesc td; td.group = q; td.tile = (int32_t)t; tiles.push_back(td); }
         for (int p = 0; p < passes; p++) if (d.nblocks > (1 << p)) pass_tiles[(size_t)p] = (int64_t)tiles.size();
     }
+    /* groups that do not finish inside k_group_blocksort: several blocks (moments + merges + walk), or empty (NA row) */
+    std::vector<int32_t> rest;
+    for (int64_t q = 0; q < n_groups; q++) if (desc[(size_t)q].nblocks != 1) rest.push_back((int32_t)q);
     if (tiles.size() > 0x7fffffffu || blocks.size() > 0x7fffffffu) return fail(err, errlen, EPX_EINVAL, "too many group blocks");
 
     EPX_CUDA(s->g_desc.reserve(desc.size()));
     EPX_CUDA(s->g_blocks.reserve(blocks.size()));
     EPX_CUDA(s->g_tiles.reserve(tiles.size()));
     EPX_CUDA(s->g_pairs.reserve((size_t)L));
+    EPX_CUDA(s->g_multi.reserve(rest.size()));
     EPX_CUDA(s->g_guard.reserve((size_t)n_groups * 3));
     EPX_CUDA(s->grp.reserve((size_t)n_groups * PAIR_COLS));
     EPX_CUDA(s->grp_stat.reserve((size_t)n_groups * 3));
@@ -707,6 +711,7 @@ int epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32
     if (!desc.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_desc.p, desc.data(), desc.size() * sizeof(GroupDesc), cudaMemcpyHostToDevice, st));
     if (!blocks.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_blocks.p, blocks.data(), blocks.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
     if (!tiles.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    if (!rest.empty()) EPX_CUDA(cudaMemcpyAsync(s->g_multi.p, rest.data(), rest.size() * 4, cudaMemcpyHostToDevice, st));
     if (L) EPX_CUDA(cudaMemcpyAsync(s->g_pairs.p, group_pairs, (size_t)L * 4, cudaMemcpyHostToDevice, st));
     EPX_CUDA(cudaStreamSynchronize(st)); /* the vectors die with this scope */
 
@@ -714,6 +719,7 @@ int epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32
     gp.meth = s->meth; gp.ld = s->ld; gp.probe_idx = s->probe_idx.p; gp.group_pairs = s->g_pairs.p;
     gp.pair_slot = s->pair_slot.p; gp.ord = s->ord.p; gp.ldo = s->ldo;
     gp.groups = s->g_desc.p; gp.blocks = s->g_blocks.p; gp.tiles = s->g_tiles.p;
+    gp.multi = s->g_multi.p; gp.n_multi = (int)rest.size();
     gp.n_groups = (int)n_groups; gp.n_blocks = (int)blocks.size();
     gp.n = n; gp.m = m; gp.cap = cap; gp.test_t = s->pp.test_t;
     gp.perm = s->perm.p; gp.lab8 = s->lab8.p; gp.ldl = s->ldl; gp.xc = s->xc.p; gp.ldx = s->ldx; gp.gene_aux = s->gene_aux.p;

@@ -48,16 +48,16 @@ __device__ unsigned short *cta_merge_runs(const double *s_val, const int n, cons
             }
             /* branch-free sequential merge: pa/pb = next unread entry of A/B, (xa, va)/(xb, vb) = the current heads */
             int pa = lo, pb = d - lo;
-            /* head of B clamped into the pair of runs; an absent B (odd run out) aliases the last entry of A */
-            auto head_b = [&](int q) { return lb > 0 ? la + min(q, lb - 1) : la - 1; };
-            unsigned short xa = A[min(pa, la - 1)], xb = A[head_b(pb)];
+            /* heads clamped into the pair of runs; an absent B (odd run out) aliases the last entry of A */
+            const int lastA = la - 1, lastB = la + lb - 1;
+            unsigned short xa = A[min(pa, lastA)], xb = A[min(la + pb, lastB)];
             double va = s_val[xa], vb = s_val[xb];
             for (int k = o; k < seg_end; k++) {
                 const bool take_a = pb >= lb || (pa < la && !comes_before<DESC>(vb, va));
                 dst[k] = take_a ? xa : xb;
                 pa += take_a ? 1 : 0;
                 pb += take_a ? 0 : 1;
-                const unsigned short nx = A[take_a ? min(pa, la - 1) : head_b(pb)];
+                const unsigned short nx = A[take_a ? min(pa, lastA) : min(la + pb, lastB)];
                 const double nv = s_val[nx];
                 xa = take_a ? nx : xa; va = take_a ? nv : va;
                 xb = take_a ? xb : nx; vb = take_a ? vb : nv;

@@ -115,6 +115,8 @@ struct GroupParams {
     const GroupDesc *groups;
     const BlockDesc *blocks;
     const TileDesc *tiles;
+    const int32_t *multi;       /* groups handled by k_group_moments / k_group_walk: more than one block, or empty */
+    int n_multi;
     int n_groups, n_blocks;
     int n, m, cap, test_t;
     const uint16_t *perm;

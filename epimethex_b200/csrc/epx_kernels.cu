@@ -1166,8 +1166,8 @@ int group_block_cap(int n) { return n <= 8192 ? 8192 : ctasort_entries(n); }
 
 cudaError_t launch_group_moments(const GroupParams &p, cudaStream_t st)
 {
-    if (p.n_groups <= 0) return cudaSuccess;
-    k_group_moments<<<p.n_groups, GROUP_THREADS, 0, st>>>(p);
+    if (p.n_multi <= 0) return cudaSuccess;
+    k_group_moments<<<p.n_multi, GROUP_THREADS, 0, st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_group_blocksort(const GroupParams &p, cudaStream_t st)
@@ -1184,8 +1184,8 @@ cudaError_t launch_group_merge(const GroupParams &p, int pass, int64_t run_len, 
 }
 cudaError_t launch_group_walk(const GroupParams &p, cudaStream_t st)
 {
-    if (p.n_groups <= 0) return cudaSuccess;
-    k_group_walk<<<p.n_groups, GROUP_THREADS, 0, st>>>(p);
+    if (p.n_multi <= 0) return cudaSuccess;
+    k_group_walk<<<p.n_multi, GROUP_THREADS, 0, st>>>(p);
     return cudaGetLastError();
 }
 
