@@ -99,6 +99,8 @@ struct epx_session {
     size_t staging_bytes = 0;
     /* pooled probe groups (epx_session_run_groups) */
     std::vector<int32_t> h_probe_idx, h_pair_gene; /* host copies of the index, to validate group lists */
+    std::vector<int64_t> h_row_ptr;
+    int64_t index_P = -1;                           /* methylation row count the index was validated against */
     DevBuf<GroupDesc> g_desc;
     DevBuf<BlockDesc> g_blocks;
     DevBuf<TileDesc> g_tiles;
@@ -267,7 +269,10 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
     }
     EPX_CUDA(cudaStreamSynchronize(s->stream));
     s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
-    s->G_index = -1; /* slots refer to the previous matrix */
+    /* the index (unique-probe slots, work items) depends on the row count only: it survives a new matrix of the
+     * same shape; everything computed from the old values does not */
+    if (s->index_P != n_probes) s->G_index = -1;
+    s->prepared = false; s->ran = false; s->n_groups = -1;
     return EPX_OK;
 }
 
@@ -300,7 +305,10 @@ int epx_session_set_methylation_cols(epx_session *s, const double *const *cols, 
     }
     stage.release();
     s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
-    s->G_index = -1;
+    /* the index (unique-probe slots, work items) depends on the row count only: it survives a new matrix of the
+     * same shape; everything computed from the old values does not */
+    if (s->index_P != n_probes) s->G_index = -1;
+    s->prepared = false; s->ran = false; s->n_groups = -1;
     return EPX_OK;
 }
 
@@ -314,7 +322,10 @@ int epx_session_set_methylation_device(epx_session *s, const double *d_rows, int
         return fail(err, errlen, EPX_EINVAL, "device methylation rows must be 16-byte aligned with an even leading dimension (bulk copies)");
     s->meth_own.release();
     s->meth = d_rows; s->P = n_probes; s->n_meth = n_samples; s->ld = ld;
-    s->G_index = -1;
+    /* the index (unique-probe slots, work items) depends on the row count only: it survives a new matrix of the
+     * same shape; everything computed from the old values does not */
+    if (s->index_P != n_probes) s->G_index = -1;
+    s->prepared = false; s->ran = false; s->n_groups = -1;
     return EPX_OK;
 }
 
@@ -342,6 +353,12 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     const int64_t Np = row_ptr[n_genes];
     if (Np < 0 || Np > 0x7fffffff) return fail(err, errlen, EPX_EINVAL, "pair count %lld out of range", (long long)Np);
     if (Np > 0 && !probe_idx) return fail(err, errlen, EPX_EINVAL, "probe_idx is NULL");
+    /* the same index again (re-run with other options, repeated calls on one gene range): everything derived
+     * from it is still on the device */
+    if (s->G_index == n_genes && s->Np == Np && s->h_row_ptr.size() == (size_t)n_genes + 1 && s->index_P == s->P &&
+        memcmp(s->h_row_ptr.data(), row_ptr, ((size_t)n_genes + 1) * sizeof(int64_t)) == 0 &&
+        (Np == 0 || memcmp(s->h_probe_idx.data(), probe_idx, (size_t)Np * sizeof(int32_t)) == 0))
+        return EPX_OK;
     EPX_CUDA(cudaSetDevice(s->device));
 
     std::vector<int32_t> slot_of((size_t)s->P, -1), pair_slot((size_t)Np), pair_gene((size_t)Np), uniq;
@@ -388,6 +405,8 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     for (size_t i = 0; i < items.size(); i++) s->item_begin[i] = items[i].begin;
     s->item_begin[items.size()] = (int32_t)Np;
     s->h_probe_idx.assign(probe_idx, probe_idx + Np);
+    s->h_row_ptr.assign(row_ptr, row_ptr + n_genes + 1);
+    s->index_P = s->P;
     s->h_pair_gene.swap(pair_gene);
     s->n_groups = -1;
     s->prepared = false;
