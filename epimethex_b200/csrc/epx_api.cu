@@ -100,6 +100,8 @@ struct epx_session {
     /* pooled probe groups (epx_session_run_groups) */
     std::vector<int32_t> h_probe_idx, h_pair_gene; /* host copies of the index, to validate group lists */
     std::vector<int64_t> h_row_ptr;
+    DevBuf<double> upload_stage;                    /* 2 x 64 MB: flat H2D chunks before re-spacing */
+    cudaEvent_t ev_up[3] = { nullptr, nullptr, nullptr };
     int64_t index_P = -1;                           /* methylation row count the index was validated against */
     DevBuf<GroupDesc> g_desc;
     DevBuf<BlockDesc> g_blocks;
@@ -199,6 +201,7 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = s->scal.reserve(8);
     if (e != cudaSuccess) {
         epx_session_destroy(s);
@@ -222,6 +225,8 @@ void epx_session_destroy(epx_session *s)
     s->g_val[0].release(); s->g_val[1].release(); s->g_lab[0].release(); s->g_lab[1].release();
     s->grp.release(); s->grp_stat.release(); s->grp_na.release(); s->grp_dnum.release();
     for (int i = 0; i < 8; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < 3; i++) if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
+    s->upload_stage.release();
     if (s->side) cudaStreamDestroy(s->side);
     if (s->staging) cudaFreeHost(s->staging);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -251,18 +256,25 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
         /* contiguous host matrix: flat copies at full PCIe rate into a staging buffer, rows re-spaced on the
          * device (a 2-D copy with 3.7 KB rows runs at a fraction of the link rate) */
         const int64_t chunk_rows = (64ll << 20) / (n_samples * 8) > 0 ? (64ll << 20) / (n_samples * 8) : 1;
-        DevBuf<double> stage;
-        EPX_CUDA(stage.reserve((size_t)(chunk_rows * n_samples)));
-        for (int64_t r0 = 0; r0 < n_probes; r0 += chunk_rows) {
+        /* two staging buffers kept by the session: the re-spacing of chunk i (side stream) overlaps the copy of
+         * chunk i+1 (main stream) */
+        EPX_CUDA(s->upload_stage.reserve((size_t)(2 * chunk_rows * n_samples)));
+        cudaEvent_t copied = s->ev_up[0], spaced[2] = { s->ev_up[1], s->ev_up[2] };
+        cudaError_t e = cudaSuccess;
+        int64_t i = 0;
+        for (int64_t r0 = 0; r0 < n_probes && e == cudaSuccess; r0 += chunk_rows, i++) {
             const int64_t nr = (n_probes - r0) < chunk_rows ? (n_probes - r0) : chunk_rows;
-            cudaError_t e = cudaMemcpyAsync(stage.p, rows + r0 * n_samples, (size_t)(nr * n_samples) * 8,
-                                            cudaMemcpyHostToDevice, s->stream);
-            if (e == cudaSuccess) e = launch_respace_rows(stage.p, s->meth_own.p + r0 * dld, nr, n_samples, dld, s->stream);
-            if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); stage.release(); return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e)); }
+            double *buf = s->upload_stage.p + (size_t)((i & 1) * chunk_rows * n_samples);
+            if (i >= 2) e = cudaStreamWaitEvent(s->stream, spaced[i & 1], 0); /* buffer free again */
+            if (e == cudaSuccess) e = cudaMemcpyAsync(buf, rows + r0 * n_samples, (size_t)(nr * n_samples) * 8, cudaMemcpyHostToDevice, s->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(copied, s->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s->side, copied, 0);
+            if (e == cudaSuccess) e = launch_respace_rows(buf, s->meth_own.p + r0 * dld, nr, n_samples, dld, s->side);
+            if (e == cudaSuccess) e = cudaEventRecord(spaced[i & 1], s->side);
         }
-        cudaError_t e = cudaStreamSynchronize(s->stream);
-        stage.release();
-        if (e != cudaSuccess) return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e));
+        cudaError_t e2 = cudaStreamSynchronize(s->side);
+        if (e == cudaSuccess) e = e2;
+        if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e)); }
     } else {
         EPX_CUDA(cudaMemcpy2DAsync(s->meth_own.p, (size_t)dld * 8, rows, (size_t)ld * 8, (size_t)n_samples * 8,
                                    (size_t)n_probes, cudaMemcpyHostToDevice, s->stream));
