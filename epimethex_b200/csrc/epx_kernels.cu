@@ -514,13 +514,16 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
 }
 
 /* k_probe_rank, one warp per referenced probe */
+template <int EPS> __host__ __device__ constexpr int rank_warps() { return SORT_WARPS; }
+
 template <int EPS>
-__global__ void __launch_bounds__(SORT_WARPS * 32, (EPS <= 16 ? 3 : 2)) k_probe_rank_w(RankParams p)
+__global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k_probe_rank_w(RankParams p)
 {
-    __shared__ unsigned short s_ord[SORT_WARPS][32 * EPS];
+    constexpr int RW = rank_warps<EPS>();
+    __shared__ unsigned short s_ord[RW][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
-    const int64_t nw = (int64_t)gridDim.x * SORT_WARPS;
-    for (int64_t slot = (int64_t)blockIdx.x * SORT_WARPS + warp; slot < p.U; slot += nw) {
+    const int64_t nw = (int64_t)gridDim.x * RW;
+    for (int64_t slot = (int64_t)blockIdx.x * RW + warp; slot < p.U; slot += nw) {
         const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
         unsigned khi[EPS], klo[EPS];
 #pragma unroll
@@ -1255,10 +1258,15 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
         }
         return cudaGetLastError();
     }
-    int64_t grid = (p.U + SORT_WARPS - 1) / SORT_WARPS;
-    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
     switch (sort_eps(p.n)) {
-#define EPX_CASE(E) case E: k_probe_rank_w<E><<<(unsigned)grid, SORT_WARPS * 32, 0, st>>>(p); break;
+#define EPX_CASE(E)                                                                          \
+    case E: {                                                                                \
+        constexpr int RW = rank_warps<E>();                                                  \
+        int64_t grid = (p.U + RW - 1) / RW;                                                  \
+        if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;                      \
+        k_probe_rank_w<E><<<(unsigned)grid, RW * 32, 0, st>>>(p);                            \
+        break;                                                                               \
+    }
         EPX_FOR_SORT_VARIANTS(EPX_CASE)
 #undef EPX_CASE
     default: return cudaErrorInvalidValue;

@@ -187,22 +187,25 @@ template <int EPS> struct WarpSort {
         }
 
         /* rare: two values closer than the coarse resolution came out inverted. Odd-even transposition on the
-         * full keys (only neighbours inside a run of equal coarse keys can ever swap). */
+         * full values, over the marked neighbour pairs only: a pair is marked when its two POSITIONS share a coarse
+         * key, which swaps inside such a run do not change, and there are only a handful of them per row. Each lane
+         * owns the marked pairs that start at its own positions. */
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < EPS; r++) s_ord[lane * EPS + r] = (unsigned short)(v[r] & IDXM);
         __syncwarp();
-        /* same[k]: positions k and k+1 share a coarse key (a property of the position pair, invariant under
-         * swaps inside a run). One bit per owned pair; a lane owns pairs k = 2*(lane + 32*q) + parity. */
         for (;;) {
             int swapped = 0;
 #pragma unroll
             for (int parity = 0; parity < 2; parity++) {
-                for (int k = 2 * lane + parity; k + 1 < n; k += 64) {
+                /* position k = lane*EPS + r: its parity is that of r (EPS even), or of the lane when EPS == 1 */
+                unsigned m = EPS > 1 ? (eqm & (parity ? 0xaaaaaaaau : 0x55555555u)) : (((lane & 1) == parity) ? eqm : 0u);
+                while (m) {
+                    const int k = lane * EPS + (__ffs(m) - 1);
+                    m &= m - 1;
                     const unsigned short ia = s_ord[k], ib = s_ord[k + 1];
                     const double ka = value(ia), kb = value(ib);
                     if ((DESC ? ka < kb : ka > kb) || (ka == kb && ia > ib)) {
-                        /* only possible inside a run of equal coarse keys */
                         s_ord[k] = ib; s_ord[k + 1] = ia;
                         swapped = 1;
                     }
@@ -217,7 +220,7 @@ template <int EPS> struct WarpSort {
             unsigned short o = padval;
             if (k < n) {
                 o = s_ord[k];
-                if (k + 1 < n && value(o) == value(s_ord[k + 1])) o |= 0x8000u;
+                if (((eqm >> r) & 1u) && value(o) == value(s_ord[k + 1])) o |= 0x8000u;
             }
             out[r] = o;
         }

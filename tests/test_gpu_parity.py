@@ -217,3 +217,30 @@ def test_heavily_tied_expression(sess):
     for te in (True, False):
         got = run_gpu(sess, x, y, idx, te=te)
         assert_parity(got, run_oracle(x, y, idx, te=te), f"tied expression te={te}")
+
+
+@pytest.mark.parametrize("n", [30, 474, 1000, 1500])
+def test_values_closer_than_the_sort_keys_coarse_resolution(sess, n):
+    """The warp sort orders rows by a 22/23-bit coarse key packed with the sample index and repairs neighbours that share a
+    coarse key from the full doubles. Rows whose values differ only in the last mantissa bits make every neighbour pair
+    collide: long runs of distinct values with equal coarse keys, plus exact ties mixed in. (The rows keep an ordinary
+    spread: a row that varies ONLY in its last bits makes the reference's own long-double Pearson noisy at 1e-8.)"""
+    rng = np.random.default_rng(n)
+    G, P = 24, 160
+    ulp = 2.0 ** -52
+    x = rng.normal(7.0, 2.0, (G, n))                                    # expression: ordinary values ...
+    half = n // 2
+    x[:, half:2 * half] = x[:, :half] * (1 + ulp * rng.integers(-2, 3, (G, half)))   # ... each with a twin 0-2 ulps away
+    y = rng.random((P, n))
+    y[:40, half:2 * half] = y[:40, :half] * (1 + ulp * rng.integers(-2, 3, (40, half)))      # twins 0-2 ulps apart
+    y[40:80] = np.round(y[40:80], 2) * (1 + ulp * rng.integers(0, 3, (40, n)))               # ~100 levels x 3 near-values: long runs
+    y[80:120] = np.where(y[80:120] < 0.5, 0.25, 0.75) * (1 + ulp * rng.integers(0, 4, (40, n)))  # two clusters of 4 near-values
+    row_ptr = np.arange(0, G * 20 + 1, 20, dtype=np.int64)
+    probe_idx = rng.integers(0, P, G * 20).astype(np.int32)
+
+    class Idx:
+        pass
+    idx = Idx(); idx.row_ptr, idx.probe_idx = row_ptr, probe_idx
+    for te, tm in ((True, False), (False, True)):
+        got = run_gpu(sess, x, y, idx, te=te, tm=tm)
+        assert_parity(got, run_oracle(x, y, idx, te=te, tm=tm), f"near-ties n={n} te={te} tm={tm}")
