@@ -203,6 +203,7 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = s->scal.reserve(8);
+    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 8 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel */
     if (e != cudaSuccess) {
         epx_session_destroy(s);
         return fail(err, errlen, EPX_ECUDA, "session setup: %s", cudaGetErrorString(e));
@@ -513,7 +514,7 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;
     pp.pair_slot = s->pair_slot.p; pp.xc = s->xc.p; pp.ldx = s->ldx; pp.lab8 = s->lab8.p; pp.ldl = s->ldl;
-    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items; pp.pair_gene = s->pair_gene.p; pp.n_pairs = (int)Np; pp.pair_begin = 0;
+    pp.perm = s->perm.p; pp.gene_aux = s->gene_aux.p; pp.items = s->items.p; pp.n_items = (int)s->n_items; pp.queue = s->scal.p + 6; pp.pair_gene = s->pair_gene.p; pp.n_pairs = (int)Np; pp.pair_begin = 0;
     pp.n = n; pp.m = m; pp.test_t = opt.test_meth_t;
     pp.exact_ok = ((double)m * (double)m < 10000.0) ? 1 : 0;
     pp.warp_smem = 0;

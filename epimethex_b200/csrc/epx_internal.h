@@ -77,6 +77,7 @@ struct PairParams {
     const double *gene_aux;
     const Item *items;
     int n_items;
+    int32_t *queue;           /* k_pair_stats2: {next ticket, warps done}, both 0 between launches */
     const int32_t *pair_gene; /* [Np] gene of each pair (CTA-per-pair kernel) */
     int pair_begin, n_pairs;  /* CTA-per-pair kernel: pairs [pair_begin, n_pairs) */
     int n, m;

@@ -62,11 +62,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (spin > (1u << 26)) __trap();
 }
 
+/* 8-byte load from a shared-window address */
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
 /* out of line on purpose: the continued fraction + lgamma code is big, and inlining it into the pair loop pushes
  * the kernel past the instruction cache */
 __device__ __noinline__ double t_two_sided_p_call(double t, double df) { return epx_t_two_sided_p(t, df); }
 
 constexpr int PAIR2_WARPS = 4;
+
+/* sorted walk: two running words of two biased 16-bit fields each, ra = [cUP-cMID | cUP-cDOWN],
+ * rb = [cMID-cDOWN | cUP]; the table holds, per sample, what its label adds to them (32-bit wrap-around sums:
+ * a field value stays within bias +- 1024, so no carry ever crosses a field in the decoded value) */
+constexpr unsigned WALK_BIAS = 0x40004000u;
+constexpr unsigned WALK_A0 = 0x00010001u, WALK_B0 = 0x00000001u; /* UP:     +1 +1 |  0 +1 */
+constexpr unsigned WALK_A1 = 0xffff0000u, WALK_B1 = 0x00010000u; /* Medium: -1  0 | +1  0 */
+constexpr unsigned WALK_A2 = 0xffffffffu, WALK_B2 = 0xffff0000u; /* Down:    0 -1 | -1  0 */
 
 __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
 
@@ -74,7 +90,7 @@ __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t
  * deferred Pearson r [32] | (t-mode) deferred Welch t and df [32][3] each */
 __host__ __device__ inline size_t pair2_warp_smem(int n, int64_t ld, int64_t ldo, bool tmode)
 {
-    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 4) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
+    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 8) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
                    (tmode ? (size_t)ITEM_PAIRS * 6 * 8 + (size_t)ITEM_PAIRS * 4 : 0));
 }
 
@@ -91,8 +107,9 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     uint64_t *bar = (uint64_t *)base;
     const uint32_t stageb = rowb + ordb;
     unsigned char *buf0 = base + 16; /* stage s lives at buf0 + s*stageb */
-    uint32_t *tab = (uint32_t *)(base + 16 + 2 * (size_t)stageb);
-    double *s_out = (double *)((unsigned char *)tab + round16((size_t)(n + 1) * 4));
+    uint2 *tab = (uint2 *)(base + 16 + 2 * (size_t)stageb);
+    const uint32_t tab_sa = smem_u32(tab);
+    double *s_out = (double *)((unsigned char *)tab + round16((size_t)(n + 1) * 8));
     double *s_med = s_out + 16;
     double *s_r = s_med + 8;
     double *s_mg = s_r + ITEM_PAIRS;          /* t mode: group means [ITEM_PAIRS][3] */
@@ -109,7 +126,6 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     const int gw = blockIdx.x * PAIR2_WARPS + warp, nw = gridDim.x * PAIR2_WARPS;
     const double dm = (double)m, dn_ = (double)n, inv_n = 1.0 / dn_, inv_m = 1.0 / dm;
     const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
-    const unsigned T1P = (unsigned)t1 * 0x00100401u, T2P = (unsigned)t2 * 0x00100401u;
     const bool m_even = (m & 1) == 0;
     const bool has_unl = 3 * m != n; /* n mod 3 != 0: the lowest-expression samples carry no label */
 
@@ -148,12 +164,18 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
         if (fpi >= 0) issue(fpi, fsl);
     }
 
-    for (; it < p.n_items; it += nw) {
-        /* descriptor + probe list of the NEXT item, fetched now so the latency hides behind this item */
-        const bool has_next = it + nw < p.n_items;
+    while (it < p.n_items) {
+        /* Work items are handed out dynamically (they hold 1..32 pairs: a static round-robin leaves the busiest
+         * warp with 1.75x the mean load on the SKCM index). The first item of a warp is its own number, the
+         * following ones come from a global ticket counter. Descriptor + probe list of the NEXT item are fetched
+         * now so that the latency hides behind this item. */
+        int nit = 0;
+        if (lane == 0) nit = nw + atomicAdd(p.queue, 1);
+        nit = __shfl_sync(FULL, nit, 0);
+        const bool has_next = nit < p.n_items;
         nmy_pi = -1; nmy_slot = -1;
         if (has_next) {
-            nitem = p.items[it + nw];
+            nitem = p.items[nit];
             if (lane < nitem.count) { nmy_pi = p.probe_idx[nitem.begin + lane]; nmy_slot = p.pair_slot[nitem.begin + lane]; }
         }
         if (item.gene != cur_gene) {
@@ -161,14 +183,18 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             const double *xc = p.xc + (int64_t)cur_gene * p.ldx;
             const uint8_t *lab = p.lab8 + (int64_t)cur_gene * p.ldl;
             labs = 0; labs64 = 0;
-            if (lane == 0) tab[n] = 0u;
+            if (lane == 0) tab[n] = make_uint2(0u, 0u);
             __syncwarp(); /* the previous gene's walk is done with tab */
 #pragma unroll
             for (int e = 0; e < EPL; e++) {
                 const int s = lane + 32 * e;
                 unsigned l = 3;
                 double v = 0.0;
-                if (s < n) { v = xc[s]; l = lab[s]; tab[s] = l < 3 ? (1u << (10 * l)) : 0u; }
+                if (s < n) {
+                    v = xc[s]; l = lab[s];
+                    tab[s] = make_uint2(l == 0 ? WALK_A0 : (l == 1 ? WALK_A1 : (l == 2 ? WALK_A2 : 0u)),
+                                        l == 0 ? WALK_B0 : (l == 1 ? WALK_B1 : (l == 2 ? WALK_B2 : 0u)));
+                }
                 xc_r[e] = v;
                 if (EPL <= 16) labs |= l << (2 * e); else labs64 |= (unsigned long long)l << (2 * e);
             }
@@ -281,73 +307,107 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             } else {
                 ow[0] = ((const unsigned short *)ordw)[lane];
             }
-            /* pass 1: label increments (one 10-bit count field per group) of this lane's positions. Pad
-             * positions (k >= n) carry index n and no tie mark (k_probe_rank_w): tab[n] = 0 makes them inert. */
-            unsigned inc[EPW];
-            unsigned tot = 0;
+            bool anytie = false;
+            if (!TMODE) {
+                unsigned tb = 0;
 #pragma unroll
-            for (int e = 0; e < EPW; e++) {
-                const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
-                inc[e] = tab[h & 0x7fffu];
-                tot += inc[e];
+                for (int c = 0; c < (EPW + 1) / 2; c++) tb |= ow[c];
+                anytie = __any_sync(FULL, (tb & 0x80008000u) != 0u);
             }
-            unsigned incl = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned t = __shfl_up_sync(FULL, incl, d);
-                if (lane >= d) incl += t;
-            }
-            /* pass 2: running counts; medians by an exact zero-field test on the group that just grew (every
-             * field < 512, so adding 511 sets a field's bit 9 iff it is non-zero); KS at tie-run ends */
-            unsigned cnt = incl - tot;
-            unsigned hw1 = 0, hw2 = 0; /* per group: 1 + position (inside this lane) of the t1-th / t2-th member */
-            unsigned ce = 0;           /* counts at the last tie-run end seen (0 = nothing evaluated yet: all differences 0) */
-            int mx01 = 0, mn01 = 0, mx02 = 0, mn02 = 0, mx12 = 0, mn12 = 0;
-#pragma unroll
-            for (int e = 0; e < EPW; e++) {
-                cnt += inc[e];
-                hw1 += ((~((cnt ^ T1P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
-                if (!TMODE) {
-                    /* evaluate the ECDF differences only at the end of a tie run: inside a run re-evaluate the
-                     * previous run end (idempotent under max/min) */
-                    const unsigned h = (e & 1) ? (ow[e / 2] >> 16) : (ow[e / 2] & 0xffffu);
-                    const unsigned tie = 0u - ((h >> 15) & 1u); /* all ones inside a tie run */
-                    ce = (ce & tie) | (cnt & ~tie);
-                    const int c0 = ce & 1023, c1 = (ce >> 10) & 1023, c2 = ce >> 20;
-                    const int d01 = c0 - c1, d02 = c0 - c2, d12 = c1 - c2;
-                    mx01 = max(mx01, d01); mn01 = min(mn01, d01);
-                    mx02 = max(mx02, d02); mn02 = min(mn02, d02);
-                    mx12 = max(mx12, d12); mn12 = min(mn12, d12);
-                }
-            }
-            if (m_even) { /* warp-uniform: the upper middle element is a different one only for even group sizes */
-                unsigned c2nd = incl - tot;
+            /* One pass, lane-local: ra = [cUP-cMID | cUP-cDOWN], rb = [cMID-cDOWN | cUP] as biased 16-bit halves
+             * of one word each, advanced by the per-sample increment pair of the gene's table (pad positions
+             * k >= n carry index n, whose entry is 0). The ECDF differences are evaluated with packed 16x2
+             * max/min (VIMNMX.U16x2) at the END of every tie run; the counts in front of the lane are added
+             * afterwards (max(prefix + x) = prefix + max(x)). */
+            unsigned ra = WALK_BIAS, rb = WALK_BIAS;
+            unsigned mxa = 0u, mna = 0xffffffffu, mxb = 0u, mnb = 0xffffffffu;
+            /* table entry of the sample in the low / high half of an order word whose tie marks are cleared:
+             * indices are <= 1024, so bits 13-15 of the low half are 0 and (w >> 13) is 8 * the high index */
+#define EPX_TAB_OF(w, e) lds_u2(((e) & 1) ? tab_sa + ((w) >> 13) : tab_sa + 8u * __byte_perm((w), 0u, 0x4410u))
+            if (TMODE || !anytie) {
 #pragma unroll
                 for (int e = 0; e < EPW; e++) {
-                    c2nd += inc[e];
-                    hw2 += ((~((c2nd ^ T2P) + 0x1ff7fdffu)) >> 9 & inc[e]) * (unsigned)(e + 1);
+                    const unsigned w = TMODE ? (ow[e / 2] & 0x7fff7fffu) : ow[e / 2];
+                    const uint2 inc = EPX_TAB_OF(w, e);
+                    ra += inc.x; rb += inc.y;
+                    if (!TMODE) {
+                        mxa = __vmaxu2(mxa, ra); mna = __vminu2(mna, ra);
+                        mxb = __vmaxu2(mxb, rb); mnb = __vminu2(mnb, rb);
+                    }
                 }
-            }
-            if (!m_even) hw2 = hw1;
-            if (hw1 | hw2) { /* this lane holds a middle element of some group */
-                const unsigned short *ord16 = (const unsigned short *)ordw + lane * EPW;
+            } else {
 #pragma unroll
-                for (int g = 0; g < 3; g++) {
-                    const unsigned a1 = (hw1 >> (10 * g)) & 1023u, a2 = (hw2 >> (10 * g)) & 1023u;
-                    if (a1) s_med[g * 2] = row[ord16[a1 - 1] & 0x7fffu];
-                    if (a2) s_med[g * 2 + 1] = row[ord16[a2 - 1] & 0x7fffu];
+                for (int e = 0; e < EPW; e++) {
+                    const unsigned w = ow[e / 2] & 0x7fff7fffu;
+                    const uint2 inc = EPX_TAB_OF(w, e);
+                    ra += inc.x; rb += inc.y;
+                    if (!(ow[e / 2] & ((e & 1) ? 0x80000000u : 0x8000u))) { /* inside a tie run nothing is evaluated */
+                        mxa = __vmaxu2(mxa, ra); mna = __vminu2(mna, ra);
+                        mxb = __vmaxu2(mxb, rb); mnb = __vminu2(mnb, rb);
+                    }
                 }
             }
+#undef EPX_TAB_OF
+            /* inclusive scan of the lane totals (32-bit wrap-around sums of the two 16-bit fields) */
+            const unsigned da = ra - WALK_BIAS, db = rb - WALK_BIAS;
+            unsigned ia = da, ib = db;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned ta = __shfl_up_sync(FULL, ia, d), tb2 = __shfl_up_sync(FULL, ib, d);
+                if (lane >= d) { ia += ta; ib += tb2; }
+            }
+            const unsigned ea = ia - da, eb = ib - db; /* counts in front of this lane */
             int d01 = 0, d02 = 0, d12 = 0;
             if (!TMODE) {
-                d01 = warp_max_i(max(mx01, -mn01)); d02 = warp_max_i(max(mx02, -mn02)); d12 = warp_max_i(max(mx12, -mn12));
+                int k01 = 0, k02 = 0, k12 = 0;
+                if (mxa != 0u) { /* the lane evaluated at least one position */
+                    const unsigned xa = mxa + ea, na_ = mna + ea, xb = mxb + eb, nb = mnb + eb;
+                    k01 = max((int)(xa >> 16) - 0x4000, 0x4000 - (int)(na_ >> 16));
+                    k02 = max((int)(xa & 0xffffu) - 0x4000, 0x4000 - (int)(na_ & 0xffffu));
+                    k12 = max((int)(xb >> 16) - 0x4000, 0x4000 - (int)(nb >> 16));
+                }
+                d01 = warp_max_i(k01); d02 = warp_max_i(k02); d12 = warp_max_i(k12);
             }
-            bool anytie = false;
-            if (p.exact_ok) {
-                bool mytie = false;
+            /* medians: the lane whose positions hold the t-th member of a group is found from the scanned
+             * counts; its EPW positions are then searched by EPW lanes at once (ballot + popc) */
+            if (m >= 1) {
+                const unsigned eab = ea + WALK_BIAS, iab = ia + WALK_BIAS;
+                const int ce0 = (int)(eb & 0xffffu), ci0 = (int)(ib & 0xffffu);
+                const int ce1 = ce0 - ((int)(eab >> 16) - 0x4000), ci1 = ci0 - ((int)(iab >> 16) - 0x4000);
+                const int ce2 = ce0 - ((int)(eab & 0xffffu) - 0x4000), ci2 = ci0 - ((int)(iab & 0xffffu) - 0x4000);
+                const unsigned short *ord16 = (const unsigned short *)ordw;
 #pragma unroll
-                for (int c = 0; c < (EPW + 1) / 2; c++) mytie = mytie || (ow[c] & 0x80008000u);
-                anytie = __any_sync(FULL, mytie);
+                for (int g = 0; g < 3; g++) {
+                    const int ce = g == 0 ? ce0 : (g == 1 ? ce1 : ce2), ci = g == 0 ? ci0 : (g == 1 ? ci1 : ci2);
+                    const unsigned labc = g == 0 ? WALK_A0 : (g == 1 ? WALK_A1 : WALK_A2);
+                    const unsigned b1 = __ballot_sync(FULL, ce < t1 && t1 <= ci);
+                    unsigned b2 = b1;
+                    if (m_even) b2 = __ballot_sync(FULL, ce < t2 && t2 <= ci);
+                    if (EPW <= 16) {
+                        /* lanes 0-15 look for the lower middle element, lanes 16-31 for the upper one */
+                        const int hs = lane >> 4, jp = lane & 15;
+                        const int L = __ffs(hs ? b2 : b1) - 1;
+                        const int k = (hs ? t2 : t1) - __shfl_sync(FULL, ce, L);
+                        const unsigned h = jp < EPW ? ord16[L * EPW + jp] & 0x7fffu : (unsigned)n;
+                        const bool isg = tab[h].x == labc;
+                        const unsigned bal = (__ballot_sync(FULL, isg) >> (16 * hs)) & 0xffffu;
+                        if (isg && __popc(bal & ((1u << jp) - 1u)) == k - 1) s_med[g * 2 + hs] = row[h];
+                    } else {
+#pragma unroll
+                        for (int hs = 0; hs < 2; hs++) {
+                            if (hs == 1 && !m_even) continue;
+                            const int L = __ffs(hs ? b2 : b1) - 1;
+                            const int k = (hs ? t2 : t1) - __shfl_sync(FULL, ce, L);
+                            const unsigned h = ord16[L * EPW + lane] & 0x7fffu;
+                            const bool isg = tab[h].x == labc;
+                            const unsigned bal = __ballot_sync(FULL, isg);
+                            if (isg && __popc(bal & ((1u << lane) - 1u)) == k - 1) {
+                                s_med[g * 2 + hs] = row[h];
+                                if (!m_even) s_med[g * 2 + 1] = row[h];
+                            }
+                        }
+                    }
+                }
             }
             __syncwarp();
             /* labels: 0 UP, 1 Medium, 2 Down */
@@ -411,8 +471,8 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                         int r0 = 0, r1 = 0, r2 = 0;
                         for (int k = 0; k < n; k++) {
                             const unsigned short v = ord16[k];
-                            const unsigned w = tab[v & 0x7fffu];
-                            r0 += w & 1u; r1 += (w >> 10) & 1u; r2 += (w >> 20) & 1u;
+                            const unsigned w = tab[v & 0x7fffu].x;
+                            r0 += w == WALK_A0; r1 += w == WALK_A1; r2 += w == WALK_A2;
                             if (!(v & 0x8000u)) {
                                 if (r0 + r1 >= 2) ties[0] = 1;
                                 if (r0 + r2 >= 2) ties[1] = 1;
@@ -429,7 +489,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 for (int c = 0; c < 3; c++) {
                     if (guard[c] != 0) { /* difference != 0 || is.na(difference) */
                         dnum[c] = dd[c] * m;
-                        stat[c] = (double)dnum[c] / (dm * dm);
+                        stat[c] = (double)dd[c] * inv_m; /* = dnum / m^2 to the last bit or one ulp */
                         pv[c] = (p.exact_ok && !ties[c]) ? p.lut_exact[dd[c]] : p.lut_asym[dd[c]];
                     } else na |= 1u << (EPX_P_UP_MID + c);
                 }
@@ -478,6 +538,12 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
         __syncwarp();
         item = nitem;
         my_pi = nmy_pi; my_slot = nmy_slot;
+        it = nit;
+    }
+    /* the last warp to leave re-arms the queue for the next launch */
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(p.queue + 1, 1) == nw - 1) { p.queue[0] = 0; p.queue[1] = 0; }
     }
 }
 

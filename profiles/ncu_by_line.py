@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Join `ncu --page source --csv` (SASS view, per-instruction executed counts) with nvdisasm line info of the
 in-tree libepx.so, to get executed warp-instructions per CUDA source line.
-usage: ncu_by_line.py <report.ncu-rep> <kernel-regex> <mangled-substring> <units> [top]"""
+usage: ncu_by_line.py <report.ncu-rep> <kernel-regex> <mangled-substring> <units> [top] [samples]
+(a 6th argument 'samples' sorts by warp-stall samples instead of executed instructions)"""
 import csv, os, re, subprocess, sys, tempfile
 from collections import Counter, defaultdict
 rep, kre, mangled, units = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
@@ -45,6 +46,8 @@ for addr, src, e, s in ins:
     ops[key][re.sub(r'^@!?U?P\d+\s+', '', src).split()[0].split('.')[0]] += e
 print('total warp-instr %d = %.1f per unit; %d SASS instr; mapped %d' % (tot, tot / units, len(ins), sum(1 for a in ins if (a[0] - base) in lines)))
 allsmp = sum(smp.values()) or 1
-for key, e in by.most_common(top):
+order = smp.most_common(top) if len(sys.argv) > 6 and sys.argv[6] == 'samples' else by.most_common(top)
+for key, _ in order:
+    e = by[key]
     print('%-22s %8.1f /unit %5.1f%%  stall-samples %5.1f%%  %s' % ('%s:%d' % key, e / units, 100.0 * e / tot, 100.0 * smp[key] / allsmp,
           ' '.join('%s:%.0f' % (o, c / units) for o, c in ops[key].most_common(5))))
