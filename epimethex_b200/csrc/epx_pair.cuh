@@ -86,12 +86,12 @@ constexpr unsigned WALK_A2 = 0xffffffffu, WALK_B2 = 0xffff0000u; /* Down:    0 -
 
 __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-/* per-warp shared memory: 2 mbarriers | 2 x (row, order) | label table | 16 output slots | 8 median slots |
- * deferred Pearson r [32] | (t-mode) deferred Welch t and df [32][3] each */
+/* per-warp shared memory: 2 mbarriers | 2 x (row, order) | label table | median owners [32][6] u16 (+ pad) |
+ * (t-mode) Pearson r [32], group means and var/m [32][3] each, defined-test bits [32] */
 __host__ __device__ inline size_t pair2_warp_smem(int n, int64_t ld, int64_t ldo, bool tmode)
 {
-    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 8) + 16 * 8 + 8 * 8 + ITEM_PAIRS * 8 +
-                   (tmode ? (size_t)ITEM_PAIRS * 6 * 8 + (size_t)ITEM_PAIRS * 4 : 0));
+    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 8) + ITEM_PAIRS * 6 * 2 + 128 +
+                   (tmode ? (size_t)ITEM_PAIRS * 8 + (size_t)ITEM_PAIRS * 6 * 8 + (size_t)ITEM_PAIRS * 4 : 0));
 }
 
 template <int EPL, bool TMODE>
@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     unsigned char *buf0 = base + 16; /* stage s lives at buf0 + s*stageb */
     uint2 *tab = (uint2 *)(base + 16 + 2 * (size_t)stageb);
     const uint32_t tab_sa = smem_u32(tab);
-    double *s_out = (double *)((unsigned char *)tab + round16((size_t)(n + 1) * 8));
-    double *s_med = s_out + 16;
-    double *s_r = s_med + 8;
+    /* per pair of the item: (lane << 6 | rank inside the lane) of the lower/upper middle element of each group */
+    unsigned short *s_own = (unsigned short *)((unsigned char *)tab + round16((size_t)(n + 1) * 8));
+    double *s_r = (double *)(s_own + ITEM_PAIRS * 6 + 64); /* t mode: Pearson r [ITEM_PAIRS] */
     double *s_mg = s_r + ITEM_PAIRS;          /* t mode: group means [ITEM_PAIRS][3] */
     double *s_va = s_mg + 3 * ITEM_PAIRS;     /* t mode: var_g / m   [ITEM_PAIRS][3] */
     int *s_ok = (int *)(s_va + 3 * ITEM_PAIRS); /* t mode: bit c = Welch test c is defined */
@@ -151,6 +151,10 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     bool x_const = true;
     int pm[6] = { 0, 0, 0, 0, 0, 0 };
     const uint16_t *perm_g = nullptr;
+
+    /* sums of pair jj of the item, kept by lane jj for the epilogue */
+    double st_syy = 0.0, st_sxy = 0.0;
+    unsigned st_ks = 0; /* KS numerators / m: 3 x 9 bits, then 3 bits "the pooled pair of groups holds a tie" */
 
     int it = gw;
     Item item, nitem;
@@ -211,7 +215,6 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
         }
 
         for (int jj = 0; jj < item.count; jj++) {
-            const int j = item.begin + jj;
             const int pi = __shfl_sync(FULL, my_pi, jj);
             /* prefetch the next pair's row + order into the other stage */
             int npi, nsl;
@@ -220,16 +223,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             __syncwarp(); /* every lane has finished reading the stage about to be refilled */
             if (npi >= 0) issue(npi, nsl);
 
-            if (pi < 0) { /* annotated probe without data: all-NA column (R/EpimethexAnalysis.R:375-394) */
-                if (lane < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + lane] = EPX_NAN;
-                if (lane < 3) { p.pair_stat[(int64_t)j * 3 + lane] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + lane] = -1; }
-                if (lane == 0) {
-                    p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
-                    s_r[jj] = EPX_NAN;
-                    if (TMODE) s_ok[jj] = 0;
-                }
-                continue;
-            }
+            if (pi < 0) continue; /* annotated probe without data: the epilogue writes its all-NA row */
             const double *row = (const double *)(buf0 + (use ? stageb : 0u));
             const uint32_t *ordw = (const uint32_t *)(buf0 + (use ? stageb : 0u) + rowb);
             if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; }
@@ -368,172 +362,208 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 }
                 d01 = warp_max_i(k01); d02 = warp_max_i(k02); d12 = warp_max_i(k12);
             }
-            /* medians: the lane whose positions hold the t-th member of a group is found from the scanned
-             * counts; its EPW positions are then searched by EPW lanes at once (ballot + popc) */
+            /* medians: the lane whose positions hold the t-th member of a group knows it from the scanned counts
+             * and leaves (lane, rank inside the lane) for the item's epilogue, which does the search */
             if (m >= 1) {
                 const unsigned eab = ea + WALK_BIAS, iab = ia + WALK_BIAS;
                 const int ce0 = (int)(eb & 0xffffu), ci0 = (int)(ib & 0xffffu);
                 const int ce1 = ce0 - ((int)(eab >> 16) - 0x4000), ci1 = ci0 - ((int)(iab >> 16) - 0x4000);
                 const int ce2 = ce0 - ((int)(eab & 0xffffu) - 0x4000), ci2 = ci0 - ((int)(iab & 0xffffu) - 0x4000);
-                const unsigned short *ord16 = (const unsigned short *)ordw;
-#pragma unroll
-                for (int g = 0; g < 3; g++) {
-                    const int ce = g == 0 ? ce0 : (g == 1 ? ce1 : ce2), ci = g == 0 ? ci0 : (g == 1 ? ci1 : ci2);
-                    const unsigned labc = g == 0 ? WALK_A0 : (g == 1 ? WALK_A1 : WALK_A2);
-                    const unsigned b1 = __ballot_sync(FULL, ce < t1 && t1 <= ci);
-                    unsigned b2 = b1;
-                    if (m_even) b2 = __ballot_sync(FULL, ce < t2 && t2 <= ci);
-                    if (EPW <= 16) {
-                        /* lanes 0-15 look for the lower middle element, lanes 16-31 for the upper one */
-                        const int hs = lane >> 4, jp = lane & 15;
-                        const int L = __ffs(hs ? b2 : b1) - 1;
-                        const int k = (hs ? t2 : t1) - __shfl_sync(FULL, ce, L);
-                        const unsigned h = jp < EPW ? ord16[L * EPW + jp] & 0x7fffu : (unsigned)n;
-                        const bool isg = tab[h].x == labc;
-                        const unsigned bal = (__ballot_sync(FULL, isg) >> (16 * hs)) & 0xffffu;
-                        if (isg && __popc(bal & ((1u << jp) - 1u)) == k - 1) s_med[g * 2 + hs] = row[h];
-                    } else {
-#pragma unroll
-                        for (int hs = 0; hs < 2; hs++) {
-                            if (hs == 1 && !m_even) continue;
-                            const int L = __ffs(hs ? b2 : b1) - 1;
-                            const int k = (hs ? t2 : t1) - __shfl_sync(FULL, ce, L);
-                            const unsigned h = ord16[L * EPW + lane] & 0x7fffu;
-                            const bool isg = tab[h].x == labc;
-                            const unsigned bal = __ballot_sync(FULL, isg);
-                            if (isg && __popc(bal & ((1u << lane) - 1u)) == k - 1) {
-                                s_med[g * 2 + hs] = row[h];
-                                if (!m_even) s_med[g * 2 + 1] = row[h];
-                            }
+                unsigned short *own = s_own + jj * 6;
+                const unsigned lane6 = (unsigned)lane << 6;
+                if (ce0 < t1 && t1 <= ci0) own[0] = (unsigned short)(lane6 | (unsigned)(t1 - ce0));
+                if (ce1 < t1 && t1 <= ci1) own[2] = (unsigned short)(lane6 | (unsigned)(t1 - ce1));
+                if (ce2 < t1 && t1 <= ci2) own[4] = (unsigned short)(lane6 | (unsigned)(t1 - ce2));
+                if (m_even) {
+                    if (ce0 < t2 && t2 <= ci0) own[1] = (unsigned short)(lane6 | (unsigned)(t2 - ce0));
+                    if (ce1 < t2 && t2 <= ci1) own[3] = (unsigned short)(lane6 | (unsigned)(t2 - ce1));
+                    if (ce2 < t2 && t2 <= ci2) own[5] = (unsigned short)(lane6 | (unsigned)(t2 - ce2));
+                }
+            }
+            unsigned tiebits = 0;
+            if (!TMODE && p.exact_ok && anytie) {
+                /* small groups with tied values: ks.test drops to the asymptotic p-value when the POOLED pair of
+                 * groups holds a tie. Rare and tiny (m < 100): one lane walks the order. */
+                if (lane == 0) {
+                    const unsigned short *ord16 = (const unsigned short *)ordw;
+                    int r0 = 0, r1 = 0, r2 = 0;
+                    for (int k = 0; k < n; k++) {
+                        const unsigned short v = ord16[k];
+                        const unsigned w = tab[v & 0x7fffu].x;
+                        r0 += w == WALK_A0; r1 += w == WALK_A1; r2 += w == WALK_A2;
+                        if (!(v & 0x8000u)) {
+                            if (r0 + r1 >= 2) tiebits |= 1u;
+                            if (r0 + r2 >= 2) tiebits |= 2u;
+                            if (r1 + r2 >= 2) tiebits |= 4u;
+                            r0 = r1 = r2 = 0;
                         }
                     }
                 }
+                tiebits = __shfl_sync(FULL, tiebits, 0);
             }
-            __syncwarp();
-            /* labels: 0 UP, 1 Medium, 2 Down */
-            const double medUP = (s_med[0] + s_med[1]) * 0.5, medMID = (s_med[2] + s_med[3]) * 0.5,
-                         medDOWN = (s_med[4] + s_med[5]) * 0.5;
-
-            /* ---- guard of calculateTtest (R/Functions.R:193): are all rank-paired differences identical? ---- */
-            int guard[3] = { -1, -1, -1 };
-            if (m >= 2) {
-                const double a0 = row[pm[0]], a1 = row[pm[1]], b0 = row[pm[2]], b1 = row[pm[3]], e0 = row[pm[4]],
-                             e1 = row[pm[5]];
-                const double dd[3] = { a0 - b0, a0 - e0, b0 - e0 };
-                const bool eq[3] = { dd[0] == a1 - b1, dd[1] == a1 - e1, dd[2] == b1 - e1 };
-                const int offA[3] = { 0, 0, m }, offB[3] = { m, 2 * m, 2 * m };
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    if (!eq[c]) { guard[c] = 1; continue; }
-                    int differs = 0; /* rare: walk the whole group */
-                    for (int i = 2 + lane; i < m; i += 32)
-                        if (row[perm_g[offA[c] + i]] - row[perm_g[offB[c] + i]] != dd[c]) differs = 1;
-                    guard[c] = __any_sync(FULL, differs) ? 1 : 0;
-                }
+            /* ---- everything else of the pair is scalar work: lane jj keeps the sums for the item's epilogue ---- */
+            if (lane == jj) {
+                st_syy = syy; st_sxy = sxy;
+                st_ks = (unsigned)d01 | ((unsigned)d02 << 9) | ((unsigned)d12 << 18) | (tiebits << 27);
             }
-
-            /* ---- tests ---- */
-            double stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
-            int dnum[3] = { -1, -1, -1 };
-            unsigned na = 0;
-            double r = EPX_NAN;
-            const bool r_ok = (!x_const && syy != 0.0 && n >= 3);
-            if (r_ok) {
-                r = sxy * rsx * rsqrt(syy);
-                r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
-            } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
-            if (TMODE) {
-                /* Welch t, df and p are computed in the deferred pass (one comparison per lane); here only what
-                 * decides NA: the guard, at least two observations, and t.test's "data are essentially constant" */
+            if (TMODE && lane < 3) {
                 const double sc = 1.0 / (dm * (dm - 1.0));
-                const double mg[3] = { mg0, mg1, mg2 };
-                const double va[3] = { ss0 * sc, ss1 * sc, ss2 * sc }; /* var_g / m */
-                const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
-                int okbits = 0;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const double thr = 10.0 * 2.220446049250313e-16 * fmax(fabs(mg[ga_[c]]), fabs(mg[gb_[c]]));
-                    const bool ok = guard[c] == 1 && m >= 2 && !(va[ga_[c]] + va[gb_[c]] < thr * thr);
-                    if (ok) okbits |= 1 << c; else na |= 1u << (EPX_P_UP_MID + c);
-                }
-                if (lane < 3) {
-                    s_mg[jj * 3 + lane] = lane == 0 ? mg0 : (lane == 1 ? mg1 : mg2);
-                    s_va[jj * 3 + lane] = lane == 0 ? va[0] : (lane == 1 ? va[1] : va[2]);
-                }
-                if (lane == 3) s_ok[jj] = okbits;
-            } else {
-                int ties[3] = { 0, 0, 0 };
-                if (p.exact_ok && anytie) {
-                    /* small groups with tied values: ks.test drops to the asymptotic p-value when the POOLED
-                     * pair of groups holds a tie. Rare and tiny (m < 100): one lane walks the order. */
-                    if (lane == 0) {
-                        const unsigned short *ord16 = (const unsigned short *)ordw;
-                        int r0 = 0, r1 = 0, r2 = 0;
-                        for (int k = 0; k < n; k++) {
-                            const unsigned short v = ord16[k];
-                            const unsigned w = tab[v & 0x7fffu].x;
-                            r0 += w == WALK_A0; r1 += w == WALK_A1; r2 += w == WALK_A2;
-                            if (!(v & 0x8000u)) {
-                                if (r0 + r1 >= 2) ties[0] = 1;
-                                if (r0 + r2 >= 2) ties[1] = 1;
-                                if (r1 + r2 >= 2) ties[2] = 1;
-                                r0 = r1 = r2 = 0;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; c++) ties[c] = __shfl_sync(FULL, ties[c], 0);
-                }
-                const int dd[3] = { d01, d02, d12 };
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    if (guard[c] != 0) { /* difference != 0 || is.na(difference) */
-                        dnum[c] = dd[c] * m;
-                        stat[c] = (double)dd[c] * inv_m; /* = dnum / m^2 to the last bit or one ulp */
-                        pv[c] = (p.exact_ok && !ties[c]) ? p.lut_exact[dd[c]] : p.lut_asym[dd[c]];
-                    } else na |= 1u << (EPX_P_UP_MID + c);
-                }
+                s_mg[jj * 3 + lane] = lane == 0 ? mg0 : (lane == 1 ? mg1 : mg2);
+                s_va[jj * 3 + lane] = (lane == 0 ? ss0 : (lane == 1 ? ss1 : ss2)) * sc; /* var_g / m */
             }
-
-            /* ---- stage the row of results, then one coalesced store per table ---- */
-            s_out[0] = medDOWN; s_out[1] = medMID; s_out[2] = medUP;
-            s_out[3] = medUP - medMID; s_out[4] = medUP - medDOWN; s_out[5] = medMID - medDOWN;
-            s_out[6] = pv[0]; s_out[7] = pv[1]; s_out[8] = pv[2];
-            s_out[9] = r;
-            s_out[11] = stat[0]; s_out[12] = stat[1]; s_out[13] = stat[2];
-            if (lane == 0) s_r[jj] = r;
-            __syncwarp();
-            /* columns 6-8 (t mode) and 10 are written by the deferred pass */
-            if (lane < PAIR_COLS - 1 && !(TMODE && lane >= 6 && lane <= 8)) p.pair[(int64_t)j * PAIR_COLS + lane] = s_out[lane];
-            if (!TMODE && lane >= 11 && lane < 14) p.pair_stat[(int64_t)j * 3 + (lane - 11)] = s_out[lane];
-            if (lane >= 14 && lane < 17) p.pair_dnum[(int64_t)j * 3 + (lane - 14)] = lane == 14 ? dnum[0] : (lane == 15 ? dnum[1] : dnum[2]);
-            if (lane == 17) p.pair_na[j] = (uint16_t)na;
         }
 
-        /* ---- deferred Student-t tails of the whole item, one per lane ---- */
+        /* ---- epilogue of the item, one pair per lane: medians, guard, tests, p-values, result rows ---- */
         __syncwarp();
-        constexpr int PER = TMODE ? 4 : 1;
-        for (int q = lane; q < item.count * PER; q += 32) {
-            const int jj = q / PER, slot = q % PER;
-            double pq = EPX_NAN;
-            int col = EPX_PEARSON_P;
-            if (TMODE && slot < 3) {
-                /* stats::t.test(var.equal = FALSE): se^2 = vx/nx + vy/ny, Welch-Satterthwaite df */
-                const int ga = slot == 2 ? 1 : 0, gb = slot == 0 ? 1 : 2;
-                double t = EPX_NAN;
-                if ((s_ok[jj] >> slot) & 1) {
-                    const double A = s_va[jj * 3 + ga], B = s_va[jj * 3 + gb], se2 = A + B;
-                    t = (s_mg[jj * 3 + ga] - s_mg[jj * 3 + gb]) / sqrt(se2);
-                    const double df = se2 * se2 * (dm - 1.0) / (A * A + B * B);
-                    pq = t_two_sided_p_call(t, df);
-                }
-                p.pair_stat[(int64_t)(item.begin + jj) * 3 + slot] = t;
-                col = EPX_P_UP_MID + slot;
+        if (lane < item.count) {
+            const int64_t j = (int64_t)item.begin + lane;
+            double *orow = p.pair + j * PAIR_COLS;
+            if (my_pi < 0) { /* annotated probe without data: all-NA column (R/EpimethexAnalysis.R:375-394) */
+#pragma unroll
+                for (int c = 0; c < PAIR_COLS; c++) orow[c] = EPX_NAN;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { p.pair_stat[j * 3 + c] = EPX_NAN; p.pair_dnum[j * 3 + c] = -1; }
+                p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
+                if (TMODE) { s_r[lane] = EPX_NAN; s_ok[lane] = 0; }
             } else {
-                const double rr = s_r[jj];
-                if (!isnan(rr)) pq = epx_pearson_p_tab(rr, p.pt_tab, p.pt_n, dn_ - 2.0);
+                const double *grow = p.meth + (int64_t)my_pi * p.ld;
+                const uint16_t *gord = p.ord + (int64_t)my_slot * p.ldo;
+                /* group medians: walk the EPW positions of the owning lane (labels: 0 UP, 1 Medium, 2 Down) */
+                double med[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+                if (m >= 1) {
+#pragma unroll
+                    for (int g = 0; g < 3; g++) {
+                        const unsigned labc = g == 0 ? WALK_A0 : (g == 1 ? WALK_A1 : WALK_A2);
+                        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                        for (int hs = 0; hs < 2; hs++) {
+                            if (hs == 1 && !m_even) { v1 = v0; continue; }
+                            const unsigned o = s_own[lane * 6 + g * 2 + hs];
+                            const int L = (int)(o >> 6), k = (int)(o & 63u);
+                            const uint16_t *src = gord + L * EPW;
+                            unsigned hit = 0;
+                            int c = 0;
+                            if (EPW >= 8) {
+#pragma unroll
+                                for (int q4 = 0; q4 < EPW / 8; q4++) {
+                                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src) + q4);
+                                    const unsigned w4[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+                                    for (int e = 0; e < 8; e++) {
+                                        const unsigned h = ((e & 1) ? (w4[e / 2] >> 16) : w4[e / 2]) & 0x7fffu;
+                                        const bool is = lds_u2(tab_sa + 8u * h).x == labc;
+                                        c += is;
+                                        if (is && c == k) hit = h;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < EPW; e++) {
+                                    const unsigned h = __ldg(src + e) & 0x7fffu;
+                                    const bool is = lds_u2(tab_sa + 8u * h).x == labc;
+                                    c += is;
+                                    if (is && c == k) hit = h;
+                                }
+                            }
+                            const double v = __ldg(grow + hit);
+                            if (hs == 0) v0 = v; else v1 = v;
+                        }
+                        med[g] = (v0 + v1) * 0.5;
+                    }
+                }
+                const double medUP = med[0], medMID = med[1], medDOWN = med[2];
+
+                /* guard of calculateTtest (R/Functions.R:193): are all rank-paired differences identical? */
+                int guard[3] = { -1, -1, -1 };
+                if (m >= 2) {
+                    const double a0 = __ldg(grow + pm[0]), a1 = __ldg(grow + pm[1]), b0 = __ldg(grow + pm[2]),
+                                 b1 = __ldg(grow + pm[3]), e0 = __ldg(grow + pm[4]), e1 = __ldg(grow + pm[5]);
+                    const double dd[3] = { a0 - b0, a0 - e0, b0 - e0 };
+                    const bool eq[3] = { dd[0] == a1 - b1, dd[1] == a1 - e1, dd[2] == b1 - e1 };
+                    const int offA[3] = { 0, 0, m }, offB[3] = { m, 2 * m, 2 * m };
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        guard[c] = 1;
+                        if (eq[c]) { /* rare: walk the whole group */
+                            int differs = 0;
+                            for (int i = 2; i < m && !differs; i++)
+                                if (__ldg(grow + perm_g[offA[c] + i]) - __ldg(grow + perm_g[offB[c] + i]) != dd[c]) differs = 1;
+                            guard[c] = differs;
+                        }
+                    }
+                }
+
+                unsigned na = 0;
+                double r = EPX_NAN;
+                if (!x_const && st_syy != 0.0 && n >= 3) {
+                    r = st_sxy * rsx * rsqrt(st_syy);
+                    r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+                } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
+                orow[0] = medDOWN; orow[1] = medMID; orow[2] = medUP;
+                orow[3] = medUP - medMID; orow[4] = medUP - medDOWN; orow[5] = medMID - medDOWN;
+                orow[9] = r;
+                if (TMODE) {
+                    /* Welch t, df and p follow in the second stage (one comparison per lane); here only what
+                     * decides NA: the guard, at least two observations, and t.test's "data are essentially constant" */
+                    const double mg[3] = { s_mg[lane * 3], s_mg[lane * 3 + 1], s_mg[lane * 3 + 2] };
+                    const double va[3] = { s_va[lane * 3], s_va[lane * 3 + 1], s_va[lane * 3 + 2] };
+                    const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
+                    int okbits = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double thr = 10.0 * 2.220446049250313e-16 * fmax(fabs(mg[ga_[c]]), fabs(mg[gb_[c]]));
+                        const bool ok = guard[c] == 1 && m >= 2 && !(va[ga_[c]] + va[gb_[c]] < thr * thr);
+                        if (ok) okbits |= 1 << c; else na |= 1u << (EPX_P_UP_MID + c);
+                        p.pair_dnum[j * 3 + c] = -1;
+                    }
+                    s_ok[lane] = okbits;
+                    s_r[lane] = r;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const int dk = (int)((st_ks >> (9 * c)) & 511u);
+                        double stat = EPX_NAN, pv = EPX_NAN;
+                        int dnum = -1;
+                        if (guard[c] != 0) { /* difference != 0 || is.na(difference) */
+                            dnum = dk * m;
+                            stat = (double)dk * inv_m; /* = dnum / m^2 to the last bit or one ulp */
+                            pv = (p.exact_ok && !((st_ks >> (27 + c)) & 1u)) ? __ldg(p.lut_exact + dk) : __ldg(p.lut_asym + dk);
+                        } else na |= 1u << (EPX_P_UP_MID + c);
+                        orow[6 + c] = pv;
+                        p.pair_stat[j * 3 + c] = stat;
+                        p.pair_dnum[j * 3 + c] = dnum;
+                    }
+                    orow[10] = isnan(r) ? EPX_NAN : epx_pearson_p_tab(r, p.pt_tab, p.pt_n, dn_ - 2.0);
+                }
+                p.pair_na[j] = (uint16_t)na;
             }
-            p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
+        }
+
+        if (TMODE) {
+            /* ---- second stage: Student-t tails of the whole item, one per lane ---- */
+            __syncwarp();
+            for (int q = lane; q < item.count * 4; q += 32) {
+                const int jj = q / 4, slot = q % 4;
+                double pq = EPX_NAN;
+                int col = EPX_PEARSON_P;
+                if (slot < 3) {
+                    /* stats::t.test(var.equal = FALSE): se^2 = vx/nx + vy/ny, Welch-Satterthwaite df */
+                    const int ga = slot == 2 ? 1 : 0, gb = slot == 0 ? 1 : 2;
+                    double t = EPX_NAN;
+                    if ((s_ok[jj] >> slot) & 1) {
+                        const double A = s_va[jj * 3 + ga], B = s_va[jj * 3 + gb], se2 = A + B;
+                        t = (s_mg[jj * 3 + ga] - s_mg[jj * 3 + gb]) / sqrt(se2);
+                        const double df = se2 * se2 * (dm - 1.0) / (A * A + B * B);
+                        pq = t_two_sided_p_call(t, df);
+                    }
+                    p.pair_stat[(int64_t)(item.begin + jj) * 3 + slot] = t;
+                    col = EPX_P_UP_MID + slot;
+                } else {
+                    const double rr = s_r[jj];
+                    if (!isnan(rr)) pq = epx_pearson_p_tab(rr, p.pt_tab, p.pt_n, dn_ - 2.0);
+                }
+                p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
+            }
         }
         __syncwarp();
         item = nitem;
