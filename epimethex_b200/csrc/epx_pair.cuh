@@ -156,6 +156,24 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     double st_syy = 0.0, st_sxy = 0.0;
     unsigned st_ks = 0; /* KS numerators / m: 3 x 9 bits, then 3 bits "the pooled pair of groups holds a tie" */
 
+    /* A gene change is split in two: the centred expression vector (registers) and the label bytes are requested
+     * before the epilogue of the previous item, which needs neither; the label table is rebuilt after it. */
+    constexpr int NLQ = (EPL * 32 + 127) / 128; /* 4 labels per 32-bit load */
+    unsigned lraw[NLQ];
+    int pend_gene = -1;
+    auto load_gene = [&](int g) {
+        const double *xc = p.xc + (int64_t)g * p.ldx;
+        const uint32_t *lab = (const uint32_t *)(p.lab8 + (int64_t)g * p.ldl);
+#pragma unroll
+        for (int e = 0; e < EPL; e++) {
+            const int s = lane + 32 * e;
+            xc_r[e] = s < n ? xc[s] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < NLQ; q++) lraw[q] = 4 * (lane + 32 * q) < (int)p.ldl ? lab[lane + 32 * q] : 0x03030303u;
+        pend_gene = g;
+    };
+
     int it = gw;
     Item item, nitem;
     item.gene = -1; item.begin = 0; item.count = 0; item.pad = 0;
@@ -166,6 +184,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
         if (lane < item.count) { my_pi = p.probe_idx[item.begin + lane]; my_slot = p.pair_slot[item.begin + lane]; }
         const int fpi = __shfl_sync(FULL, my_pi, 0), fsl = __shfl_sync(FULL, my_slot, 0);
         if (fpi >= 0) issue(fpi, fsl);
+        load_gene(item.gene);
     }
 
     while (it < p.n_items) {
@@ -182,25 +201,21 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
             nitem = p.items[nit];
             if (lane < nitem.count) { nmy_pi = p.probe_idx[nitem.begin + lane]; nmy_slot = p.pair_slot[nitem.begin + lane]; }
         }
-        if (item.gene != cur_gene) {
-            cur_gene = item.gene;
-            const double *xc = p.xc + (int64_t)cur_gene * p.ldx;
-            const uint8_t *lab = p.lab8 + (int64_t)cur_gene * p.ldl;
-            labs = 0; labs64 = 0;
+        if (pend_gene >= 0) {
+            /* second half of the gene change (the loads were issued before the previous item's epilogue) */
+            cur_gene = pend_gene;
+            pend_gene = -1;
             if (lane == 0) tab[n] = make_uint2(0u, 0u);
-            __syncwarp(); /* the previous gene's walk is done with tab */
 #pragma unroll
-            for (int e = 0; e < EPL; e++) {
-                const int s = lane + 32 * e;
-                unsigned l = 3;
-                double v = 0.0;
-                if (s < n) {
-                    v = xc[s]; l = lab[s];
-                    tab[s] = make_uint2(l == 0 ? WALK_A0 : (l == 1 ? WALK_A1 : (l == 2 ? WALK_A2 : 0u)),
-                                        l == 0 ? WALK_B0 : (l == 1 ? WALK_B1 : (l == 2 ? WALK_B2 : 0u)));
+            for (int q = 0; q < NLQ; q++) {
+#pragma unroll
+                for (int b4 = 0; b4 < 4; b4++) {
+                    const int s4 = 4 * (lane + 32 * q) + b4;
+                    const unsigned l = (lraw[q] >> (8 * b4)) & 0xffu;
+                    if (s4 < n)
+                        tab[s4] = make_uint2(l == 0 ? WALK_A0 : (l == 1 ? WALK_A1 : (l == 2 ? WALK_A2 : 0u)),
+                                             l == 0 ? WALK_B0 : (l == 1 ? WALK_B1 : (l == 2 ? WALK_B2 : 0u)));
                 }
-                xc_r[e] = v;
-                if (EPL <= 16) labs |= l << (2 * e); else labs64 |= (unsigned long long)l << (2 * e);
             }
             const double *ga = p.gene_aux + 4 * (int64_t)cur_gene;
             x_const = ga[0] == 0.0;
@@ -212,6 +227,16 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 pm[4] = perm_g[2 * m]; pm[5] = perm_g[2 * m + 1];
             }
             __syncwarp();
+            if (TMODE) { /* label of this lane's element e, for the per-group sums */
+                labs = 0; labs64 = 0;
+#pragma unroll
+                for (int e = 0; e < EPL; e++) {
+                    const int s = lane + 32 * e;
+                    unsigned l = 3;
+                    if (s < n) { const unsigned a = tab[s].x; l = a == WALK_A0 ? 0u : (a == WALK_A1 ? 1u : (a == WALK_A2 ? 2u : 3u)); }
+                    if (EPL <= 16) labs |= l << (2 * e); else labs64 |= (unsigned long long)l << (2 * e);
+                }
+            }
         }
 
         for (int jj = 0; jj < item.count; jj++) {
@@ -412,6 +437,8 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 s_va[jj * 3 + lane] = (lane == 0 ? ss0 : (lane == 1 ? ss1 : ss2)) * sc; /* var_g / m */
             }
         }
+
+        if (has_next && nitem.gene != cur_gene) load_gene(nitem.gene);
 
         /* ---- epilogue of the item, one pair per lane: medians, guard, tests, p-values, result rows ---- */
         __syncwarp();
