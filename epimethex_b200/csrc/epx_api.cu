@@ -202,8 +202,8 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = s->scal.reserve(8);
-    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 8 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel */
+    if (e == cudaSuccess) e = s->scal.reserve(16);
+    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 16 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel; [8], [9]: of the rank kernel */
     if (e != cudaSuccess) {
         epx_session_destroy(s);
         return fail(err, errlen, EPX_ECUDA, "session setup: %s", cudaGetErrorString(e));
@@ -509,7 +509,7 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
 
     RankParams rp;
     rp.meth = s->meth; rp.ld = s->ld; rp.uniq_probe = s->uniq_probe.p; rp.U = s->U; rp.n = n; rp.npad = next_pow2(n);
-    rp.ord = s->ord.p; rp.ldo = s->ldo; rp.one = 1u;
+    rp.ord = s->ord.p; rp.ldo = s->ldo; rp.one = 1u; rp.queue = s->scal.p + 8;
 
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;

@@ -60,6 +60,7 @@ struct RankParams {
     uint16_t *ord;          /* [U][ldo]: sample index of the k-th smallest value | 0x8000 when equal to the next */
     int64_t ldo;
     unsigned one;           /* = 1, opaque to the compiler (see ce_fma) */
+    int32_t *queue;         /* k_probe_rank_w: {next ticket, warps done}, both 0 between launches */
 };
 
 struct PairParams {

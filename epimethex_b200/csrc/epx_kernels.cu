@@ -522,8 +522,12 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
     constexpr int RW = rank_warps<EPS>();
     __shared__ unsigned short s_ord[RW][32 * EPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
-    const int64_t nw = (int64_t)gridDim.x * RW;
-    for (int64_t slot = (int64_t)blockIdx.x * RW + warp; slot < p.U; slot += nw) {
+    const int nw = (int)gridDim.x * RW;
+    /* Rows are handed out by a ticket counter: rows with tied or nearly tied values take the longer exact path, and
+     * a static split of a one-wave grid lost 6 % to that imbalance (a grid of 8 CTAs per SM, 3 resident, lost more
+     * in its partial last wave). The other warps of the SM cover the latency of the ticket. */
+    int64_t slot = (int64_t)blockIdx.x * RW + warp;
+    while (slot < p.U) {
         const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
         unsigned khi[EPS], klo[EPS];
 #pragma unroll
@@ -550,6 +554,13 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
             for (int r = 0; r < EPS; r++)
                 if (lane * EPS + r < p.ldo) o[r] = out[r];
         }
+        int nslot = 0;
+        if (lane == 0) nslot = nw + atomicAdd(p.queue, 1);
+        slot = __shfl_sync(FULL, nslot, 0);
+    }
+    if (lane == 0) { /* the last warp to leave re-arms the queue for the next launch */
+        __threadfence();
+        if (atomicAdd(p.queue + 1, 1) == nw - 1) { p.queue[0] = 0; p.queue[1] = 0; }
     }
 }
 
@@ -1262,8 +1273,15 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
 #define EPX_CASE(E)                                                                          \
     case E: {                                                                                \
         constexpr int RW = rank_warps<E>();                                                  \
+        /* persistent grid of exactly one wave: a grid of 8 CTAs per SM with 3 resident ran 2.67 waves */ \
+        static int per_sm = 0;                                                               \
+        if (per_sm == 0) {                                                                   \
+            int nb = 0;                                                                      \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w<E>, RW * 32, 0) != cudaSuccess || nb < 1) nb = 1; \
+            per_sm = nb;                                                                     \
+        }                                                                                    \
         int64_t grid = (p.U + RW - 1) / RW;                                                  \
-        if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;                      \
+        if (grid > (int64_t)sm_count * per_sm) grid = (int64_t)sm_count * per_sm;            \
         k_probe_rank_w<E><<<(unsigned)grid, RW * 32, 0, st>>>(p);                            \
         break;                                                                               \
     }
