@@ -1330,9 +1330,12 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
     if (p.n_items <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
         const size_t stage = big_stage_bytes(p.ld, p.ldo), labb = (size_t)((p.n + 15) & ~15);
-        const bool two = 2 * stage + labb + 4096 <= 227 * 1024;
+        /* two single-stage CTAs per SM when they fit (while one sits in its barriers and scalar tail the other
+         * computes), else one CTA with two stages, else one stage */
+        const bool pair_up = 2 * (stage + labb + 2048) <= 227 * 1024;
+        const bool two = !pair_up && 2 * stage + labb + 4096 <= 227 * 1024;
         const size_t smem = (two ? 2 : 1) * stage + labb;
-        int grid = sm_count; /* one 512-thread CTA per SM, persistent */
+        int grid = sm_count * (pair_up ? 2 : 1); /* 512-thread CTAs, persistent */
         if (grid > p.n_pairs - p.pair_begin) grid = p.n_pairs - p.pair_begin;
         if (grid < 1) return cudaSuccess;
         if (two) {
