@@ -1,6 +1,6 @@
 /*
  * epx_ctasort.cuh — one CTA (8 warps) orders one long row (1024 < n <= 16384 values, e.g. the 9,000-sample
- * pan-cancer shape) held in shared memory: every warp sorts 1024-value chunks with the register bitonic sort of
+ * pan-cancer shape) held in shared memory: every warp sorts 512-value chunks with the register bitonic sort of
  * epx_warpsort.cuh, then log2(chunks) merge passes (merge path: each thread produces a contiguous slice of the
  * output after a binary search for its split point) combine them. Exact and stable: equal values keep ascending
  * sample index, because chunks are contiguous index ranges and merges prefer the left run on ties.
@@ -11,10 +11,11 @@
 namespace epx {
 
 constexpr int CTASORT_THREADS = 256;
-constexpr int CTASORT_CHUNK = 1024;
+constexpr int CTASORT_EPS = 16;                    /* values per lane in the register sort of a chunk */
+constexpr int CTASORT_CHUNK = 32 * CTASORT_EPS;    /* 512: the 1,024-value network costs 3.4x the 512-value one, a merge pass far less */
 
 /* entries of each of the two index buffers: a whole number of chunks, so that the second buffer can double as
- * the warp sorts' scratch (1024 entries per chunk being sorted) while the first one is being filled */
+ * the warp sorts' scratch (one chunk of entries per chunk being sorted) while the first one is being filled */
 __host__ __device__ inline int ctasort_entries(int n) { return (n + CTASORT_CHUNK - 1) / CTASORT_CHUNK * CTASORT_CHUNK; }
 
 /* shared memory needed besides the row itself */
@@ -81,18 +82,18 @@ __device__ unsigned short *cta_sort_row(const double *s_val, const int n, unsign
     for (int c = warp; c < nchunks; c += nwarps) {
         const int base = c * CTASORT_CHUNK;
         const int nc = min(CTASORT_CHUNK, n - base);
-        unsigned khi[32], klo[32];
+        unsigned khi[CTASORT_EPS], klo[CTASORT_EPS];
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
+        for (int e = 0; e < CTASORT_EPS; e++) {
             key_halves(s_val[base + min(lane + 32 * e, nc - 1)], khi[e], klo[e]);
             if (DESC) { khi[e] = ~khi[e]; klo[e] = ~klo[e]; }
         }
-        unsigned short out[32];
-        WarpSort<32>::template order<DESC>(khi, klo, nc, lane, s_b + c * CTASORT_CHUNK,
+        unsigned short out[CTASORT_EPS];
+        WarpSort<CTASORT_EPS>::template order<DESC>(khi, klo, nc, lane, s_b + c * CTASORT_CHUNK,
                                            [&](int i) { return s_val[base + i]; }, (unsigned short)0xffffu, one, out);
 #pragma unroll
-        for (int r = 0; r < 32; r++) {
-            const int k = lane * 32 + r;
+        for (int r = 0; r < CTASORT_EPS; r++) {
+            const int k = lane * CTASORT_EPS + r;
             if (k < nc) s_a[base + k] = (unsigned short)(base + (out[r] & 0x7fff));
         }
     }

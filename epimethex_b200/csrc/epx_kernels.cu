@@ -274,10 +274,23 @@ __global__ void __launch_bounds__(CTASORT_THREADS, 2) k_probe_rank(RankParams p)
     double *s_val = (double *)smem;
     unsigned short *s_a = (unsigned short *)(s_val + ((n + 1) & ~1));
     unsigned short *s_b = s_a + ctasort_entries(n);
+    /* the row comes in as ONE bulk copy (cp.async.bulk + mbarrier) when it is 16-byte aligned: a per-thread loop of
+     * loads and shared stores ran as ~35 dependent round trips to DRAM and took a quarter of the kernel */
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t rowbytes = (uint32_t)((n + 1) & ~1) * 8u;
+    const bool bulk = ((((uintptr_t)p.meth) | ((uintptr_t)p.ld * 8u)) & 15u) == 0;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    uint32_t phase = 0;
     for (int64_t slot = blockIdx.x; slot < p.U; slot += gridDim.x) {
         const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
-        __syncthreads(); /* the previous row is done with the buffers */
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
+        __syncthreads(); /* the previous row is done with the buffers (and the barrier is initialised) */
+        if (bulk) {
+            if (threadIdx.x == 0) { mbar_expect_tx(&bar, rowbytes); bulk_g2s(s_val, row, rowbytes, &bar); }
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
+        }
         __syncthreads();
         const unsigned short *ord = cta_sort_row<false>(s_val, n, s_a, s_b, p.one);
         uint16_t *o = p.ord + slot * p.ldo;
