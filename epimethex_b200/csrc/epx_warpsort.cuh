@@ -27,6 +27,13 @@ __device__ __forceinline__ void ce_fma(unsigned &a, unsigned &b, const unsigned 
     b = mx;
 }
 
+/* Cross-lane half of a compare-exchange, in place: v = upper ? max(v, t) : min(v, t) as two predicated VIMNMX
+ * (the C form compiles to a min into a temporary, a predicated max over it and, inside loops, a move back). */
+__device__ __forceinline__ void ce_half(unsigned &v, const unsigned t, const unsigned upper)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@!p min.u32 %0, %0, %1;\n\t@p max.u32 %0, %0, %1;\n\t}" : "+r"(v) : "r"(t), "r"(upper));
+}
+
 template <int EPS> struct WarpSort {
     static constexpr int N = 32 * EPS;
     static constexpr int IDXB = (EPS == 1 ? 5 : EPS == 2 ? 6 : EPS == 4 ? 7 : EPS == 8 ? 8 : EPS == 16 ? 9 : 10);
@@ -79,20 +86,24 @@ template <int EPS> struct WarpSort {
         for (int q = 1; q < 32; q <<= 1) { /* phase k = 2*EPS*q */
             {
                 const int lm = 2 * q - 1;
-                const bool lower = (lane & q) == 0;
+                const unsigned upper = (unsigned)(lane & q);
                 unsigned t[EPS];
 #pragma unroll
                 for (int r = 0; r < EPS; r++) t[r] = __shfl_xor_sync(FULL, v[r], lm);
 #pragma unroll
-                for (int r = 0; r < EPS; r++) v[r] = lower ? min(v[r], t[r ^ (EPS - 1)]) : max(v[r], t[r ^ (EPS - 1)]);
+                for (int r = 0; r < EPS; r++) ce_half(v[r], t[r ^ (EPS - 1)], upper);
             }
-#pragma unroll 1
-            for (int j = q >> 1; j >= 1; j >>= 1) {
-                const bool lower = (lane & j) == 0;
+            /* the up to four cross-lane half-cleaners as straight-line code behind warp-uniform tests: only the
+             * phase loop has a back edge (ptxas pays ~16 register moves per back edge of a loop over v[]) */
 #pragma unroll
-                for (int r = 0; r < EPS; r++) {
-                    const unsigned t = __shfl_xor_sync(FULL, v[r], j);
-                    v[r] = lower ? min(v[r], t) : max(v[r], t);
+            for (int j = 8; j >= 1; j >>= 1) {
+                if (j <= (q >> 1)) {
+                    const unsigned upper = (unsigned)(lane & j);
+#pragma unroll
+                    for (int r = 0; r < EPS; r++) {
+                        const unsigned t = __shfl_xor_sync(FULL, v[r], j);
+                        ce_half(v[r], t, upper);
+                    }
                 }
             }
             thread_tail(v, EPS / 2, one, minus1);
