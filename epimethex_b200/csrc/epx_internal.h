@@ -46,7 +46,6 @@ struct GeneTestParams {
     int32_t *ref_gene;
     int32_t *status;
     int test_t, data_linear, fc_from_means;
-    int batch;              /* k_gene_tests_w, t mode: genes per warp and batch (set by launch_gene_tests) */
     double *gene;           /* [G][15] */
     uint16_t *gene_na;
     int32_t *gene_dnum;     /* [G][3] */

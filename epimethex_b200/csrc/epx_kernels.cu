@@ -372,7 +372,6 @@ __global__ void __launch_bounds__(SORT_WARPS * 32, (EPS <= 16 ? 3 : 2)) k_gene_s
 
 /* k_gene_tests, one warp per gene: the column in the gene's descending order is staged in shared memory */
 constexpr int GT_WARPS = 4;
-constexpr int GT_BATCH = 8; /* genes per warp and batch in t mode: 24 Student-t tails on 24 lanes */
 
 template <int EPS>
 __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p)
@@ -386,15 +385,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
     const int len[3] = { nUP, nM, nD };
     const int ca[3] = { 0, 0, 1 }, cb[3] = { 1, 2, 2 };
     const int nw = gridDim.x * GT_WARPS;
-    /* t mode: a warp takes p.batch (<= GT_BATCH) consecutive genes and evaluates their 3 x batch Student-t tails
-     * (a continued fraction of ~2,000 instructions each) on as many lanes at once, instead of 3 lanes per gene */
-    double *s_t = (double *)smem + (size_t)GT_WARPS * (32 * EPS + 2) + (size_t)warp * (2 * 3 * GT_BATCH);
-    double *s_df = s_t + 3 * GT_BATCH;
-    const int gb = p.test_t ? p.batch : 1;
-    for (int g0 = (blockIdx.x * GT_WARPS + warp) * gb; g0 < p.G; g0 += nw * gb) {
-      const int nb = min(gb, p.G - g0);
-      for (int bi = 0; bi < nb; bi++) {
-        const int g = g0 + bi;
+    for (int g = blockIdx.x * GT_WARPS + warp; g < p.G; g += nw) {
         const double *x = p.expr + (int64_t)g * n;
         const uint16_t *perm = p.perm + (int64_t)g * n;
         __syncwarp();
@@ -500,11 +491,9 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
                     const double ma = c == 2 ? mean[1] : mean[0], va = c == 2 ? var[1] : var[0];
                     const double mb = c == 0 ? mean[1] : mean[2], vb = c == 0 ? var[1] : var[2];
                     if (epx_welch(ma, va, (double)la, mb, vb, (double)lb, &t, &df) == 0) {
-                        stat = t; ok = true;
-                        s_t[bi * 3 + c] = t; s_df[bi * 3 + c] = df;
+                        stat = t; pv = epx_t_two_sided_p(t, df); ok = true;
                     }
                 }
-                if (!ok) s_df[bi * 3 + c] = EPX_NAN; /* no test: the batched stage writes NA */
             } else if (gd != 0 && la > 0 && lb > 0) {
                 dn = c == 0 ? dmaxv[0] : (c == 1 ? dmaxv[1] : dmaxv[2]);
                 const int tv = c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]);
@@ -516,7 +505,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
             double *o = p.gene + (int64_t)g * GENE_COLS;
             const bool exact_pending = !p.test_t && ok && (double)la * (double)lb < 10000.0 &&
                                        !(c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]));
-            if (!exact_pending && !p.test_t) o[3 + c] = pv; /* otherwise lane 0 (KS, exact) or the batched stage (t) writes it */
+            if (!exact_pending) o[3 + c] = pv; /* otherwise lane 0 writes it below */
             o[6 + c] = stat;
             p.gene_dnum[(int64_t)g * 3 + c] = dn;
             if (!ok) na = (uint16_t)((1u << (3 + c)) | (1u << (6 + c)));
@@ -534,15 +523,6 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
         na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 1);
         na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 2);
         if (lane == 0) p.gene_na[g] = na;
-      }
-      if (p.test_t) {
-        __syncwarp();
-        if (lane < 3 * nb) {
-            const double df = s_df[lane];
-            p.gene[(int64_t)(g0 + lane / 3) * GENE_COLS + 3 + lane % 3] = isnan(df) ? EPX_NAN : epx_t_two_sided_p(s_t[lane], df);
-        }
-        __syncwarp();
-      }
     }
 }
 
@@ -1274,21 +1254,12 @@ cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_
         k_gene_tests<<<p.G, 128, (size_t)(p.n + 2) * sizeof(double), st>>>(p);
         return cudaGetLastError();
     }
-    /* one gene per warp; in t mode up to GT_BATCH genes per warp, as many as still leave about one wave of warps */
-    GeneTestParams q = p;
-    q.batch = 1;
-    if (p.test_t) {
-        const int wave = sm_count * 20;
-        q.batch = (p.G + wave - 1) / wave;
-        if (q.batch > GT_BATCH) q.batch = GT_BATCH;
-        if (q.batch < 1) q.batch = 1;
-    }
-    const int units = (p.G + q.batch - 1) / q.batch;
-    int grid = (units + GT_WARPS - 1) / GT_WARPS;
+    int grid = (p.G + GT_WARPS - 1) / GT_WARPS; /* one gene per warp */
+    (void)sm_count;
     const int eps = sort_eps(p.n);
-    const size_t smem = (size_t)GT_WARPS * (32 * eps + 2 + 2 * 3 * GT_BATCH) * sizeof(double);
+    const size_t smem = (size_t)GT_WARPS * (32 * eps + 2) * sizeof(double);
     switch (eps) {
-#define EPX_CASE(E) case E: k_gene_tests_w<E><<<grid, GT_WARPS * 32, smem, st>>>(q); break;
+#define EPX_CASE(E) case E: k_gene_tests_w<E><<<grid, GT_WARPS * 32, smem, st>>>(p); break;
         EPX_FOR_SORT_VARIANTS(EPX_CASE)
 #undef EPX_CASE
     default: return cudaErrorInvalidValue;
