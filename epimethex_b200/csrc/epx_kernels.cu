@@ -577,6 +577,104 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
     }
 }
 
+/* k_probe_rank_w2: rows of 513..1024 values (EPIC-array cohorts: n = 1,000). One warp per row: the row is staged in
+ * shared memory, its two halves are ordered by the 512-value register sort (a 1,024-value network costs 3.4x as
+ * many instructions as a 512-value one and needs 128 registers), and one merge-path pass — lane L produces outputs
+ * [32L, 32L + 32) after a binary search for its split point; the left half wins ties, which keeps equal values in
+ * ascending sample index — writes the order row with its tie marks. Same output as k_probe_rank_w<32>. */
+constexpr int RANK2_WARPS = 6;
+constexpr int RANK2_WARP_SMEM = 1024 * 8 + 1024 * 2 + 1024 * 2; /* values | run indices | merged (first the sort's scratch) */
+
+__global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
+    double *vals = (double *)(smem + (size_t)warp * RANK2_WARP_SMEM);
+    unsigned short *runs = (unsigned short *)(vals + 1024);
+    unsigned short *merged = runs + 1024;
+    unsigned short *scratch = merged; /* WarpSort's 512 entries of scratch are dead before the merge starts */
+    const int nw = (int)gridDim.x * RANK2_WARPS;
+    const int la = 512, lb = n - 512;
+    int64_t slot = (int64_t)blockIdx.x * RANK2_WARPS + warp;
+    while (slot < p.U) {
+        const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+            const int s = lane + 32 * e;
+            if (s < n) vals[s] = __ldg(row + s);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+            const int base = 512 * c, nc = c == 0 ? la : lb;
+            unsigned khi[16], klo[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) key_halves(vals[base + min(lane + 32 * e, nc - 1)], khi[e], klo[e]);
+            unsigned short out[16];
+            WarpSort<16>::template order<false>(khi, klo, nc, lane, scratch, [&](int i) { return vals[base + i]; },
+                                                (unsigned short)0xffffu, p.one, out);
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k = lane * 16 + r;
+                if (k < nc) runs[base + k] = (unsigned short)(base + (out[r] & 0x7fff));
+            }
+        }
+        __syncwarp();
+        /* merge path: of the first d outputs, i come from A (A wins ties) */
+        const unsigned short *A = runs, *B = runs + 512;
+        const int d = min(lane * 32, n), d_end = min(d + 32, n);
+        int lo = max(0, d - lb), hi = min(d, la);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (!(vals[B[d - 1 - mid]] < vals[A[mid]])) lo = mid + 1; else hi = mid;
+        }
+        int pa = lo, pb = d - lo;
+        unsigned short xa = A[min(pa, la - 1)], xb = B[min(pb, lb - 1)];
+        double va = vals[xa], vb = vals[xb];
+        for (int k = d; k < d_end; k++) {
+            const bool take_a = pb >= lb || (pa < la && !(vb < va));
+            merged[k] = take_a ? xa : xb;
+            pa += take_a ? 1 : 0;
+            pb += take_a ? 0 : 1;
+            const unsigned short nx = take_a ? A[min(pa, la - 1)] : B[min(pb, lb - 1)];
+            const double nv = vals[nx];
+            xa = take_a ? nx : xa; va = take_a ? nv : va;
+            xb = take_a ? xb : nx; vb = take_a ? vb : nv;
+        }
+        __syncwarp();
+        /* tie marks and the padded row (pad positions carry index n), 16 bytes per store */
+        uint16_t *o = p.ord + slot * p.ldo;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int k0 = (lane + 32 * c) * 8;
+            if (k0 < p.ldo) {
+                unsigned w[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int k = k0 + i;
+                    unsigned v = (unsigned)n;
+                    if (k < n) {
+                        v = merged[k];
+                        if (k + 1 < n && vals[v] == vals[merged[k + 1]]) v |= 0x8000u;
+                    }
+                    w[i] = v;
+                }
+                uint4 q;
+                q.x = w[0] | (w[1] << 16); q.y = w[2] | (w[3] << 16); q.z = w[4] | (w[5] << 16); q.w = w[6] | (w[7] << 16);
+                *reinterpret_cast<uint4 *>(o + k0) = q;
+            }
+        }
+        int nslot = 0;
+        if (lane == 0) nslot = nw + atomicAdd(p.queue, 1);
+        slot = __shfl_sync(FULL, nslot, 0);
+    }
+    if (lane == 0) { /* the last warp to leave re-arms the queue for the next launch */
+        __threadfence();
+        if (atomicAdd(p.queue + 1, 1) == nw - 1) { p.queue[0] = 0; p.queue[1] = 0; }
+    }
+}
+
 /* ============================================================ k_pair_stats (warp per pair, n <= 1024) */
 
 constexpr int PAIR_WARPS = 8;
@@ -1185,6 +1283,7 @@ cudaError_t kernels_init()
     EPX_FOR_PAIR2_VARIANTS(EPX_PAIR2_ATTR)
 #undef EPX_PAIR2_ATTR
     if ((e = allow_max_dynamic_smem(k_group_blocksort)) != cudaSuccess) return e;
+    if ((e = allow_max_dynamic_smem(k_probe_rank_w2)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1280,6 +1379,19 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
             if (grid > p.U) grid = p.U;
             k_probe_rank<<<(unsigned)grid, CTASORT_THREADS, smem, st>>>(p);
         }
+        return cudaGetLastError();
+    }
+    if (p.n > 512 && (p.ldo & 7) == 0 && ((uintptr_t)p.ord & 15) == 0) { /* two 512-value halves + one merge per warp */
+        static int per_sm2 = 0;
+        const size_t smem = (size_t)RANK2_WARPS * RANK2_WARP_SMEM;
+        if (per_sm2 == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w2, RANK2_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+            per_sm2 = nb;
+        }
+        int64_t grid = (p.U + RANK2_WARPS - 1) / RANK2_WARPS;
+        if (grid > (int64_t)sm_count * per_sm2) grid = (int64_t)sm_count * per_sm2;
+        k_probe_rank_w2<<<(unsigned)grid, RANK2_WARPS * 32, smem, st>>>(p);
         return cudaGetLastError();
     }
     switch (sort_eps(p.n)) {

@@ -244,3 +244,28 @@ def test_values_closer_than_the_sort_keys_coarse_resolution(sess, n):
     for te, tm in ((True, False), (False, True)):
         got = run_gpu(sess, x, y, idx, te=te, tm=tm)
         assert_parity(got, run_oracle(x, y, idx, te=te, tm=tm), f"near-ties n={n} te={te} tm={tm}")
+
+
+@pytest.mark.parametrize("tm", [False, True])
+def test_repeated_and_chunked_runs_are_identical(sess, tm):
+    """The rank and pair kernels draw their rows / work items from ticket counters that the last warp re-arms:
+    a second run on the same session, and a run cut into chunks of work items, must give the same tables."""
+    x, y, idx = _synth(400, 473, 6000, missing_every=11)
+    first = run_gpu(sess, x, y, idx, tm=tm)
+    assert_parity(first, run_oracle(x, y, idx, tm=tm), f"first run tm={tm}")
+    opts = _native.make_options(True, True, tm)
+    for n_chunks in (1, 3, 7):
+        sess.run_prepare(opts)
+        for c in range(n_chunks):
+            sess.run_pairs(c, n_chunks)
+        again = sess.fetch()
+        for name in ("pair", "pair_stat", "gene"):
+            assert np.array_equal(getattr(first, name), getattr(again, name), equal_nan=True), (name, n_chunks)
+        for name in ("ks_dnum", "pair_na", "gene_na", "perm"):
+            assert np.array_equal(getattr(first, name), getattr(again, name)), (name, n_chunks)
+    covered = 0
+    for c in range(7):
+        b, cnt = sess.pairs_chunk(c, 7)
+        assert b == covered
+        covered += cnt
+    assert covered == idx.probe_idx.size
