@@ -13,7 +13,8 @@ reference, C + OpenMP, all host cores) on a bounded gene sample of the same work
 
 Under torchrun (N > 1) every rank runs its own cohort of the same shape (weak scaling: genes/probes shard
 with no data-path collective) and the per-rank result tables are gathered to rank 0 over NCCL inside the
-timed region, as the path's only exchange step.
+timed region, as the path's only exchange step.  `--workload pancan_full` (BASELINE configs[4]) is the one
+strong-scaling workload: one 9,000-sample cohort, genes cut into N ranges, probe-sliced methylation.
 """
 from __future__ import annotations
 
@@ -47,6 +48,12 @@ WORKLOADS = {
     # 8-GPU job); only the rows the slice references are generated
     "pancan_slice": dict(shape="pancan", genes=(0, 2000), te=True, tm=False,
                          desc="synthetic pan-cancer shape, 9,000 samples, gene range 1-2000 of 20,531, 485,577 probes"),
+    # BASELINE.json configs[4] in full: all 20,531 genes at 9,000 samples. STRONG scaling: the genes are cut into N
+    # contiguous ranges with equal pair counts (distributed.partition_genes) and rank r analyses range r as one
+    # (from, to) call of the reference would -- the unit the reference itself is run in (README cap: 1000 genes per
+    # call). Methylation is probe-sliced: a rank generates and uploads only the rows its genes reference.
+    "pancan_full": dict(shape="pancan", genes=(0, 20531), te=True, tm=False, shard=True,
+                        desc="synthetic pan-cancer shape: 20,531 genes x 9,000 samples x 485,577 probes, genes sharded over the GPUs, probe-sliced methylation"),
     "tiny": dict(shape=None, genes=(0, 300), te=True, tm=False, n_samples=99, n_probes=6000, n_genes=300,
                  desc="tiny self-test workload"),
 }
@@ -96,11 +103,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(name: str, rank: int):
-    """Synthetic inputs for one rank. Rank r draws its own cohort (data seeds + r) over the same annotation."""
+def make_workload(name: str, rank: int, world: int = 1):
+    """Synthetic inputs for one rank. Rank r draws its own cohort (data seeds + r) over the same annotation; a
+    workload with shard=True is ONE cohort whose genes are cut into `world` ranges (strong scaling)."""
     from epimethex_b200 import _native, synth
 
     w = WORKLOADS[name]
+    if w.get("shard"):
+        return make_sharded_workload(w, rank, world)
     dims = dict(synth.SHAPES[w["shape"]]) if w["shape"] else dict(n_genes=w["n_genes"], n_samples=w["n_samples"], n_probes=w["n_probes"])
     n, P = dims["n_samples"], dims["n_probes"]
     g0, g1 = w["genes"]
@@ -122,11 +132,50 @@ def make_workload(name: str, rank: int):
     def work(chunk):
         meth[chunk] = synth.methylation_rows(chunk, n, ann, seed=synth.SEED_METH + rank)
 
-    chunks = [used[i:i + 4096] for i in range(0, used.size, 4096)]
+    step = max(16, 1_000_000 // n)      # ~8 MB of temporaries per numpy pass: stays in the host caches
+    chunks = [used[i:i + step] for i in range(0, used.size, step)]
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(work, chunks))
     return dict(w=w, n=n, P=P, G=g1 - g0, ann=ann, idx=idx, expr=np.ascontiguousarray(expr), meth=meth,
-                gen_s=time.time() - t0, n_unique=int(used.size), pinned=pinned)
+                gen_s=time.time() - t0, n_unique=int(used.size), pinned=pinned, rows=P)
+
+
+def make_sharded_workload(w, rank: int, world: int):
+    """one cohort, genes cut into `world` ranges of equal pair counts; this rank's range with a probe-sliced
+    methylation copy (only the rows its pairs name, re-indexed)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from dataclasses import replace
+
+    from epimethex_b200 import _native, distributed, synth
+
+    dims = dict(synth.SHAPES[w["shape"]])
+    n, P = dims["n_samples"], dims["n_probes"]
+    t0 = time.time()
+    ann = synth.annotation(P, dims["n_genes"])
+    g_lo, g_hi = w["genes"]
+    whole = synth.probe_index(ann, g_lo, g_hi)
+    a, b = distributed.partition_genes(whole.row_ptr, world)[rank]
+    g0, g1 = g_lo + a, g_lo + b
+    idx = synth.probe_index(ann, g0, g1)
+    rows, local = distributed.slice_probes(idx.probe_idx)
+    idx = replace(idx, probe_idx=local)
+    expr = synth.expression(g1 - g0, n, g0=g0, seed=synth.SEED_EXPR)
+    pinned = True
+    try:
+        meth = _native.pinned_empty((max(1, rows.size), n))
+    except Exception:
+        meth, pinned = np.empty((max(1, rows.size), n)), False
+    threads = max(1, min(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    step = max(16, 1_000_000 // n)
+
+    def work(i):
+        meth[i:i + step] = synth.methylation_rows(rows[i:i + step], n, ann, seed=synth.SEED_METH)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(0, rows.size, step)))
+    return dict(w=w, n=n, P=P, G=g1 - g0, ann=ann, idx=idx, expr=np.ascontiguousarray(expr), meth=meth,
+                gen_s=time.time() - t0, n_unique=int(rows.size), pinned=pinned, rows=int(meth.shape[0]),
+                gene_range=(g0, g1))
 
 
 _CPU_RATE = {}
@@ -194,7 +243,7 @@ def main():
         # so that warmup + steps finish in about --ref-budget seconds.
         if rank != 0:
             return 0
-        wl = make_workload(args.workload, 0)
+        wl = make_workload(args.workload, 0, args.gpus)
         total = args.warmup + args.steps
         per_step = max(0.05, args.ref_budget / max(1, total))
         runs = [cpu_baseline(wl, per_step, cores) for _ in range(total)][args.warmup:]
@@ -218,8 +267,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = make_workload(args.workload, rank)
+    wl = make_workload(args.workload, rank, world)
     idx, n, G, P = wl["idx"], wl["n"], wl["G"], wl["P"]
+    strong = bool(wl["w"].get("shard"))
     Np = idx.n_pairs
     opts = _native.make_options(True, wl["w"]["te"], wl["w"]["tm"])
     sess = _native.Session(local_rank)
@@ -255,17 +305,38 @@ def main():
             pair_t = torch.as_tensor(_DevArray(ptr, (Np, 11)), device="cuda")   # the library's table, no copy
             gptr, _ = sess.result_device_ptr(4)
             gene_t = torch.as_tensor(_DevArray(gptr, (G, 15)), device="cuda")
-            pdst = [torch.empty_like(pair_t) for _ in range(world)] if rank == 0 else None
-            gdst = [torch.empty_like(gene_t) for _ in range(world)] if rank == 0 else None
+            if strong:
+                # ragged shards: every rank's table sizes, once; rank 0 then receives exact-size tables point to point
+                mine = torch.tensor([Np, G], device="cuda", dtype=torch.int64)
+                sizes = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(sizes, mine)
+                sizes = [(int(c[0]), int(c[1])) for c in sizes]
+                pdst = [torch.empty((a, 11), dtype=torch.float64, device="cuda") for a, _ in sizes] if rank == 0 else None
+                gdst = [torch.empty((b, 15), dtype=torch.float64, device="cuda") for _, b in sizes] if rank == 0 else None
+            else:
+                pdst = [torch.empty_like(pair_t) for _ in range(world)] if rank == 0 else None
+                gdst = [torch.empty_like(gene_t) for _ in range(world)] if rank == 0 else None
             gather_plan = (pair_t, pdst, gene_t, gdst, torch.cuda.Event())
         pair_t, pdst, gene_t, gdst, ev_gene = gather_plan
         tstream.wait_stream(gstream)              # previous pair-table gather done before the table is overwritten
         sess.run_pairs(0, 1, stream)
         gstream.wait_stream(tstream)
         with torch.cuda.stream(gstream):
-            dist.gather(gene_t, gdst, dst=0)
-            ev_gene.record(gstream)
-            dist.gather(pair_t, pdst, dst=0)
+            if strong:
+                if rank == 0:
+                    ops = [dist.P2POp(dist.irecv, gdst[r], r) for r in range(1, world)]
+                    ops += [dist.P2POp(dist.irecv, pdst[r], r) for r in range(1, world)]
+                    gdst[0].copy_(gene_t)
+                    pdst[0].copy_(pair_t)
+                else:
+                    ops = [dist.P2POp(dist.isend, gene_t, 0), dist.P2POp(dist.isend, pair_t, 0)]
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                ev_gene.record(gstream)
+            else:
+                dist.gather(gene_t, gdst, dst=0)
+                ev_gene.record(gstream)
+                dist.gather(pair_t, pdst, dst=0)
 
     def finish():
         if world > 1:
@@ -351,7 +422,7 @@ def main():
     # ---- e2e through the blocking C-ABI call with host buffers ----
     # methylation + expression go over PCIe every step; the index (1.9 MB) is compared on the host and re-sent only if
     # it changed, so it is not counted
-    h2d = P * n * 8 + G * n * 8
+    h2d = wl["rows"] * n * 8 + G * n * 8
     d2h = Np * (11 * 8 + 2) + G * (15 * 8 + 2)
     e2e_ms = []
     e2e_upload_ms = []
@@ -390,10 +461,11 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload, {}).get(dom[:-3])
         line = {
             "metric": "gene-probe pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["w"]["desc"], "name": args.workload, "pairs_per_gpu": Np, "genes": G, "samples": n,
-                       "probes": P, "unique_probes": wl["n_unique"], "l2": "inputs (%.2f GB methylation) exceed the 126 MB L2; no flush" % (P * n * 8 / 1e9),
+                       "probes": P, "unique_probes": wl["n_unique"], "methylation_rows_on_gpu": wl["rows"], "total_pairs": int(total_pairs),
+                       "l2": "inputs (%.2f GB methylation on this GPU) exceed the 126 MB L2; no flush" % (wl["rows"] * n * 8 / 1e9),
                        "parallelism": f"genes sharded, {world} rank(s), NCCL gather of result tables" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": dom[:-3], "achieved": kernels[dom[:-3]]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom[:-3]]["frac"], "traffic": traffic, "peak_source": peak_src,

@@ -27,7 +27,7 @@ EXPORTS = [
     "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
     "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
-    "epx_multi_set_methylation_rows", "epx_multi_analyze", "epx_session_run_groups", "epx_session_fetch_groups",
+    "epx_multi_set_methylation_rows", "epx_multi_set_methylation_sliced", "epx_multi_analyze", "epx_session_run_groups", "epx_session_fetch_groups",
     "epx_write_csv", "epx_format_real15",
 ]
 
@@ -112,6 +112,7 @@ def lib():
     L.epx_multi_destroy.argtypes = [vp]
     L.epx_multi_destroy.restype = None
     L.epx_multi_set_methylation_rows.argtypes = [vp, vp, i64, i64, i64] + e
+    L.epx_multi_set_methylation_sliced.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64] + e
     L.epx_multi_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
     L.epx_session_run_groups.argtypes = [vp, vp, vp, i64, vp] + e
     L.epx_session_fetch_groups.argtypes = [vp, C.POINTER(_GroupResult), vp] + e
@@ -422,6 +423,16 @@ class MultiSession:
         b = _errbuf()
         _check(lib().epx_multi_set_methylation_rows(self._h, rows.ctypes.data, rows.shape[0], rows.shape[1],
                                                     rows.shape[1], b, len(b)), b)
+
+    def set_methylation_sliced(self, rows: np.ndarray, row_ptr, probe_idx):
+        """probe-sliced copies: each device gets only the rows its share of the genes references"""
+        rows = np.ascontiguousarray(rows, np.float64)
+        row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        probe_idx = np.ascontiguousarray(probe_idx, np.int32)
+        b = _errbuf()
+        _check(lib().epx_multi_set_methylation_sliced(self._h, rows.ctypes.data, rows.shape[0], rows.shape[1],
+                                                      rows.shape[1], row_ptr.ctypes.data, probe_idx.ctypes.data,
+                                                      row_ptr.size - 1, b, len(b)), b)
 
     def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None) -> Result:
         expr = np.ascontiguousarray(expr, np.float64)

@@ -116,7 +116,26 @@ struct epx_session {
 
 struct epx_multi {
     std::vector<epx_session *> sess;
+    /* probe-sliced mode (epx_multi_set_methylation_sliced): device i holds only the methylation rows
+       rows_of[i][0..] (ascending), as its rows 0..; empty vectors = every device holds the whole matrix */
+    std::vector<std::vector<int32_t>> rows_of;
+    bool sliced = false;
 };
+
+/* contiguous gene ranges with (nearly) equal pair counts: cut[r] .. cut[r+1] is device r's range */
+static std::vector<int64_t> gene_cuts(const int64_t *row_ptr, int64_t n_genes, int W)
+{
+    std::vector<int64_t> cut((size_t)W + 1, 0);
+    cut[(size_t)W] = n_genes;
+    const int64_t Np = row_ptr[n_genes];
+    for (int r = 1; r < W; r++) {
+        const int64_t target = Np * r / W;
+        int64_t g = cut[(size_t)r - 1];
+        while (g < n_genes && row_ptr[g] < target) g++;
+        cut[(size_t)r] = g;
+    }
+    return cut;
+}
 
 /* run fn(i) for every device on its own thread; first failure wins */
 template <typename F> static int for_each_device(epx_multi *m, F fn, char *err, size_t errlen)
@@ -827,9 +846,48 @@ int epx_multi_set_methylation_rows(epx_multi *m, const double *rows, int64_t n_p
                                    char *err, size_t errlen)
 {
     if (!m) return fail(err, errlen, EPX_EINVAL, "NULL handle");
+    m->sliced = false;
+    m->rows_of.clear();
     return for_each_device(m, [&](int i, char *e, size_t el) {
         return epx_session_set_methylation_rows(m->sess[(size_t)i], rows, n_probes, n_samples, ld, e, el);
     }, err, errlen);
+}
+
+int epx_multi_set_methylation_sliced(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples, int64_t ld,
+                                     const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
+                                     char *err, size_t errlen)
+{
+    if (!m) return fail(err, errlen, EPX_EINVAL, "NULL handle");
+    if (!rows || !row_ptr || n_genes < 1 || n_probes < 1 || n_samples < 1 || ld < n_samples)
+        return fail(err, errlen, EPX_EINVAL, "bad arguments");
+    const int64_t Np = row_ptr[n_genes];
+    if (Np > 0 && !probe_idx) return fail(err, errlen, EPX_EINVAL, "probe_idx is NULL");
+    for (int64_t k = 0; k < Np; k++)
+        if (probe_idx[k] >= n_probes) return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d is outside the %lld methylation rows",
+                                                  (long long)k, probe_idx[k], (long long)n_probes);
+    const int W = (int)m->sess.size();
+    const std::vector<int64_t> cut = gene_cuts(row_ptr, n_genes, W);
+    m->sliced = false;
+    m->rows_of.assign((size_t)W, std::vector<int32_t>());
+    int rc = for_each_device(m, [&](int i, char *e, size_t el) -> int {
+        const int64_t lo = row_ptr[cut[(size_t)i]], hi = row_ptr[cut[(size_t)i + 1]];
+        std::vector<int32_t> &u = m->rows_of[(size_t)i];
+        for (int64_t k = lo; k < hi; k++)
+            if (probe_idx[k] >= 0) u.push_back(probe_idx[k]);
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        const size_t U = u.size() ? u.size() : 1;        /* a device without pairs still gets one (zero) row */
+        double *compact = (double *)calloc(U * (size_t)n_samples, sizeof(double));
+        if (!compact) return fail(e, el, EPX_ENOMEM, "out of host memory for %zu sliced rows", U);
+        for (size_t j = 0; j < u.size(); j++)
+            memcpy(compact + j * (size_t)n_samples, rows + (size_t)u[j] * (size_t)ld, (size_t)n_samples * sizeof(double));
+        int r = epx_session_set_methylation_rows(m->sess[(size_t)i], compact, (int64_t)U, n_samples, n_samples, e, el);
+        free(compact);
+        return r;
+    }, err, errlen);
+    if (rc) { m->rows_of.clear(); return rc; }
+    m->sliced = true;
+    return EPX_OK;
 }
 
 int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t n_samples, const int64_t *row_ptr,
@@ -837,16 +895,7 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
 {
     if (!m || !expr || !row_ptr || !out || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad arguments");
     const int W = (int)m->sess.size();
-    const int64_t Np = row_ptr[n_genes];
-    /* contiguous gene ranges with (nearly) equal pair counts */
-    std::vector<int64_t> cut((size_t)W + 1, 0);
-    cut[(size_t)W] = n_genes;
-    for (int r = 1; r < W; r++) {
-        const int64_t target = Np * r / W;
-        int64_t g = cut[(size_t)r - 1];
-        while (g < n_genes && row_ptr[g] < target) g++;
-        cut[(size_t)r] = g;
-    }
+    const std::vector<int64_t> cut = gene_cuts(row_ptr, n_genes, W);
     return for_each_device(m, [&](int i, char *e, size_t el) -> int {
         epx_session *s = m->sess[(size_t)i];
         const int64_t g0 = cut[(size_t)i], g1 = cut[(size_t)i + 1];
@@ -864,7 +913,24 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
         if (out->pair_stat) r.pair_stat = out->pair_stat + lo * 3;
         if (out->pair_ks_dnum) r.pair_ks_dnum = out->pair_ks_dnum + lo * 3;
         if (i == 0) { r.gene = out->gene; r.gene_na = out->gene_na; r.gene_ks_dnum = out->gene_ks_dnum; r.perm = out->perm; }
-        int rc = epx_analyze(s, expr, n_genes, n_samples, rp.data(), probe_idx ? probe_idx + lo : nullptr, opt, &r, e, el);
+        const int32_t *pi = probe_idx ? probe_idx + lo : nullptr;
+        std::vector<int32_t> local;
+        if (m->sliced && pi) {
+            /* global methylation row -> row of this device's slice */
+            const std::vector<int32_t> &u = m->rows_of[(size_t)i];
+            local.resize((size_t)(hi - lo));
+            for (int64_t k = 0; k < hi - lo; k++) {
+                if (pi[k] < 0) { local[(size_t)k] = -1; continue; }
+                auto it = std::lower_bound(u.begin(), u.end(), pi[k]);
+                if (it == u.end() || *it != pi[k])
+                    return fail(e, el, EPX_ESTATE, "pair %lld needs methylation row %d, which is not in this device's slice "
+                                "(the index differs from the one passed to epx_multi_set_methylation_sliced)",
+                                (long long)(lo + k), pi[k]);
+                local[(size_t)k] = (int32_t)(it - u.begin());
+            }
+            pi = local.data();
+        }
+        int rc = epx_analyze(s, expr, n_genes, n_samples, rp.data(), pi, opt, &r, e, el);
         if (rc == EPX_OK && i == 0) { memcpy(out->counts, r.counts, sizeof r.counts); out->ref_gene = r.ref_gene; }
         return rc;
     }, err, errlen);

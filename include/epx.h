@@ -175,7 +175,8 @@ int  epx_session_result_device_ptr(epx_session *s, int which, void **ptr, int64_
 /* ---- several GPUs from ONE process (R is a single process; replaces the PSOCK cluster of
  * R/EpimethexAnalysis.R:333-352 and its `.combine = cbind`) ----
  * One session per device, each driven by its own host thread. Genes are cut into contiguous ranges with equal
- * numbers of pairs; every device holds a replica of the methylation matrix and the whole expression matrix (the
+ * numbers of pairs; every device holds a replica of the methylation matrix (or, with epx_multi_set_methylation_sliced,
+ * only the rows its genes reference) and the whole expression matrix (the
  * gene-level kernels run everywhere, so the bin.var reference gene needs no exchange) and computes its own pairs,
  * which are copied straight into the caller's result tables (the destination is host memory, so no device-to-device
  * gather is needed in this mode; the one-process-per-GPU mode of bench.py gathers over NCCL instead). */
@@ -184,6 +185,14 @@ int  epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *
 void epx_multi_destroy(epx_multi *m);
 int  epx_multi_set_methylation_rows(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples,
                                     int64_t ld, char *err, size_t errlen);
+/* Probe-sliced copies instead of replicas (pan-cancer: 35 GB of methylation, of which a device needs only the rows
+ * its own genes reference): cuts the genes of the given index exactly as epx_multi_analyze will, and uploads to each
+ * device only the distinct rows of `rows` that its pairs name, so the total host-to-device traffic is about one
+ * matrix instead of one per device. epx_multi_analyze must then be called with the same index (a pair naming a row
+ * that is not in its device's slice is EPX_ESTATE); it translates probe_idx to slice rows itself. */
+int  epx_multi_set_methylation_sliced(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples,
+                                      int64_t ld, const int64_t *row_ptr, const int32_t *probe_idx,
+                                      int64_t n_genes, char *err, size_t errlen);
 int  epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t n_samples,
                        const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
                        epx_result *out, char *err, size_t errlen);

@@ -28,6 +28,29 @@ def test_partition_is_contiguous_balanced_and_complete():
     assert np.array_equal(pi, idx.probe_idx[first:first + count])
 
 
+def test_probe_slices_cover_each_rank_and_total_one_matrix():
+    """probe-sliced copies: a rank's slice holds exactly the rows its pairs name; the oracle on the slice
+    with the translated index equals the oracle on the whole matrix"""
+    ann = synth.annotation(3000, 200)
+    has = np.ones(3000, bool); has[::41] = False
+    idx = synth.probe_index(ann, 0, 200, probe_has_data=has)
+    x = synth.expression(200, 30)
+    y = synth.methylation(3000, 30, ann, threads=1)
+    whole = oracle.analyze(x, y, idx.row_ptr, idx.probe_idx)
+    total_rows = 0
+    for g0, g1 in distributed.partition_genes(idx.row_ptr, 3):
+        rp, pi, first, count = distributed.shard_index(idx, g0, g1)
+        rows, local = distributed.slice_probes(pi)
+        assert np.all(np.diff(rows) > 0) and np.array_equal(local < 0, pi < 0)
+        assert np.array_equal(rows[local[local >= 0]], pi[pi >= 0])
+        total_rows += rows.size
+        part = oracle.analyze(x, np.ascontiguousarray(y[rows]), rp, local)
+        assert np.array_equal(part.pair, whole.pair[first:first + count], equal_nan=True)
+        assert np.array_equal(part.ks_dnum, whole.ks_dnum[first:first + count])
+    used = np.unique(idx.probe_idx[idx.probe_idx >= 0]).size
+    assert used <= total_rows <= used + 3 * int(np.diff(idx.row_ptr).max())    # ~ one matrix in total, not three
+
+
 def _oracle_compute(sess, expr, row_ptr, probe_idx, opts):
     return oracle.analyze(expr, sess, row_ptr, probe_idx, test_meth_t=opts["tm"])
 

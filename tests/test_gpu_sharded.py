@@ -74,3 +74,34 @@ def test_one_process_multi_gpu_equals_one_gpu():
             assert np.array_equal(many.pair, one.pair, equal_nan=True) and np.array_equal(many.pair_na, one.pair_na)
             assert np.array_equal(many.ks_dnum, one.ks_dnum) and np.array_equal(many.pair_stat, one.pair_stat, equal_nan=True)
             assert np.array_equal(many.gene, one.gene, equal_nan=True) and np.array_equal(many.perm, one.perm)
+
+
+def test_probe_sliced_copies_equal_replicas():
+    """epx_multi_set_methylation_sliced: each device holds only the rows its genes reference (pan-cancer).
+    On a one-GPU box the two sessions share device 0 -- the slicing and the row translation are the same code."""
+    nd = min(_native.device_count(), 4)
+    devices = list(range(nd)) if nd >= 2 else [0, 0, 0]
+    ann = synth.annotation(5000, 300)
+    x = synth.expression(300, 99); y = synth.methylation(5000, 99, ann, threads=2)
+    has = np.ones(5000, bool); has[::37] = False           # some annotated probes without data (-1 in the index)
+    idx = synth.probe_index(ann, 0, 300, probe_has_data=has)
+    assert (idx.probe_idx < 0).any()
+    with _native.Session(0) as sess:
+        sess.set_methylation(y)
+        one = sess.analyze(x, idx.row_ptr, idx.probe_idx)
+    with _native.MultiSession(devices) as ms:
+        ms.set_methylation_sliced(y, idx.row_ptr, idx.probe_idx)
+        for _ in range(2):
+            many = ms.analyze(x, idx.row_ptr, idx.probe_idx)
+            assert many.counts == one.counts and many.ref_gene == one.ref_gene
+            assert np.array_equal(many.pair, one.pair, equal_nan=True) and np.array_equal(many.pair_na, one.pair_na)
+            assert np.array_equal(many.ks_dnum, one.ks_dnum) and np.array_equal(many.pair_stat, one.pair_stat, equal_nan=True)
+            assert np.array_equal(many.gene, one.gene, equal_nan=True) and np.array_equal(many.perm, one.perm)
+        # an index that needs rows outside the slices is refused, not silently mis-read
+        other = synth.probe_index(ann, 0, 300)
+        with pytest.raises(_native.EpxError, match="EPX_ESTATE"):
+            ms.analyze(x, other.row_ptr, other.probe_idx)
+        # back to replicas: any index works again
+        ms.set_methylation(y)
+        full = ms.analyze(x, other.row_ptr, other.probe_idx)
+        assert full.pair.shape[0] == other.n_pairs
