@@ -102,6 +102,7 @@ struct epx_session {
     std::vector<int64_t> h_row_ptr;
     DevBuf<double> upload_stage;                    /* 2 x 64 MB: flat H2D chunks before re-spacing */
     cudaEvent_t ev_up[3] = { nullptr, nullptr, nullptr };
+    bool join_side = false;                         /* run_pairs must join the side stream (gene tests) */
     int64_t index_P = -1;                           /* methylation row count the index was validated against */
     DevBuf<GroupDesc> g_desc;
     DevBuf<BlockDesc> g_blocks;
@@ -558,7 +559,10 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
     EPX_CUDA(cudaEventRecord(s->ev[6], st));
     if (s->U > 0) { EPX_CUDA(launch_probe_rank(rp, s->sm_count, st)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[3], st));
-    if (overlap) EPX_CUDA(cudaStreamWaitEvent(st, s->ev[2], 0));
+    /* the pair kernel needs the gene order/labels/centred expression (gene sort) but not the gene-level tests: it
+     * waits for ev[1] only, and the main stream joins the rest of the side stream after the pair kernel (run_pairs) */
+    if (overlap) EPX_CUDA(cudaStreamWaitEvent(st, s->ev[1], 0));
+    s->join_side = overlap;
     s->pp = pp;
     s->prepared = true;
     s->ran = false;
@@ -603,6 +607,7 @@ int epx_session_run_pairs(epx_session *s, int chunk, int n_chunks, void *stream,
         s->launches++;
     }
     if (chunk == n_chunks - 1) {
+        if (s->join_side) EPX_CUDA(cudaStreamWaitEvent(st, s->ev[2], 0)); /* gene tests (side stream) are part of the run */
         EPX_CUDA(cudaEventRecord(s->ev[4], st));
         s->ran = true;
     }
