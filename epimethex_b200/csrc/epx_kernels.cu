@@ -1152,7 +1152,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
                         if (s_row[perm_g[offA[c] + i]] - s_row[perm_g[offB[c] + i]] != dd) differs = 1;
                 guard[c] = __syncthreads_or(differs) ? 1 : 0;
             }
-        }
+        } else __syncthreads();
+        /* single stage: nobody reads the row or the order any more (the barrier above), so the next pair's copy
+         * starts now and runs under the scalar tail below */
+        if (STAGES == 1 && tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, 0);
 
         if (tid == 0) {
             double out[PAIR_COLS], stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
@@ -1191,10 +1194,6 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             for (int c = 0; c < PAIR_COLS; c++) p.pair[(int64_t)j * PAIR_COLS + c] = out[c];
             for (int c = 0; c < 3; c++) { p.pair_stat[(int64_t)j * 3 + c] = stat[c]; p.pair_dnum[(int64_t)j * 3 + c] = dnum[c]; }
             p.pair_na[j] = (uint16_t)na;
-        }
-        if (STAGES == 1) {
-            __syncthreads();
-            if (tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, 0);
         }
     }
 }
