@@ -22,7 +22,7 @@ namespace epx {
 
 /* ============================================================ k_gene_sort */
 
-__global__ void __launch_bounds__(CTASORT_THREADS) k_gene_sort(GeneParams p)
+__global__ void __launch_bounds__(CTASORT_THREADS, 2) k_gene_sort(GeneParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int g = blockIdx.x, n = p.n;
