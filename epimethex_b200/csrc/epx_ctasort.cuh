@@ -1,5 +1,5 @@
 /*
- * epx_ctasort.cuh — one CTA (12 warps) orders one long row (1024 < n <= 16384 values, e.g. the 9,000-sample
+ * epx_ctasort.cuh — one CTA (8 warps) orders one long row (1024 < n <= 16384 values, e.g. the 9,000-sample
  * pan-cancer shape) held in shared memory: every warp sorts 512-value chunks with the register bitonic sort of
  * epx_warpsort.cuh, then log2(chunks) merge passes (merge path: each thread produces a contiguous slice of the
  * output after a binary search for its split point) combine them. Exact and stable: equal values keep ascending
@@ -10,7 +10,7 @@
 
 namespace epx {
 
-constexpr int CTASORT_THREADS = 384;                 /* 12 warps: 2 CTAs of 80 registers per thread fill the register file */
+constexpr int CTASORT_THREADS = 256;
 constexpr int CTASORT_EPS = 16;                    /* values per lane in the register sort of a chunk */
 constexpr int CTASORT_CHUNK = 32 * CTASORT_EPS;    /* 512: the 1,024-value network costs 3.4x the 512-value one, a merge pass far less */
 
