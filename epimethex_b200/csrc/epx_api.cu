@@ -121,6 +121,7 @@ struct epx_multi {
        rows_of[i][0..] (ascending), as its rows 0..; empty vectors = every device holds the whole matrix */
     std::vector<std::vector<int32_t>> rows_of;
     bool sliced = false;
+    std::vector<int64_t> pair_lo;   /* after epx_multi_analyze: device i owns pairs [pair_lo[i], pair_lo[i+1]) */
 };
 
 /* contiguous gene ranges with (nearly) equal pair counts: cut[r] .. cut[r+1] is device r's range */
@@ -858,6 +859,17 @@ int epx_multi_set_methylation_rows(epx_multi *m, const double *rows, int64_t n_p
     }, err, errlen);
 }
 
+int epx_multi_set_methylation_cols(epx_multi *m, const double *const *cols, int64_t n_samples, int64_t n_probes,
+                                   char *err, size_t errlen)
+{
+    if (!m) return fail(err, errlen, EPX_EINVAL, "NULL handle");
+    m->sliced = false;
+    m->rows_of.clear();
+    return for_each_device(m, [&](int i, char *e, size_t el) {
+        return epx_session_set_methylation_cols(m->sess[(size_t)i], cols, n_samples, n_probes, e, el);
+    }, err, errlen);
+}
+
 int epx_multi_set_methylation_sliced(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples, int64_t ld,
                                      const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
                                      char *err, size_t errlen)
@@ -901,7 +913,8 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
     if (!m || !expr || !row_ptr || !out || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad arguments");
     const int W = (int)m->sess.size();
     const std::vector<int64_t> cut = gene_cuts(row_ptr, n_genes, W);
-    return for_each_device(m, [&](int i, char *e, size_t el) -> int {
+    m->pair_lo.clear();
+    int rc_all = for_each_device(m, [&](int i, char *e, size_t el) -> int {
         epx_session *s = m->sess[(size_t)i];
         const int64_t g0 = cut[(size_t)i], g1 = cut[(size_t)i + 1];
         const int64_t lo = row_ptr[g0], hi = row_ptr[g1];
@@ -938,6 +951,67 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
         int rc = epx_analyze(s, expr, n_genes, n_samples, rp.data(), pi, opt, &r, e, el);
         if (rc == EPX_OK && i == 0) { memcpy(out->counts, r.counts, sizeof r.counts); out->ref_gene = r.ref_gene; }
         return rc;
+    }, err, errlen);
+    if (rc_all == EPX_OK)
+        for (int i = 0; i <= W; i++) m->pair_lo.push_back(row_ptr[cut[(size_t)i]]);
+    return rc_all;
+}
+
+int epx_multi_groups(epx_multi *m, const int64_t *group_ptr, const int32_t *group_pairs, int64_t n_groups,
+                     epx_group_result *out, char *err, size_t errlen)
+{
+    if (!m || !group_ptr || !out || n_groups < 0) return fail(err, errlen, EPX_EINVAL, "bad group arguments");
+    if (m->pair_lo.empty()) return fail(err, errlen, EPX_ESTATE, "epx_multi_groups before epx_multi_analyze");
+    if (group_ptr[0] != 0) return fail(err, errlen, EPX_EINVAL, "bad group_ptr");
+    const int W = (int)m->sess.size();
+    /* a group lies inside one gene, hence on one device: the one that owns its first pair (empty groups: device 0) */
+    std::vector<std::vector<int64_t>> mine((size_t)W);
+    for (int64_t q = 0; q < n_groups; q++) {
+        const int64_t b = group_ptr[q], e = group_ptr[q + 1];
+        if (e < b) return fail(err, errlen, EPX_EINVAL, "group_ptr is not monotone at group %lld", (long long)q);
+        int dev = 0;
+        if (e > b) {
+            if (!group_pairs) return fail(err, errlen, EPX_EINVAL, "group_pairs is NULL");
+            const int64_t first = group_pairs[b];
+            if (first < 0 || first >= m->pair_lo[(size_t)W])
+                return fail(err, errlen, EPX_EINVAL, "group %lld names pair %lld outside [0,%lld)", (long long)q, (long long)first, (long long)m->pair_lo[(size_t)W]);
+            dev = (int)(std::upper_bound(m->pair_lo.begin(), m->pair_lo.end(), first) - m->pair_lo.begin()) - 1;
+            if (dev >= W) dev = W - 1;
+            for (int64_t j = b; j < e; j++)
+                if (group_pairs[j] < m->pair_lo[(size_t)dev] || group_pairs[j] >= m->pair_lo[(size_t)dev + 1])
+                    return fail(err, errlen, EPX_EINVAL, "group %lld mixes genes of two devices", (long long)q);
+        }
+        mine[(size_t)dev].push_back(q);
+    }
+    return for_each_device(m, [&](int i, char *e, size_t el) -> int {
+        const std::vector<int64_t> &qs = mine[(size_t)i];
+        if (qs.empty()) return EPX_OK;
+        const size_t Q = qs.size();
+        const int64_t lo = m->pair_lo[(size_t)i];
+        std::vector<int64_t> ptr(Q + 1, 0);
+        std::vector<int32_t> pairs;
+        for (size_t k = 0; k < Q; k++) {
+            for (int64_t j = group_ptr[qs[k]]; j < group_ptr[qs[k] + 1]; j++) pairs.push_back((int32_t)(group_pairs[j] - lo));
+            ptr[k + 1] = (int64_t)pairs.size();
+        }
+        std::vector<double> g(out->group ? Q * PAIR_COLS : 0), st(out->group_stat ? Q * 3 : 0);
+        std::vector<uint16_t> na(out->group_na ? Q : 0);
+        std::vector<int64_t> dn(out->group_ks_dnum ? Q * 3 : 0);
+        epx_group_result r;
+        r.group = out->group ? g.data() : nullptr; r.group_na = out->group_na ? na.data() : nullptr;
+        r.group_stat = out->group_stat ? st.data() : nullptr; r.group_ks_dnum = out->group_ks_dnum ? dn.data() : nullptr;
+        epx_session *s = m->sess[(size_t)i];
+        int rc = epx_session_run_groups(s, ptr.data(), pairs.data(), (int64_t)Q, nullptr, e, el);
+        if (rc == EPX_OK) rc = epx_session_fetch_groups(s, &r, nullptr, e, el);
+        if (rc != EPX_OK) return rc;
+        for (size_t k = 0; k < Q; k++) { /* rows of different devices are disjoint: no locking */
+            const size_t q = (size_t)qs[k];
+            if (out->group) memcpy(out->group + q * PAIR_COLS, g.data() + k * PAIR_COLS, PAIR_COLS * sizeof(double));
+            if (out->group_na) out->group_na[q] = na[k];
+            if (out->group_stat) memcpy(out->group_stat + q * 3, st.data() + k * 3, 3 * sizeof(double));
+            if (out->group_ks_dnum) memcpy(out->group_ks_dnum + q * 3, dn.data() + k * 3, 3 * sizeof(int64_t));
+        }
+        return EPX_OK;
     }, err, errlen);
 }
 

@@ -185,6 +185,9 @@ int  epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *
 void epx_multi_destroy(epx_multi *m);
 int  epx_multi_set_methylation_rows(epx_multi *m, const double *rows, int64_t n_probes, int64_t n_samples,
                                     int64_t ld, char *err, size_t errlen);
+/* the same from sample-major columns (what the R shim holds: the data.frame's columns) */
+int  epx_multi_set_methylation_cols(epx_multi *m, const double *const *cols, int64_t n_samples, int64_t n_probes,
+                                    char *err, size_t errlen);
 /* Probe-sliced copies instead of replicas (pan-cancer: 35 GB of methylation, of which a device needs only the rows
  * its own genes reference): cuts the genes of the given index exactly as epx_multi_analyze will, and uploads to each
  * device only the distinct rows of `rows` that its pairs name, so the total host-to-device traffic is about one
@@ -215,6 +218,12 @@ typedef struct epx_group_result {
 int  epx_session_run_groups(epx_session *s, const int64_t *group_ptr, const int32_t *group_pairs,
                             int64_t n_groups, void *stream, char *err, size_t errlen);
 int  epx_session_fetch_groups(epx_session *s, epx_group_result *out, void *stream, char *err, size_t errlen);
+
+/* The pooled tables on several GPUs (one process): call after epx_multi_analyze with pair indices of THAT index. A
+ * group lies inside one gene, so it runs on the device that owns the gene; the rows come back in group order. Blocking:
+ * runs and fetches. */
+int  epx_multi_groups(epx_multi *m, const int64_t *group_ptr, const int32_t *group_pairs, int64_t n_groups,
+                      epx_group_result *out, char *err, size_t errlen);
 
 /* ---- result files: R's write.csv, formatted on several host threads (no GPU involved) ----
  * Replaces write.csv(...) at R/EpimethexAnalysis.R:470, :545, :577, :615. values [n_rows][n_cols] row-major;
