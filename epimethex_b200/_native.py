@@ -27,7 +27,8 @@ EXPORTS = [
     "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
     "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
-    "epx_multi_set_methylation_rows", "epx_multi_set_methylation_sliced", "epx_multi_analyze", "epx_session_run_groups", "epx_session_fetch_groups",
+    "epx_multi_set_methylation_rows", "epx_multi_set_methylation_cols", "epx_multi_set_methylation_sliced",
+    "epx_multi_analyze", "epx_multi_groups", "epx_session_run_groups", "epx_session_fetch_groups",
     "epx_write_csv", "epx_format_real15",
 ]
 
@@ -112,6 +113,8 @@ def lib():
     L.epx_multi_destroy.argtypes = [vp]
     L.epx_multi_destroy.restype = None
     L.epx_multi_set_methylation_rows.argtypes = [vp, vp, i64, i64, i64] + e
+    L.epx_multi_set_methylation_cols.argtypes = [vp, C.POINTER(vp), i64, i64] + e
+    L.epx_multi_groups.argtypes = [vp, vp, vp, i64, C.POINTER(_GroupResult)] + e
     L.epx_multi_set_methylation_sliced.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64] + e
     L.epx_multi_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
     L.epx_session_run_groups.argtypes = [vp, vp, vp, i64, vp] + e
@@ -423,6 +426,28 @@ class MultiSession:
         b = _errbuf()
         _check(lib().epx_multi_set_methylation_rows(self._h, rows.ctypes.data, rows.shape[0], rows.shape[1],
                                                     rows.shape[1], b, len(b)), b)
+
+    def set_methylation_columns(self, cols):
+        """cols: n float64 arrays of length P (one per sample: data.frame columns); replicated on every device"""
+        cols = [np.ascontiguousarray(c, np.float64) for c in cols]
+        P = cols[0].shape[0]
+        assert all(c.shape == (P,) for c in cols)
+        ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        b = _errbuf()
+        _check(lib().epx_multi_set_methylation_cols(self._h, ptrs, len(cols), P, b, len(b)), b)
+
+    def analyze_groups(self, group_ptr, group_pairs) -> GroupResult:
+        """pooled tables of the index of the last analyze(): every group runs on the device that owns its gene"""
+        group_ptr = np.ascontiguousarray(group_ptr, np.int64)
+        group_pairs = np.ascontiguousarray(group_pairs, np.int32)
+        q = group_ptr.size - 1
+        res = GroupResult(group=np.empty((q, 11)), group_na=np.zeros(q, np.uint16), group_stat=np.empty((q, 3)),
+                          group_dnum=np.empty((q, 3), np.int64))
+        r = _GroupResult(res.group.ctypes.data, res.group_na.ctypes.data, res.group_stat.ctypes.data,
+                         res.group_dnum.ctypes.data)
+        b = _errbuf()
+        _check(lib().epx_multi_groups(self._h, group_ptr.ctypes.data, group_pairs.ctypes.data, q, C.byref(r), b, len(b)), b)
+        return res
 
     def set_methylation_sliced(self, rows: np.ndarray, row_ptr, probe_idx):
         """probe-sliced copies: each device gets only the rows its share of the genes references"""

@@ -2,6 +2,7 @@
 # the reference (R/EpimethexAnalysis.R:70-72, :88-91, :470; R/Functions.R:224-229). The string work stays in R
 # (annotation explode, R's own collation for ordering); integers and doubles go to libepx through .Call.
 # NOT RUN in the build environment (no R there); epimethex_b200/analysis.py is the executed mirror of this file.
+# device: one GPU (0L) or several (0:7): R stays one process, libepx drives every GPU from its own host thread.
 epimethex.analysis <- function(dfExpressions, dfGpl, dfMethylation, minRangeGene, maxRangeGene, numCores,
                                dataGenesLinear, testExpression, testMethylation,
                                session = NULL, compat_fc = c("reference", "means"), strict = FALSE, device = 0L) {

@@ -21,34 +21,63 @@
 
 #include "epx.h"
 
+/* The handle behind the external pointer: one session (device = one integer) or an epx_multi (device = several
+ * integers: one process drives all GPUs of the box, replacing the PSOCK cluster of R/EpimethexAnalysis.R:333-352). */
+typedef struct { epx_session *one; epx_multi *many; } handle;
+
 static void session_finalizer(SEXP ptr)
 {
-    epx_session *s = (epx_session *)R_ExternalPtrAddr(ptr);
-    if (s) { epx_session_destroy(s); R_ClearExternalPtr(ptr); }
+    handle *h = (handle *)R_ExternalPtrAddr(ptr);
+    if (h) {
+        if (h->one) epx_session_destroy(h->one);
+        if (h->many) epx_multi_destroy(h->many);
+        free(h);
+        R_ClearExternalPtr(ptr);
+    }
 }
 
-/* .Call(C_epx_upload, methylation_data_frame_columns, device) -> external pointer holding the device copy.
+static handle *get_handle(SEXP session)
+{
+    handle *h = (handle *)R_ExternalPtrAddr(session);
+    if (!h) Rf_error("libepx: the session has been released");
+    return h;
+}
+
+/* .Call(C_epx_upload, methylation_data_frame_columns, device) -> external pointer holding the device copy/copies.
  * methCols: VECSXP of n REALSXP columns of length P (the data.frame itself, minus its name column):
- * no as.matrix(), so the 9,000-sample shape never needs an R long vector. */
+ * no as.matrix(), so the 9,000-sample shape never needs an R long vector. device: INTSXP, one or several GPUs. */
 SEXP C_epx_upload(SEXP methCols, SEXP device)
 {
     char err[512] = "";
     const R_xlen_t n = XLENGTH(methCols);
+    const int nd = Rf_length(device);
     if (TYPEOF(methCols) != VECSXP || n < 3) Rf_error("methylation must be a list of at least 3 numeric columns");
+    if (TYPEOF(device) != INTSXP || nd < 1) Rf_error("device must be an integer vector");
     const R_xlen_t P = XLENGTH(VECTOR_ELT(methCols, 0));
     const double **cols = (const double **)malloc((size_t)n * sizeof(double *));
-    if (!cols) Rf_error("out of memory");
+    handle *h = (handle *)calloc(1, sizeof(handle));
+    if (!cols || !h) { free(cols); free(h); Rf_error("out of memory"); }
     for (R_xlen_t j = 0; j < n; j++) {
         SEXP c = VECTOR_ELT(methCols, j);
-        if (TYPEOF(c) != REALSXP || XLENGTH(c) != P) { free(cols); Rf_error("column %ld is not a numeric vector of length %ld", (long)j + 1, (long)P); }
+        if (TYPEOF(c) != REALSXP || XLENGTH(c) != P) { free(cols); free(h); Rf_error("column %ld is not a numeric vector of length %ld", (long)j + 1, (long)P); }
         cols[j] = REAL(c);
     }
-    epx_session *s = NULL;
-    int rc = epx_session_create(Rf_asInteger(device), &s, err, sizeof err);
-    if (rc == EPX_OK) rc = epx_session_set_methylation_cols(s, cols, (int64_t)n, (int64_t)P, err, sizeof err);
+    int rc;
+    if (nd == 1) {
+        rc = epx_session_create(INTEGER(device)[0], &h->one, err, sizeof err);
+        if (rc == EPX_OK) rc = epx_session_set_methylation_cols(h->one, cols, (int64_t)n, (int64_t)P, err, sizeof err);
+    } else {
+        rc = epx_multi_create(INTEGER(device), nd, &h->many, err, sizeof err);
+        if (rc == EPX_OK) rc = epx_multi_set_methylation_cols(h->many, cols, (int64_t)n, (int64_t)P, err, sizeof err);
+    }
     free(cols);
-    if (rc != EPX_OK) { if (s) epx_session_destroy(s); Rf_error("libepx: %s", err); }
-    SEXP ptr = PROTECT(R_MakeExternalPtr(s, R_NilValue, R_NilValue));
+    if (rc != EPX_OK) {
+        if (h->one) epx_session_destroy(h->one);
+        if (h->many) epx_multi_destroy(h->many);
+        free(h);
+        Rf_error("libepx: %s", err);
+    }
+    SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, session_finalizer, TRUE);
     UNPROTECT(1);
     return ptr;
@@ -61,8 +90,7 @@ SEXP C_epx_upload(SEXP methCols, SEXP device)
 SEXP C_epx_analyze(SEXP session, SEXP expr, SEXP rowPtr, SEXP probeIdx, SEXP opts)
 {
     char err[512] = "";
-    epx_session *s = (epx_session *)R_ExternalPtrAddr(session);
-    if (!s) Rf_error("libepx: the session has been released");
+    handle *h = get_handle(session);
     SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
     if (TYPEOF(expr) != REALSXP || Rf_length(dim) != 2) Rf_error("expr must be a numeric matrix");
     const int64_t n = INTEGER(dim)[0], G = INTEGER(dim)[1];
@@ -89,7 +117,10 @@ SEXP C_epx_analyze(SEXP session, SEXP expr, SEXP rowPtr, SEXP probeIdx, SEXP opt
     memset(&r, 0, sizeof r);
     r.pair = REAL(pair); r.pair_na = pna; r.gene = REAL(gene); r.gene_na = gna;
     r.pair_ks_dnum = INTEGER(dnum); r.perm = perm16;
-    int rc = (pna && gna && perm16) ? epx_analyze(s, REAL(expr), G, n, rp, pi, &o, &r, err, sizeof err) : EPX_ENOMEM;
+    int rc = EPX_ENOMEM;
+    if (pna && gna && perm16)
+        rc = h->one ? epx_analyze(h->one, REAL(expr), G, n, rp, pi, &o, &r, err, sizeof err)
+                    : epx_multi_analyze(h->many, REAL(expr), G, n, rp, pi, &o, &r, err, sizeof err);
     if (rc == EPX_OK) {
         /* NA convention: NaN + mask from the engine -> R's NA_real_ (genuine NaN, e.g. 0/0 fold change, stays NaN) */
         for (int64_t j = 0; j < Np; j++)
@@ -121,8 +152,7 @@ SEXP C_epx_analyze(SEXP session, SEXP expr, SEXP rowPtr, SEXP probeIdx, SEXP opt
 SEXP C_epx_groups(SEXP session, SEXP groupPtr, SEXP groupPairs)
 {
     char err[512] = "";
-    epx_session *s = (epx_session *)R_ExternalPtrAddr(session);
-    if (!s) Rf_error("libepx: the session has been released");
+    handle *h = get_handle(session);
     const int64_t Q = (int64_t)Rf_xlength(groupPtr) - 1;
     if (Q < 0) Rf_error("groupPtr must hold at least one offset");
     int64_t *gp = (int64_t *)malloc((size_t)(Q + 1) * sizeof(int64_t));
@@ -133,8 +163,13 @@ SEXP C_epx_groups(SEXP session, SEXP groupPtr, SEXP groupPairs)
     epx_group_result r;
     memset(&r, 0, sizeof r);
     r.group = REAL(grp); r.group_na = na;
-    int rc = epx_session_run_groups(s, gp, (const int32_t *)INTEGER(groupPairs), Q, NULL, err, sizeof err);
-    if (rc == EPX_OK) rc = epx_session_fetch_groups(s, &r, NULL, err, sizeof err);
+    int rc;
+    if (h->one) {
+        rc = epx_session_run_groups(h->one, gp, (const int32_t *)INTEGER(groupPairs), Q, NULL, err, sizeof err);
+        if (rc == EPX_OK) rc = epx_session_fetch_groups(h->one, &r, NULL, err, sizeof err);
+    } else {
+        rc = epx_multi_groups(h->many, gp, (const int32_t *)INTEGER(groupPairs), Q, &r, err, sizeof err);
+    }
     if (rc == EPX_OK)
         for (int64_t q = 0; q < Q; q++)
             for (int c = 0; c < EPX_PAIR_COLS; c++)

@@ -105,3 +105,32 @@ def test_probe_sliced_copies_equal_replicas():
         ms.set_methylation(y)
         full = ms.analyze(x, other.row_ptr, other.probe_idx)
         assert full.pair.shape[0] == other.n_pairs
+
+
+def test_multi_gpu_pooled_groups_and_column_upload():
+    """epx_multi_groups + epx_multi_set_methylation_cols: the pooled tables of CG_of_a_genes / CG_by_position, each group
+    on the device that owns its gene, equal the single-session result; methylation given as data.frame columns"""
+    from epimethex_b200.annotation import build_groups
+    nd = min(_native.device_count(), 4)
+    devices = list(range(nd)) if nd >= 2 else [0, 0, 0]
+    ann = synth.annotation(5000, 300)
+    x = synth.expression(300, 99); y = synth.methylation(5000, 99, ann, threads=2)
+    has = np.ones(5000, bool); has[::29] = False
+    idx = synth.probe_index(ann, 0, 300, probe_has_data=has)
+    with _native.Session(0) as sess:
+        sess.set_methylation(y)
+        one = sess.analyze(x, idx.row_ptr, idx.probe_idx)
+        ref = {by: (gi, sess.analyze_groups(gi.group_ptr, gi.group_pairs))
+               for by in ("gene", "position") for gi in [build_groups(idx, by)]}
+    with _native.MultiSession(devices) as ms:
+        with pytest.raises(_native.EpxError, match="EPX_ESTATE"):
+            ms.analyze_groups(np.zeros(1, np.int64), np.zeros(0, np.int32))     # before analyze
+        ms.set_methylation_columns([np.ascontiguousarray(y[:, j]) for j in range(y.shape[1])])
+        many = ms.analyze(x, idx.row_ptr, idx.probe_idx)
+        assert np.array_equal(many.pair, one.pair, equal_nan=True)
+        for by, (gi, want) in ref.items():
+            assert gi.n_groups > 10
+            got = ms.analyze_groups(gi.group_ptr, gi.group_pairs)
+            assert np.array_equal(got.group, want.group, equal_nan=True), by
+            assert np.array_equal(got.group_na, want.group_na) and np.array_equal(got.group_dnum, want.group_dnum)
+            assert np.array_equal(got.group_stat, want.group_stat, equal_nan=True)
