@@ -1047,20 +1047,27 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
         bulk_g2s(dst + rowb, p.ord + (int64_t)p.pair_slot[j] * p.ldo, ordb, &bar[stage]);
     };
     int cur_gene = -1;
-    if (tid == 0 && p.pair_begin + (int)blockIdx.x < p.n_pairs) issue(p.pair_begin + blockIdx.x, 0);
+    /* every CTA takes a CONTIGUOUS run of pairs: consecutive pairs share their gene (about 23 pairs per gene), so the
+     * label bytes are reloaded once per gene instead of once per pair and the gene's centred expression stays in L1/L2
+     * (a stride of gridDim.x pairs changed gene at every step: 11 % of the stall samples sat in the label reload) */
+    const int np_all = p.n_pairs - p.pair_begin;
+    const int per_cta = (np_all + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int j_begin = p.pair_begin + (int)blockIdx.x * per_cta;
+    const int j_end = min(j_begin + per_cta, p.n_pairs);
+    if (tid == 0 && j_begin < j_end) issue(j_begin, 0);
 
     int it = 0;
-    for (int j = p.pair_begin + blockIdx.x; j < p.n_pairs; j += gridDim.x, it++) {
+    for (int j = j_begin; j < j_end; j++, it++) {
         const int stage = STAGES == 2 ? (it & 1) : 0;
         const int pi = p.probe_idx[j];
         const int gene = p.pair_gene[j];
         __syncthreads(); /* everybody is done with the other stage (and with s_lab / s_med of the previous pair) */
-        if (STAGES == 2 && tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, stage ^ 1);
+        if (STAGES == 2 && tid == 0 && j + 1 < j_end) issue(j + 1, stage ^ 1);
         if (pi < 0) {
             if (tid < PAIR_COLS) p.pair[(int64_t)j * PAIR_COLS + tid] = EPX_NAN;
             if (tid < 3) { p.pair_stat[(int64_t)j * 3 + tid] = EPX_NAN; p.pair_dnum[(int64_t)j * 3 + tid] = -1; }
             if (tid == 0) p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
-            if (STAGES == 1 && tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, 0);
+            if (STAGES == 1 && tid == 0 && j + 1 < j_end) issue(j + 1, 0);
             continue;
         }
         const double *s_row = (const double *)(smem + (size_t)stage * stageb);
@@ -1170,7 +1177,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
         } else __syncthreads();
         /* single stage: nobody reads the row or the order any more (the barrier above), so the next pair's copy
          * starts now and runs under the scalar tail below */
-        if (STAGES == 1 && tid == 0 && j + (int)gridDim.x < p.n_pairs) issue(j + gridDim.x, 0);
+        if (STAGES == 1 && tid == 0 && j + 1 < j_end) issue(j + 1, 0);
 
         if (tid == 0) {
             double out[PAIR_COLS], stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
@@ -1340,7 +1347,7 @@ cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
 {
     if (p.G <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
-        k_gene_sort<<<p.G, CTASORT_THREADS, sort_smem(p.n), st>>>(p);
+        k_gene_sort<<<p.G, ctasort_threads(p.n), sort_smem(p.n), st>>>(p);
         return cudaGetLastError();
     }
     int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS; /* one gene per warp: G is small, favour parallelism */
@@ -1391,7 +1398,7 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sm_count * per_sm;
             if (grid > p.U) grid = p.U;
-            k_probe_rank<<<(unsigned)grid, CTASORT_THREADS, smem, st>>>(p);
+            k_probe_rank<<<(unsigned)grid, ctasort_threads(p.n), smem, st>>>(p);
         }
         return cudaGetLastError();
     }
