@@ -638,7 +638,9 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
         __syncwarp();
         /* merge path: of the first d outputs, i come from A (A wins ties) */
         const unsigned short *A = runs, *B = runs + 512;
-        const int d = min(lane * 32, n), d_end = min(d + 32, n);
+        /* 33 outputs per lane, not 32: with 32 the lanes' 16-bit stores (and their reads of the runs) start 64 bytes
+         * apart and fall on two banks */
+        const int d = min(lane * 33, n), d_end = min(d + 33, n);
         int lo = max(0, d - lb), hi = min(d, la);
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -1031,6 +1033,13 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
     __shared__ int ired[BIG_THREADS / 32];
     __shared__ int s_wtot[BIG_THREADS / 32][3];
     __shared__ double s_med[8];
+    /* scalar results of up to TAIL_PAIRS finished pairs: their tails (Pearson p, tests, p-values, 17 result values --
+     * serial work with dependent global loads) are done 32 at a time, one pair per lane of warp 0, instead of by one
+     * thread per pair while the other 511 wait at the next barrier (12 % of the stall samples) */
+    constexpr int TAIL_PAIRS = 32;
+    __shared__ double t_d[TAIL_PAIRS][TMODE ? 11 : 5]; /* syy, sxy, medUP, medMID, medDOWN, then mg[3], ss[3] (t mode) */
+    __shared__ int t_i[TAIL_PAIRS][6];                 /* pair, gene, guard bits (2 per comparison, biased by 1), d01, d02, d12 */
+    int npend = 0;
     const double dm = (double)m, dn_ = (double)n;
     const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
     const int lane = tid & 31, warp = tid >> 5;
@@ -1045,6 +1054,57 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
         mbar_expect_tx(&bar[stage], stageb);
         bulk_g2s(dst, p.meth + (int64_t)pi * p.ld, rowb, &bar[stage]);
         bulk_g2s(dst + rowb, p.ord + (int64_t)p.pair_slot[j] * p.ldo, ordb, &bar[stage]);
+    };
+    auto flush_tails = [&](int count) { /* all threads call; ends on a barrier-free note: slots are rewritten by tid 0 only */
+        __syncthreads();
+        if (warp == 0) {
+            if (lane < count) {
+                const double syy = t_d[lane][0], sxy = t_d[lane][1];
+                const double medUP = t_d[lane][2], medMID = t_d[lane][3], medDOWN = t_d[lane][4];
+                const int j = t_i[lane][0];
+                const double *ga = p.gene_aux + 4 * (int64_t)t_i[lane][1];
+                const int gbits = t_i[lane][2];
+                double out[PAIR_COLS], stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
+                int dnum[3] = { -1, -1, -1 };
+                unsigned na = 0;
+                double r = EPX_NAN, pr = EPX_NAN;
+                if (ga[0] != 0.0 && syy != 0.0 && n >= 3) {
+                    r = sxy * ga[3] * rsqrt(syy);
+                    r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+                    pr = epx_pearson_p_tab(r, p.pt_tab, p.pt_n, dn_ - 2.0);
+                } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
+                if (TMODE) {
+                    const double mg[3] = { t_d[lane][TMODE ? 5 : 0], t_d[lane][TMODE ? 6 : 0], t_d[lane][TMODE ? 7 : 0] };
+                    const double vg[3] = { t_d[lane][TMODE ? 8 : 0] / (dm - 1.0), t_d[lane][TMODE ? 9 : 0] / (dm - 1.0),
+                                           t_d[lane][TMODE ? 10 : 0] / (dm - 1.0) };
+                    const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
+                    for (int c = 0; c < 3; c++) {
+                        double df = EPX_NAN;
+                        bool ok = false;
+                        if (((gbits >> (2 * c)) & 3) - 1 == 1)
+                            ok = epx_welch(mg[ga_[c]], vg[ga_[c]], dm, mg[gb_[c]], vg[gb_[c]], dm, &stat[c], &df) == 0;
+                        if (ok) pv[c] = epx_t_two_sided_p(stat[c], df);
+                        else { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
+                    }
+                } else {
+                    for (int c = 0; c < 3; c++) {
+                        const int ddc = t_i[lane][3 + c];
+                        if (((gbits >> (2 * c)) & 3) - 1 != 0) {
+                            dnum[c] = ddc * m;
+                            stat[c] = (double)dnum[c] / (dm * dm);
+                            pv[c] = p.lut_asym[ddc]; /* m > 341: n.x*n.y >= 10000, always asymptotic */
+                        } else na |= 1u << (EPX_P_UP_MID + c);
+                    }
+                }
+                out[0] = medDOWN; out[1] = medMID; out[2] = medUP;
+                out[3] = medUP - medMID; out[4] = medUP - medDOWN; out[5] = medMID - medDOWN;
+                out[6] = pv[0]; out[7] = pv[1]; out[8] = pv[2]; out[9] = r; out[10] = pr;
+                for (int c = 0; c < PAIR_COLS; c++) p.pair[(int64_t)j * PAIR_COLS + c] = out[c];
+                for (int c = 0; c < 3; c++) { p.pair_stat[(int64_t)j * 3 + c] = stat[c]; p.pair_dnum[(int64_t)j * 3 + c] = dnum[c]; }
+                p.pair_na[j] = (uint16_t)na;
+            }
+            __syncwarp(); /* lane 0 refills the slots only after every lane has read its own */
+        }
     };
     int cur_gene = -1;
     /* every CTA takes a CONTIGUOUS run of pairs: consecutive pairs share their gene (about 23 pairs per gene), so the
@@ -1124,7 +1184,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
         }
 
         /* sorted walk: thread t owns positions [t*chunk, (t+1)*chunk); label counts by warp scan + warp totals */
-        const int chunk = (n + nt - 1) / nt;
+        int chunk = (n + nt - 1) / nt;
+        chunk += (chunk & 3) == 0 ? 1 : 0; /* lanes start `chunk` 16-bit entries apart: a multiple of 4 would share two banks */
         const int k0 = min(tid * chunk, n), k1 = min(k0 + chunk, n);
         int c0 = 0, c1 = 0, c2 = 0;
         for (int k = k0; k < k1; k++) {
@@ -1180,44 +1241,19 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
         if (STAGES == 1 && tid == 0 && j + 1 < j_end) issue(j + 1, 0);
 
         if (tid == 0) {
-            double out[PAIR_COLS], stat[3] = { EPX_NAN, EPX_NAN, EPX_NAN }, pv[3] = { EPX_NAN, EPX_NAN, EPX_NAN };
-            int dnum[3] = { -1, -1, -1 };
-            unsigned na = 0;
-            double r = EPX_NAN, pr = EPX_NAN;
-            if (ga[0] != 0.0 && syy != 0.0 && n >= 3) {
-                r = sxy * ga[3] * rsqrt(syy);
-                r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
-                pr = epx_pearson_p_tab(r, p.pt_tab, p.pt_n, dn_ - 2.0);
-            } else na |= (1u << EPX_PEARSON_R) | (1u << EPX_PEARSON_P);
+            t_d[npend][0] = syy; t_d[npend][1] = sxy;
+            t_d[npend][2] = medUP; t_d[npend][3] = medMID; t_d[npend][4] = medDOWN;
             if (TMODE) {
-                const double mg[3] = { mg0, mg1, mg2 };
-                const double vg[3] = { ss0 / (dm - 1.0), ss1 / (dm - 1.0), ss2 / (dm - 1.0) };
-                const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
-                for (int c = 0; c < 3; c++) {
-                    double df = EPX_NAN;
-                    bool ok = false;
-                    if (guard[c] == 1) ok = epx_welch(mg[ga_[c]], vg[ga_[c]], dm, mg[gb_[c]], vg[gb_[c]], dm, &stat[c], &df) == 0;
-                    if (ok) pv[c] = epx_t_two_sided_p(stat[c], df);
-                    else { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
-                }
-            } else {
-                const int dd[3] = { d01, d02, d12 };
-                for (int c = 0; c < 3; c++) {
-                    if (guard[c] != 0) {
-                        dnum[c] = dd[c] * m;
-                        stat[c] = (double)dnum[c] / (dm * dm);
-                        pv[c] = p.lut_asym[dd[c]]; /* m > 341: n.x*n.y >= 10000, always asymptotic */
-                    } else na |= 1u << (EPX_P_UP_MID + c);
-                }
+                t_d[npend][TMODE ? 5 : 0] = mg0; t_d[npend][TMODE ? 6 : 0] = mg1; t_d[npend][TMODE ? 7 : 0] = mg2;
+                t_d[npend][TMODE ? 8 : 0] = ss0; t_d[npend][TMODE ? 9 : 0] = ss1; t_d[npend][TMODE ? 10 : 0] = ss2;
             }
-            out[0] = medDOWN; out[1] = medMID; out[2] = medUP;
-            out[3] = medUP - medMID; out[4] = medUP - medDOWN; out[5] = medMID - medDOWN;
-            out[6] = pv[0]; out[7] = pv[1]; out[8] = pv[2]; out[9] = r; out[10] = pr;
-            for (int c = 0; c < PAIR_COLS; c++) p.pair[(int64_t)j * PAIR_COLS + c] = out[c];
-            for (int c = 0; c < 3; c++) { p.pair_stat[(int64_t)j * 3 + c] = stat[c]; p.pair_dnum[(int64_t)j * 3 + c] = dnum[c]; }
-            p.pair_na[j] = (uint16_t)na;
+            t_i[npend][0] = j; t_i[npend][1] = gene;
+            t_i[npend][2] = (guard[0] + 1) | ((guard[1] + 1) << 2) | ((guard[2] + 1) << 4);
+            t_i[npend][3] = d01; t_i[npend][4] = d02; t_i[npend][5] = d12;
         }
+        if (++npend == TAIL_PAIRS) { flush_tails(npend); npend = 0; }
     }
+    if (npend > 0) flush_tails(npend);
 }
 
 /* ============================================================ transpose (sample-major upload) */
