@@ -1,5 +1,5 @@
 /*
- * epx_ctasort.cuh — one CTA (8 to 10 warps) orders one long row (1024 < n <= 16384 values, e.g. the 9,000-sample
+ * epx_ctasort.cuh — one CTA (8 warps) orders one long row (1024 < n <= 16384 values, e.g. the 9,000-sample
  * pan-cancer shape) held in shared memory: every warp sorts 512-value chunks with the register bitonic sort of
  * epx_warpsort.cuh, then log2(chunks) merge passes (merge path: each thread produces a contiguous slice of the
  * output after a binary search for its split point) combine them. Exact and stable: equal values keep ascending
@@ -10,22 +10,14 @@
 
 namespace epx {
 
-constexpr int CTASORT_THREADS = 320;               /* launch bound: 8..10 warps, see ctasort_threads() */
+constexpr int CTASORT_THREADS = 256;               /* launch bound, see ctasort_threads() */
 constexpr int CTASORT_EPS = 16;                    /* values per lane in the register sort of a chunk */
 constexpr int CTASORT_CHUNK = 32 * CTASORT_EPS;    /* 512: the 1,024-value network costs 3.4x the 512-value one, a merge pass far less */
 
-/* Threads of the sorting CTA for rows of n values: the 512-value chunks are sorted one per warp, round after round, and
- * a last round with a few busy warps costs as much as a full one (the sort is latency-bound per warp), so take the
- * warp count in 8..10 that needs the fewest rounds (n = 9,000: 18 chunks -> 9 warps, two full rounds instead of
- * 8 + 8 + 2). */
-inline int ctasort_threads(int n)
-{
-    const int chunks = (n + CTASORT_CHUNK - 1) / CTASORT_CHUNK;
-    int best = 8;
-    for (int w = 9; w <= 10; w++)
-        if ((chunks + w - 1) / w < (chunks + best - 1) / best) best = w;
-    return 32 * best;
-}
+/* Threads of the sorting CTA. Measured on the 9,000-sample shape (18 chunks of 512 values): 8 warps 7.36 ms, 9 warps
+ * (two full rounds of chunk sorts instead of 8 + 8 + 2) 7.94 ms, 12 warps 7.40 ms -- the kernel is bound by
+ * shared-memory traffic in the merge passes, not by the number of rounds, so the smallest CTA stays. */
+inline int ctasort_threads(int) { return 256; }
 
 /* entries of each of the two index buffers: a whole number of chunks, so that the second buffer can double as
  * the warp sorts' scratch (one chunk of entries per chunk being sorted) while the first one is being filled */
@@ -44,10 +36,11 @@ __device__ unsigned short *cta_merge_runs(const double *s_val, const int n, cons
                                           unsigned short *s_b)
 {
     unsigned short *src = s_a, *dst = s_b;
-    /* entries per thread and pass; never a multiple of 4: the lanes of a warp start `per` 16-bit entries apart, and a
-     * multiple of 4 (n = 9,000 on 288 threads: 32) puts them on two banks -- measured 26 % slower than 8 warps */
+    /* entries per thread and pass; never a multiple of 8: the lanes of a warp start `per` 16-bit entries apart, and a
+     * multiple of 8 puts them on at most eight banks (n = 9,000 on 288 threads: per = 32, two banks, measured 26 %
+     * slower than per = 36 on 256 threads; 37 instead of 36 measured 6 % slower again, so only the bad strides move) */
     int per = (n + blockDim.x - 1) / blockDim.x;
-    per += (per & 3) == 0 ? 1 : 0;
+    per += (per & 7) == 0 ? 1 : 0;
     for (int len = run_len; len < n; len <<= 1) {
         int o = min((int)threadIdx.x * per, n);
         const int o_end = min(o + per, n);

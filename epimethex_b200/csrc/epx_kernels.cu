@@ -1185,7 +1185,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
 
         /* sorted walk: thread t owns positions [t*chunk, (t+1)*chunk); label counts by warp scan + warp totals */
         int chunk = (n + nt - 1) / nt;
-        chunk += (chunk & 3) == 0 ? 1 : 0; /* lanes start `chunk` 16-bit entries apart: a multiple of 4 would share two banks */
+        chunk += (chunk & 7) == 0 ? 1 : 0; /* lanes start `chunk` 16-bit entries apart: a multiple of 8 would share few banks */
         const int k0 = min(tid * chunk, n), k1 = min(k0 + chunk, n);
         int c0 = 0, c1 = 0, c2 = 0;
         for (int k = k0; k < k1; k++) {
