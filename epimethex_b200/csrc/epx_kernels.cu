@@ -649,9 +649,17 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
         int pa = lo, pb = d - lo;
         unsigned short xa = A[min(pa, la - 1)], xb = B[min(pb, lb - 1)];
         double va = vals[xa], vb = vals[xb];
+        /* the tie mark of an output (bit 15: the next output holds an equal value) is known one step later, so every
+         * store is delayed by one step; the last output of a lane's slice is compared with the first of the next lane's */
+        unsigned short prev_x = 0;
+        double prev_v = 0.0, first_v = 0.0;
         for (int k = d; k < d_end; k++) {
             const bool take_a = pb >= lb || (pa < la && !(vb < va));
-            merged[k] = take_a ? xa : xb;
+            const unsigned short cur_x = take_a ? xa : xb;
+            const double cur_v = take_a ? va : vb;
+            if (k > d) merged[k - 1] = (unsigned short)(prev_x | (cur_v == prev_v ? 0x8000u : 0u));
+            else first_v = cur_v;
+            prev_x = cur_x; prev_v = cur_v;
             pa += take_a ? 1 : 0;
             pb += take_a ? 0 : 1;
             const unsigned short nx = take_a ? A[min(pa, la - 1)] : B[min(pb, lb - 1)];
@@ -659,8 +667,10 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
             xa = take_a ? nx : xa; va = take_a ? nv : va;
             xb = take_a ? xb : nx; vb = take_a ? vb : nv;
         }
+        const double next_first = __shfl_down_sync(FULL, first_v, 1);
+        if (d < d_end) merged[d_end - 1] = (unsigned short)(prev_x | ((d_end < n && prev_v == next_first) ? 0x8000u : 0u));
         __syncwarp();
-        /* tie marks and the padded row (pad positions carry index n), 16 bytes per store */
+        /* the padded row (pad positions carry index n), 16 bytes per store */
         uint16_t *o = p.ord + slot * p.ldo;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -670,12 +680,7 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int k = k0 + i;
-                    unsigned v = (unsigned)n;
-                    if (k < n) {
-                        v = merged[k];
-                        if (k + 1 < n && vals[v] == vals[merged[k + 1]]) v |= 0x8000u;
-                    }
-                    w[i] = v;
+                    w[i] = k < n ? (unsigned)merged[k] : (unsigned)n;
                 }
                 uint4 q;
                 q.x = w[0] | (w[1] << 16); q.y = w[2] | (w[3] << 16); q.z = w[4] | (w[5] << 16); q.w = w[6] | (w[7] << 16);
