@@ -31,7 +31,11 @@ template <bool DESC> __device__ __forceinline__ bool comes_before(double a, doub
 /* merge passes: s_a holds sorted runs of run_len entries (the last one may be shorter); every pass merges adjacent
  * pairs of runs (merge path: each thread produces a contiguous slice of the output after a binary search for its split
  * point; the left run wins ties). Ends on a __syncthreads(); returns the buffer that holds the result. */
-template <bool DESC>
+/* MARK: the LAST pass also sets bit 15 of every output whose successor holds an equal value (the tie mark of the order
+ * rows). The mark of an output is known one step later (the merge state after an output names the next one, also
+ * across the slices of two threads), so the stores of that pass are delayed by one step; this replaces a separate sweep
+ * of two 8-byte value gathers per element. Needs at least one pass (n > run_len). */
+template <bool DESC, bool MARK = false>
 __device__ unsigned short *cta_merge_runs(const double *s_val, const int n, const int run_len, unsigned short *s_a,
                                           unsigned short *s_b)
 {
@@ -62,15 +66,28 @@ __device__ unsigned short *cta_merge_runs(const double *s_val, const int n, cons
             const int lastA = la - 1, lastB = la + lb - 1;
             unsigned short xa = A[min(pa, lastA)], xb = A[min(la + pb, lastB)];
             double va = s_val[xa], vb = s_val[xb];
+            const bool mark = MARK && 2 * len >= n; /* one pair of runs is left: this thread has one segment */
+            unsigned short prev_x = 0;
+            double prev_v = 0.0;
             for (int k = o; k < seg_end; k++) {
                 const bool take_a = pb >= lb || (pa < la && !comes_before<DESC>(vb, va));
-                dst[k] = take_a ? xa : xb;
+                if (mark) {
+                    const unsigned short cur_x = take_a ? xa : xb;
+                    const double cur_v = take_a ? va : vb;
+                    if (k > o) dst[k - 1] = (unsigned short)(prev_x | (cur_v == prev_v ? 0x8000u : 0u));
+                    prev_x = cur_x; prev_v = cur_v;
+                } else dst[k] = take_a ? xa : xb;
                 pa += take_a ? 1 : 0;
                 pb += take_a ? 0 : 1;
                 const unsigned short nx = A[take_a ? min(pa, lastA) : min(la + pb, lastB)];
                 const double nv = s_val[nx];
                 xa = take_a ? nx : xa; va = take_a ? nv : va;
                 xb = take_a ? xb : nx; vb = take_a ? vb : nv;
+            }
+            if (mark && seg_end > o) {
+                const bool more = pa < la || pb < lb; /* the heads now name output seg_end, if there is one */
+                const bool take_a = pb >= lb || (pa < la && !comes_before<DESC>(vb, va));
+                dst[seg_end - 1] = (unsigned short)(prev_x | ((more && (take_a ? va : vb) == prev_v) ? 0x8000u : 0u));
             }
             o = seg_end;
         }
@@ -82,7 +99,7 @@ __device__ unsigned short *cta_merge_runs(const double *s_val, const int n, cons
 
 /* s_val: the row (n doubles, shared); s_a, s_b: ctasort_entries(n) uint16 each. All threads of the CTA must call.
  * Returns the buffer (s_a or s_b) that holds the sample indices in sorted order. */
-template <bool DESC>
+template <bool DESC, bool MARK = false>
 __device__ unsigned short *cta_sort_row(const double *s_val, const int n, unsigned short *s_a, unsigned short *s_b,
                                         const unsigned one)
 {
@@ -108,7 +125,7 @@ __device__ unsigned short *cta_sort_row(const double *s_val, const int n, unsign
     }
     __syncthreads();
 
-    return cta_merge_runs<DESC>(s_val, n, CTASORT_CHUNK, s_a, s_b);
+    return cta_merge_runs<DESC, MARK>(s_val, n, CTASORT_CHUNK, s_a, s_b);
 }
 
 } // namespace epx

@@ -306,15 +306,23 @@ __global__ void __launch_bounds__(CTASORT_THREADS, 2) k_probe_rank(RankParams p)
             for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
         }
         __syncthreads();
-        const unsigned short *ord = cta_sort_row<false>(s_val, n, s_a, s_b, p.one);
+        /* n > 1024 here, so there is a last merge pass and it leaves the tie marks in place */
+        const unsigned short *ord = cta_sort_row<false, true>(s_val, n, s_a, s_b, p.one);
         uint16_t *o = p.ord + slot * p.ldo;
-        for (int k = threadIdx.x; k < p.ldo; k += blockDim.x) {
-            unsigned short v = (unsigned short)n; /* pad */
-            if (k < n) {
-                v = ord[k];
-                if (k + 1 < n && s_val[v] == s_val[ord[k + 1]]) v |= 0x8000u;
+        if ((p.ldo & 7) == 0 && (((uintptr_t)p.ord) & 15u) == 0) { /* 16 bytes per load and store */
+            for (int k0 = threadIdx.x * 8; k0 < p.ldo; k0 += blockDim.x * 8) {
+                uint4 q;
+                if (k0 + 8 <= n) q = *reinterpret_cast<const uint4 *>(ord + k0);
+                else {
+                    unsigned w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = k0 + i < n ? (unsigned)ord[k0 + i] : (unsigned)n; /* pad */
+                    q.x = w[0] | (w[1] << 16); q.y = w[2] | (w[3] << 16); q.z = w[4] | (w[5] << 16); q.w = w[6] | (w[7] << 16);
+                }
+                *reinterpret_cast<uint4 *>(o + k0) = q;
             }
-            o[k] = v;
+        } else {
+            for (int k = threadIdx.x; k < p.ldo; k += blockDim.x) o[k] = k < n ? ord[k] : (unsigned short)n;
         }
     }
 }
@@ -676,14 +684,14 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
         for (int c = 0; c < 4; c++) {
             const int k0 = (lane + 32 * c) * 8;
             if (k0 < p.ldo) {
-                unsigned w[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int k = k0 + i;
-                    w[i] = k < n ? (unsigned)merged[k] : (unsigned)n;
-                }
                 uint4 q;
-                q.x = w[0] | (w[1] << 16); q.y = w[2] | (w[3] << 16); q.z = w[4] | (w[5] << 16); q.w = w[6] | (w[7] << 16);
+                if (k0 + 8 <= n) q = *reinterpret_cast<const uint4 *>(merged + k0);
+                else {
+                    unsigned w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = k0 + i < n ? (unsigned)merged[k0 + i] : (unsigned)n;
+                    q.x = w[0] | (w[1] << 16); q.y = w[2] | (w[3] << 16); q.z = w[4] | (w[5] << 16); q.w = w[6] | (w[7] << 16);
+                }
                 *reinterpret_cast<uint4 *>(o + k0) = q;
             }
         }
