@@ -103,14 +103,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(name: str, rank: int, world: int = 1):
+def _host_matrix(shape, pinned: bool):
+    """page-locked (epx_host_alloc) for the GPU arm; plain numpy for the reference arm, which must not load libepx"""
+    if pinned:
+        from epimethex_b200 import _native
+        try:
+            return _native.pinned_empty(shape), True
+        except Exception:
+            pass
+    return np.empty(shape), False
+
+
+def make_workload(name: str, rank: int, world: int = 1, pinned: bool = True):
     """Synthetic inputs for one rank. Rank r draws its own cohort (data seeds + r) over the same annotation; a
     workload with shard=True is ONE cohort whose genes are cut into `world` ranges (strong scaling)."""
-    from epimethex_b200 import _native, synth
+    from epimethex_b200 import synth
 
     w = WORKLOADS[name]
     if w.get("shard"):
-        return make_sharded_workload(w, rank, world)
+        return make_sharded_workload(w, rank, world, pinned)
     dims = dict(synth.SHAPES[w["shape"]]) if w["shape"] else dict(n_genes=w["n_genes"], n_samples=w["n_samples"], n_probes=w["n_probes"])
     n, P = dims["n_samples"], dims["n_probes"]
     g0, g1 = w["genes"]
@@ -118,11 +129,7 @@ def make_workload(name: str, rank: int, world: int = 1):
     ann = synth.annotation(P, dims["n_genes"])
     idx = synth.probe_index(ann, g0, g1)
     expr = synth.expression(g1 - g0, n, g0=g0, seed=synth.SEED_EXPR + rank)
-    pinned = True
-    try:
-        meth = _native.pinned_empty((P, n))
-    except Exception:
-        meth, pinned = np.empty((P, n)), False
+    meth, pinned = _host_matrix((P, n), pinned)
     threads = max(1, min(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     # only rows some pair references are ever read; generate those, zero the rest
     used = np.unique(idx.probe_idx[idx.probe_idx >= 0])
@@ -137,16 +144,17 @@ def make_workload(name: str, rank: int, world: int = 1):
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(work, chunks))
     return dict(w=w, n=n, P=P, G=g1 - g0, ann=ann, idx=idx, expr=np.ascontiguousarray(expr), meth=meth,
-                gen_s=time.time() - t0, n_unique=int(used.size), pinned=pinned, rows=P)
+                gen_s=time.time() - t0, n_unique=int(used.size), pinned=pinned, rows=P,
+                total_pairs=int(idx.n_pairs) * world)
 
 
-def make_sharded_workload(w, rank: int, world: int):
+def make_sharded_workload(w, rank: int, world: int, pinned: bool = True):
     """one cohort, genes cut into `world` ranges of equal pair counts; this rank's range with a probe-sliced
     methylation copy (only the rows its pairs name, re-indexed)"""
     from concurrent.futures import ThreadPoolExecutor
     from dataclasses import replace
 
-    from epimethex_b200 import _native, distributed, synth
+    from epimethex_b200 import distributed, synth
 
     dims = dict(synth.SHAPES[w["shape"]])
     n, P = dims["n_samples"], dims["n_probes"]
@@ -154,17 +162,17 @@ def make_sharded_workload(w, rank: int, world: int):
     ann = synth.annotation(P, dims["n_genes"])
     g_lo, g_hi = w["genes"]
     whole = synth.probe_index(ann, g_lo, g_hi)
-    a, b = distributed.partition_genes(whole.row_ptr, world)[rank]
+    parts = distributed.partition_genes(whole.row_ptr, world)
+    a, b = parts[rank]
     g0, g1 = g_lo + a, g_lo + b
     idx = synth.probe_index(ann, g0, g1)
+    # every rank's (from, to) call builds its own index (the reference's dedup acts inside one call only)
+    total_pairs = sum(int(synth.probe_index(ann, g_lo + pa, g_lo + pb).n_pairs) if (pa, pb) != (a, b) else int(idx.n_pairs)
+                      for pa, pb in parts)
     rows, local = distributed.slice_probes(idx.probe_idx)
     idx = replace(idx, probe_idx=local)
     expr = synth.expression(g1 - g0, n, g0=g0, seed=synth.SEED_EXPR)
-    pinned = True
-    try:
-        meth = _native.pinned_empty((max(1, rows.size), n))
-    except Exception:
-        meth, pinned = np.empty((max(1, rows.size), n)), False
+    meth, pinned = _host_matrix((max(1, rows.size), n), pinned)
     threads = max(1, min(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     step = max(16, 1_000_000 // n)
 
@@ -175,43 +183,97 @@ def make_sharded_workload(w, rank: int, world: int):
         list(ex.map(work, range(0, rows.size, step)))
     return dict(w=w, n=n, P=P, G=g1 - g0, ann=ann, idx=idx, expr=np.ascontiguousarray(expr), meth=meth,
                 gen_s=time.time() - t0, n_unique=int(rows.size), pinned=pinned, rows=int(meth.shape[0]),
-                gene_range=(g0, g1))
+                gene_range=(g0, g1), total_pairs=total_pairs)
 
 
 _CPU_RATE = {}
 
 
-def cpu_baseline(wl, target_s: float, threads: int):
+def gene_sample(idx, G: int, stride: int, offset: int = 0):
+    """every stride-th gene of the workload as its own CSR: (selected genes, row_ptr, probe_idx)"""
+    sel = np.arange(offset % stride, G, stride)
+    counts = idx.row_ptr[sel + 1] - idx.row_ptr[sel]
+    ptr = np.zeros(sel.size + 1, np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    pi = (np.concatenate([idx.probe_idx[idx.row_ptr[g]:idx.row_ptr[g + 1]] for g in sel]) if sel.size
+          else np.zeros(0, np.int32))
+    return sel, ptr, np.ascontiguousarray(pi, np.int32)
+
+
+def cpu_baseline(wl, target_s: float, threads: int, keep: bool = False):
     """oracle (restated reference, C + OpenMP over genes) on every k-th gene of the same workload, sized to take
-    about target_s seconds"""
+    about target_s seconds (k = 1, the whole workload, when that fits). keep=True also returns the oracle's tables
+    and the gene sample, which the parity check of the GPU arm compares with the GPU's tables for the same sample."""
     import oracle
 
     idx, expr, meth = wl["idx"], wl["expr"], wl["meth"]
     G = wl["G"]
 
     def run(stride, offset=0):
-        sel = np.arange(offset % stride, G, stride)
-        counts = idx.row_ptr[sel + 1] - idx.row_ptr[sel]
-        ptr = np.zeros(sel.size + 1, np.int64)
-        np.cumsum(counts, out=ptr[1:])
-        pi = np.concatenate([idx.probe_idx[idx.row_ptr[g]:idx.row_ptr[g + 1]] for g in sel]) if sel.size else np.zeros(0, np.int32)
+        sel, ptr, pi = gene_sample(idx, G, stride, offset)
         t = time.perf_counter()
-        oracle.analyze(expr[sel], meth, ptr, pi, test_expr_t=wl["w"]["te"], test_meth_t=wl["w"]["tm"], threads=threads)
-        return int(ptr[-1]), time.perf_counter() - t, sel.size
+        res = oracle.analyze(expr[sel], meth, ptr, pi, test_expr_t=wl["w"]["te"], test_meth_t=wl["w"]["tm"], threads=threads)
+        return int(ptr[-1]), time.perf_counter() - t, sel, ptr, pi, res
 
     key = id(wl)
     if key not in _CPU_RATE:
-        pairs, dt, _ = run(max(1, G // 64))
+        pairs, dt = run(max(1, G // 64))[:2]
         _CPU_RATE[key] = [pairs / max(dt, 1e-6), 0]
     rate = _CPU_RATE[key][0]
     total_pairs = int(idx.row_ptr[-1])
     want_pairs = min(total_pairs, max(500, int(rate * target_s)))
-    stride = max(1, int(round(total_pairs / max(want_pairs, 1))))
+    stride = max(1, int(total_pairs / max(want_pairs, 1) + 0.999))
     _CPU_RATE[key][1] += 1
-    pairs, dt, ngenes = run(stride, _CPU_RATE[key][1])
-    return {"value": pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port", "pairs": pairs, "seconds": dt,
-            "sample": f"every {stride}th gene of the workload ({ngenes} genes, {pairs} pairs) in {dt:.2f} s; "
-                      "C/OpenMP restatement of the R reference (R is not installable here)"}
+    pairs, dt, sel, ptr, pi, res = run(stride, _CPU_RATE[key][1])
+    _CPU_RATE[key][0] = pairs / max(dt, 1e-6)
+    out = {"value": pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port", "pairs": pairs, "seconds": dt,
+           "sample": f"every {stride}th gene of the workload ({sel.size} genes, {pairs} pairs) in {dt:.2f} s; "
+                     "C/OpenMP restatement of the R reference (R is not installable here)"}
+    if keep:
+        out["oracle"] = (sel, ptr, pi, res)
+    return out
+
+
+RTOL, ATOL = 1e-8, 1e-10   # BASELINE.json north_star: doubles within 1e-10 absolute or 1e-8 relative
+
+
+def parity_report(got, ref, what: str):
+    """GPU tables against the oracle's on the same inputs: integers (sample order, KS numerators, NA masks, bin.var
+    group sizes, reference gene) must be identical, doubles within RTOL/ATOL (NaN == NaN)."""
+    ints = 0
+    ints += int(tuple(got.counts) != tuple(ref.counts)) + int(got.ref_gene != ref.ref_gene)
+    for a, b in ((got.perm.astype(np.int32), ref.perm), (got.ks_dnum, ref.ks_dnum), (got.gene_ks_dnum, ref.gene_ks_dnum)):
+        ints += int((np.asarray(a) != np.asarray(b)).sum())
+    na_bad = int((got.pair_na != ref.pair_na).sum() + (got.gene_na != ref.gene_na).sum())
+    max_abs, max_rel, bad = 0.0, 0.0, 0
+    for a, b in ((got.pair, ref.pair), (got.pair_stat, ref.pair_stat), (got.gene, ref.gene)):
+        nan_a, nan_b = np.isnan(a), np.isnan(b)
+        bad += int((nan_a != nan_b).sum())
+        fin = ~(nan_a | nan_b)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            d = np.abs(a[fin] - b[fin])
+            d = np.where(a[fin] == b[fin], 0.0, d)      # equal infinities
+            bad += int((d > ATOL + RTOL * np.abs(b[fin])).sum())
+            if d.size:
+                big = d > ATOL                          # the relative bar only matters where the absolute one fails
+                max_abs = max(max_abs, float(d.max()))
+                if big.any():
+                    max_rel = max(max_rel, float((d[big] / np.abs(b[fin][big])).max()))
+    return {"against": "oracle (C restatement of the R reference; parity unpinned: no R available)", "sample": what,
+            "pairs_checked": int(ref.pair.shape[0]), "genes_checked": int(ref.gene.shape[0]),
+            "int_mismatches": ints, "na_mismatches": na_bad, "double_mismatches": bad,
+            "max_abs": max_abs, "max_rel_where_abs_exceeds_atol": max_rel, "rtol": RTOL, "atol": ATOL,
+            "ok": bool(ints == 0 and na_bad == 0 and bad == 0)}
+
+
+def config_of(wl, name: str, world: int, total_pairs: int):
+    """the `config` object: identical keys and values in the GPU arm and in the reference arm"""
+    idx, n, G, P = wl["idx"], wl["n"], wl["G"], wl["P"]
+    return {"workload": wl["w"]["desc"], "name": name, "pairs_per_gpu": int(idx.n_pairs), "genes": int(G), "samples": int(n),
+            "probes": int(P), "unique_probes": int(wl["n_unique"]), "methylation_rows_on_gpu": int(wl["rows"]),
+            "total_pairs": int(total_pairs),
+            "l2": "inputs (%.2f GB methylation on this GPU) exceed the 126 MB L2; no flush" % (wl["rows"] * n * 8 / 1e9),
+            "parallelism": f"genes sharded, {world} rank(s), NCCL gather of result tables" if world > 1 else "single GPU"}
 
 
 def main():
@@ -224,9 +286,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-mode", dest="other_mode", action="store_false",
+                    help="skip the second timing with the other methylation test (KS <-> Welch t)")
     ap.add_argument("--pooled", default="", choices=["", "gene", "position", "island"],
                     help="also time the pooled probe-group pass (CG_of_a_genes / by position / by island rows)")
-    ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: seconds for warmup + steps")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds for warmup + steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -239,21 +303,24 @@ def main():
 
     if args.impl == "reference":
         # the reference's CPU implementation of the path (the oracle port: the reference is pure R and R is not
-        # installable) on this host's cores; rank 0 only. Every step is a bounded gene sample of the workload, sized
-        # so that warmup + steps finish in about --ref-budget seconds.
+        # installable) on this host's cores; rank 0 only. Every step is the whole workload when warmup + steps of that
+        # fit --ref-budget seconds, else a bounded gene sample (every k-th gene). No libepx, no CUDA context, no torch.
         if rank != 0:
             return 0
-        wl = make_workload(args.workload, 0, args.gpus)
+        wl = make_workload(args.workload, 0, args.gpus, pinned=False)
         total = args.warmup + args.steps
         per_step = max(0.05, args.ref_budget / max(1, total))
         runs = [cpu_baseline(wl, per_step, cores) for _ in range(total)][args.warmup:]
         pairs = sum(r["pairs"] for r in runs)
         secs = sum(r["seconds"] for r in runs)
         v = pairs / secs
+        # at N > 1 the GPU arm runs one cohort of this shape per GPU (weak scaling): same per-GPU config, N x the pairs
+        strong = bool(wl["w"].get("shard"))
+        cfg = config_of(wl, args.workload, args.gpus, wl["total_pairs"])
         line = {"impl": "reference", "metric": "gene-probe pairs/s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["w"]["desc"], "name": args.workload},
+                "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": runs[-1]["sample"]},
                 "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -362,6 +429,24 @@ def main():
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    # N > 1: rank 0 checks every gathered shard against a bit-exact checksum taken by the rank that computed it
+    # (64-bit wrap-around sum of the table's bit patterns: order-independent, so it is exact)
+    shards = None
+    if world > 1:
+        pair_t, pdst, gene_t, gdst, _ = gather_plan
+        mine = torch.stack([pair_t.view(torch.int64).sum(), gene_t.view(torch.int64).sum(),
+                            torch.tensor(pair_t.shape[0], device="cuda"), torch.tensor(gene_t.shape[0], device="cuda")])
+        sums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            bad = []
+            for r in range(world):
+                want = [int(v) for v in sums[r].tolist()]
+                have = [int(pdst[r].view(torch.int64).sum()), int(gdst[r].view(torch.int64).sum()), pdst[r].shape[0], gdst[r].shape[0]]
+                if want != have:
+                    bad.append(r)
+            shards = {"ranks_checked": world, "mismatched_ranks": bad, "ok": not bad,
+                      "how": "64-bit wrap-around sum of the bit patterns of the pair and gene tables, sender vs rank 0's copy"}
     # per-kernel CUDA-event times of the last step (events recorded by the library on the same stream)
     tim = sess.timing()
     # per-kernel times: a few more steps with the kernels serialised (no overlap of the gene kernels with the probe
@@ -420,30 +505,80 @@ def main():
     value = total_pairs / (ms_per_step * 1e-3)
 
     # ---- e2e through the blocking C-ABI call with host buffers ----
-    # methylation + expression go over PCIe every step; the index (1.9 MB) is compared on the host and re-sent only if
-    # it changed, so it is not counted
-    h2d = wl["rows"] * n * 8 + G * n * 8
+    # methylation + expression + index go over PCIe every step. The reference is called once per gene range with a new
+    # annotation join every time (README.md:90), so consecutive steps alternate between two indices (the workload's, and
+    # the same one without the pairs of its last gene that has any): epx_session_set_index sees a different index on
+    # every call and rebuilds its unique-probe slots and work items inside the timed region.
+    rp_alt = idx.row_ptr.copy()
+    last = int(np.nonzero(np.diff(idx.row_ptr) > 0)[0][-1]) if Np else 0
+    if Np:
+        rp_alt[last + 1:] = rp_alt[last]
+    pi_alt = np.ascontiguousarray(idx.probe_idx[:int(rp_alt[-1])])
+    variants = [(idx.row_ptr, idx.probe_idx), (rp_alt, pi_alt)]
+    h2d = wl["rows"] * n * 8 + G * n * 8 + (G + 1) * 8 + Np * 4
     d2h = Np * (11 * 8 + 2) + G * (15 * 8 + 2)
     e2e_ms = []
     e2e_upload_ms = []
+    e2e_pairs = []
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+        rp_i, pi_i = variants[i & 1]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         sess.set_methylation(wl["meth"])
         t1 = time.perf_counter()
-        sess.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts, full=False, pinned_results=True)
+        sess.analyze(wl["expr_pinned"], rp_i, pi_i, opts, full=False, pinned_results=True)
         dt = time.perf_counter() - t0
         if i > 0:
             e2e_ms.append(dt * 1e3)
             e2e_upload_ms.append((t1 - t0) * 1e3)
+            e2e_pairs.append(int(rp_i[-1]))
     e2e_t = float(np.median(e2e_ms)) if e2e_ms else float("nan")  # median: host-side outliers (page faults, PCIe neighbours)
     if args.e2e_steps <= 0:
         e2e_t = float("nan")
+    e2e_frac = float(np.mean(e2e_pairs)) / Np if e2e_pairs and Np else 1.0   # pairs actually analysed per e2e step
     if world > 1:
         tmax = torch.tensor([e2e_t], device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_t = float(tmax.item())
-    e2e_value = total_pairs / (e2e_t * 1e-3)
+    e2e_value = total_pairs * e2e_frac / (e2e_t * 1e-3)
+
+    # ---- parity: the GPU's tables against the oracle's on the same inputs (the whole workload when the oracle does it
+    # within --cpu-seconds, else every k-th gene), through the same blocking C-ABI call ----
+    cb = parity = None
+    if not args.no_cpu_baseline and rank == 0:
+        cb = cpu_baseline(wl, args.cpu_seconds if world == 1 else min(args.cpu_seconds, 4.0), cores, keep=True)
+        sel, ptr_s, pi_s, ref = cb.pop("oracle")
+        sess.set_methylation(wl["meth"])
+        got = sess.analyze(wl["expr"][sel], ptr_s, pi_s, opts, full=True)
+        parity = parity_report(got, ref, cb["sample"].split(";")[0])
+        del got, ref
+    # the other mode of the methylation test on the same inputs (north_star: "t-test and KS modes")
+    modes = None
+    if world == 1 and not wl["w"].get("shard") and args.other_mode:
+        tm2 = not wl["w"]["tm"]
+        opts2 = _native.make_options(True, wl["w"]["te"], tm2, serialize=True)
+        sess.set_methylation(wl["meth"])
+        sess.set_expression(wl["expr"])
+        sess.set_index(idx.row_ptr, idx.probe_idx)
+        k2 = {"probe_rank_ms": 0.0, "pair_stats_ms": 0.0, "total_ms": 0.0}
+        for i in range(3 + 5):
+            sess.run(opts2, stream)
+            t = sess.timing()
+            if i >= 3:
+                for k in k2:
+                    k2[k] += t[k] / 5
+        pk = peaks()[0]
+        modes = {("tt" if tm2 else "ks"): {
+            "methylation_test": "Welch t" if tm2 else "Kolmogorov-Smirnov", "ms_per_step_serialised": round(k2["total_ms"], 4),
+            "pairs_per_s": Np / (k2["total_ms"] * 1e-3), "pair_stats_ms": round(k2["pair_stats_ms"], 4),
+            "pair_stats_frac": round(Np * (8 * n + 88) / (k2["pair_stats_ms"] * 1e-3) / 1e9 / pk, 4),
+            "probe_rank_ms": round(k2["probe_rank_ms"], 4)}}
+        if not args.no_cpu_baseline:
+            sel2, ptr2, pi2 = gene_sample(idx, G, max(1, G // 400))
+            import oracle
+            ref2 = oracle.analyze(wl["expr"][sel2], wl["meth"], ptr2, pi2, test_expr_t=wl["w"]["te"], test_meth_t=tm2, threads=cores)
+            got2 = sess.analyze(wl["expr"][sel2], ptr2, pi2, _native.make_options(True, wl["w"]["te"], tm2), full=True)
+            modes["tt" if tm2 else "ks"]["parity"] = parity_report(got2, ref2, f"{sel2.size} genes, {int(ptr2[-1])} pairs")
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -463,15 +598,13 @@ def main():
             "metric": "gene-probe pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["w"]["desc"], "name": args.workload, "pairs_per_gpu": Np, "genes": G, "samples": n,
-                       "probes": P, "unique_probes": wl["n_unique"], "methylation_rows_on_gpu": wl["rows"], "total_pairs": int(total_pairs),
-                       "l2": "inputs (%.2f GB methylation on this GPU) exceed the 126 MB L2; no flush" % (wl["rows"] * n * 8 / 1e9),
-                       "parallelism": f"genes sharded, {world} rank(s), NCCL gather of result tables" if world > 1 else "single GPU"},
+            "config": config_of(wl, args.workload, world, int(total_pairs)),
             "roofline": {"bound": "hbm", "kernel": dom[:-3], "achieved": kernels[dom[:-3]]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom[:-3]]["frac"], "traffic": traffic, "peak_source": peak_src,
                          "traffic_source": "ncu --set full, profiles/traffic_r01.json" if traffic else None},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "index_rebuilt_every_step": True,
                     "ms_per_step": e2e_t, "steps": len(e2e_ms), "ms_each": [round(v, 2) for v in e2e_ms],
                     "methylation_upload_ms": round(float(np.median(e2e_upload_ms)), 2) if e2e_upload_ms else None, "pinned_host_buffers": bool(wl["pinned"]),
                     "h2d_gbs": round(h2d / (e2e_t * 1e-3) / 1e9, 1) if e2e_t == e2e_t else None},
@@ -481,12 +614,19 @@ def main():
         }
         if pooled:
             line["pooled"] = pooled
-        if not args.no_cpu_baseline and world == 1:
-            cb = cpu_baseline(wl, args.cpu_seconds, cores)
+        if parity is not None:
+            line["parity"] = parity
+        if shards is not None:
+            line["gathered_shards"] = shards
+        if modes:
+            line["modes"] = modes
+        if cb is not None and world == 1:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        assert int(total_pairs) == wl["total_pairs"], (total_pairs, wl["total_pairs"])
         print(json.dumps(line))
     sess.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

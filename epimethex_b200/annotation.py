@@ -50,6 +50,17 @@ def _paste(a, b) -> str:
     return sa + "_" + sb
 
 
+def _strsplit(s: str) -> list:
+    """base::strsplit(s, ";") for one string: "" gives no element at all, and ONE trailing empty field is dropped
+    ("A;B;" -> A, B) while leading and inner empty fields stay (";A" -> "", A)."""
+    if s == "":
+        return []
+    parts = s.split(";")
+    if parts[-1] == "":
+        parts.pop()
+    return parts
+
+
 def explode_annotation(dfGpl):
     """R/EpimethexAnalysis.R:93-100 and :248-257. Returns parallel lists (cg, coord, gene, position, island)
     in exploded order."""
@@ -68,16 +79,17 @@ def explode_annotation(dfGpl):
     coord = df["Coordinate_36"].to_numpy(dtype=object)
     gname = df["UCSC_RefGene_Name"].astype(str).to_numpy(dtype=object)
     ggroup = df["UCSC_RefGene_Group"].astype(str).to_numpy(dtype=object)
+    # data.frame(cg = rep(ID, lengths(s)), gene = unlist(s), position = unlist(s2), ...): the gene and position columns
+    # are the two flattened lists laid side by side, so entries pair up by their place in the WHOLE frame, not per probe
     for i in range(len(df)):
-        genes = gname[i].split(";")
-        groups = ggroup[i].split(";")
-        if len(groups) != len(genes):
-            # data.frame(...) would stop with "arguments imply differing number of rows"
-            raise ValueError(f"probe {ids[i]}: {len(genes)} gene names but {len(groups)} RefGene groups")
+        genes = _strsplit(gname[i])
         island = _paste(rel[i], isl[i])
-        for g, p in zip(genes, groups):
-            cg_out.append(str(ids[i])); coord_out.append(coord[i]); gene_out.append(g)
-            pos_out.append(p); island_out.append(island)
+        for g in genes:
+            cg_out.append(str(ids[i])); coord_out.append(coord[i]); gene_out.append(g); island_out.append(island)
+        pos_out.extend(_strsplit(ggroup[i]))
+    if len(pos_out) != len(gene_out):
+        raise ValueError(f"arguments imply differing number of rows: {len(gene_out)}, {len(pos_out)} "
+                         "(UCSC_RefGene_Name and UCSC_RefGene_Group list different numbers of entries)")
     return cg_out, coord_out, gene_out, pos_out, island_out
 
 

@@ -113,6 +113,7 @@ struct epx_session {
     DevBuf<uint16_t> grp_na;
     DevBuf<int64_t> grp_dnum;
     int64_t n_groups = -1;
+    DevBuf<unsigned long long> first_bad;           /* smallest row * n + sample of an uploaded value that is NaN / infinite */
 };
 
 struct epx_multi {
@@ -245,7 +246,7 @@ void epx_session_destroy(epx_session *s)
     s->pair_dnum.release(); s->gene_dnum.release();
     s->g_desc.release(); s->g_blocks.release(); s->g_tiles.release(); s->g_pairs.release(); s->g_guard.release(); s->g_multi.release();
     s->g_val[0].release(); s->g_val[1].release(); s->g_lab[0].release(); s->g_lab[1].release();
-    s->grp.release(); s->grp_stat.release(); s->grp_na.release(); s->grp_dnum.release();
+    s->grp.release(); s->grp_stat.release(); s->grp_na.release(); s->grp_dnum.release(); s->first_bad.release();
     for (int i = 0; i < 8; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 3; i++) if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
     s->upload_stage.release();
@@ -263,6 +264,25 @@ static int check_samples(epx_session *s, int64_t n, char *err, size_t errlen)
     return EPX_OK;
 }
 
+/* the upload kernels atomicMin the position of the first non-finite value into s->first_bad */
+static cudaError_t arm_finite_check(epx_session *s, cudaStream_t st)
+{
+    cudaError_t e = s->first_bad.reserve(1);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(s->first_bad.p, 0xff, sizeof(unsigned long long), st);
+}
+/* after the stream has been synchronised: 0 when every value was finite, else EPX_EINVAL naming the first bad one */
+static int finite_check_result(epx_session *s, const char *what, const char *unit, int64_t n, char *err, size_t errlen)
+{
+    unsigned long long bad = ~0ull;
+    EPX_CUDA(cudaMemcpy(&bad, s->first_bad.p, sizeof bad, cudaMemcpyDeviceToHost));
+    if (bad == ~0ull) return EPX_OK;
+    return fail(err, errlen, EPX_EINVAL,
+                "%s %s %lld holds a NaN or an infinite value (sample %lld): drop incomplete %ss before the call, as the "
+                "reference does with na.omit (R/EpimethexAnalysis.R:114, :278)",
+                what, unit, (long long)(bad / (unsigned long long)n), (long long)(bad % (unsigned long long)n), unit);
+}
+
 int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t n_probes, int64_t n_samples,
                                      int64_t ld, char *err, size_t errlen)
 {
@@ -272,8 +292,12 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
     EPX_CUDA(cudaSetDevice(s->device));
     const int64_t dld = round_up(n_samples, 4); /* 32-byte aligned rows */
     EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
+    /* a failed upload leaves no usable matrix behind */
+    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    EPX_CUDA(arm_finite_check(s, s->stream));
     if (ld == dld) {
         EPX_CUDA(cudaMemcpyAsync(s->meth_own.p, rows, (size_t)(n_probes * dld) * 8, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(launch_check_finite(s->meth_own.p, n_probes, n_samples, dld, s->first_bad.p, s->stream));
     } else if (ld == n_samples) {
         /* contiguous host matrix: flat copies at full PCIe rate into a staging buffer, rows re-spaced on the
          * device (a 2-D copy with 3.7 KB rows runs at a fraction of the link rate) */
@@ -282,7 +306,8 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
          * chunk i+1 (main stream) */
         EPX_CUDA(s->upload_stage.reserve((size_t)(2 * chunk_rows * n_samples)));
         cudaEvent_t copied = s->ev_up[0], spaced[2] = { s->ev_up[1], s->ev_up[2] };
-        cudaError_t e = cudaSuccess;
+        cudaError_t e = cudaEventRecord(copied, s->stream); /* the side stream starts after the check word is armed */
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s->side, copied, 0);
         int64_t i = 0;
         for (int64_t r0 = 0; r0 < n_probes && e == cudaSuccess; r0 += chunk_rows, i++) {
             const int64_t nr = (n_probes - r0) < chunk_rows ? (n_probes - r0) : chunk_rows;
@@ -291,7 +316,7 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
             if (e == cudaSuccess) e = cudaMemcpyAsync(buf, rows + r0 * n_samples, (size_t)(nr * n_samples) * 8, cudaMemcpyHostToDevice, s->stream);
             if (e == cudaSuccess) e = cudaEventRecord(copied, s->stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(s->side, copied, 0);
-            if (e == cudaSuccess) e = launch_respace_rows(buf, s->meth_own.p + r0 * dld, nr, n_samples, dld, s->side);
+            if (e == cudaSuccess) e = launch_respace_rows(buf, s->meth_own.p + r0 * dld, nr, n_samples, dld, r0, s->first_bad.p, s->side);
             if (e == cudaSuccess) e = cudaEventRecord(spaced[i & 1], s->side);
         }
         cudaError_t e2 = cudaStreamSynchronize(s->side);
@@ -300,8 +325,11 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
     } else {
         EPX_CUDA(cudaMemcpy2DAsync(s->meth_own.p, (size_t)dld * 8, rows, (size_t)ld * 8, (size_t)n_samples * 8,
                                    (size_t)n_probes, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(launch_check_finite(s->meth_own.p, n_probes, n_samples, dld, s->first_bad.p, s->stream));
     }
     EPX_CUDA(cudaStreamSynchronize(s->stream));
+    rc = finite_check_result(s, "methylation", "probe", n_samples, err, errlen);
+    if (rc) return rc;
     s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
     /* the index (unique-probe slots, work items) depends on the row count only: it survives a new matrix of the
      * same shape; everything computed from the old values does not */
@@ -325,6 +353,8 @@ int epx_session_set_methylation_cols(epx_session *s, const double *const *cols, 
     if (chunk > n_samples) chunk = (int)n_samples;
     DevBuf<double> stage;
     EPX_CUDA(stage.reserve((size_t)chunk * (size_t)n_probes));
+    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    EPX_CUDA(arm_finite_check(s, s->stream));
     for (int64_t s0 = 0; s0 < n_samples; s0 += chunk) {
         const int ns = (int)((n_samples - s0) < chunk ? (n_samples - s0) : chunk);
         for (int j = 0; j < ns; j++) {
@@ -333,11 +363,13 @@ int epx_session_set_methylation_cols(epx_session *s, const double *const *cols, 
                                             cudaMemcpyHostToDevice, s->stream);
             if (e != cudaSuccess) { stage.release(); return fail(err, errlen, EPX_ECUDA, "H2D: %s", cudaGetErrorString(e)); }
         }
-        cudaError_t e = launch_transpose_cols(stage.p, s->meth_own.p, n_probes, ns, s0, dld, s->stream);
+        cudaError_t e = launch_transpose_cols(stage.p, s->meth_own.p, n_probes, ns, s0, dld, n_samples, s->first_bad.p, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e != cudaSuccess) { stage.release(); return fail(err, errlen, EPX_ECUDA, "transpose: %s", cudaGetErrorString(e)); }
     }
     stage.release();
+    rc = finite_check_result(s, "methylation", "probe", n_samples, err, errlen);
+    if (rc) return rc;
     s->meth = s->meth_own.p; s->P = n_probes; s->n_meth = n_samples; s->ld = dld;
     /* the index (unique-probe slots, work items) depends on the row count only: it survives a new matrix of the
      * same shape; everything computed from the old values does not */
@@ -354,7 +386,14 @@ int epx_session_set_methylation_device(epx_session *s, const double *d_rows, int
     if (rc) return rc;
     if ((((uintptr_t)d_rows) & 15) != 0 || (ld & 1) != 0)
         return fail(err, errlen, EPX_EINVAL, "device methylation rows must be 16-byte aligned with an even leading dimension (bulk copies)");
+    EPX_CUDA(cudaSetDevice(s->device));
     s->meth_own.release();
+    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    EPX_CUDA(arm_finite_check(s, s->stream));
+    EPX_CUDA(launch_check_finite(d_rows, n_probes, n_samples, ld, s->first_bad.p, s->stream));
+    EPX_CUDA(cudaStreamSynchronize(s->stream));
+    rc = finite_check_result(s, "methylation", "probe", n_samples, err, errlen);
+    if (rc) return rc;
     s->meth = d_rows; s->P = n_probes; s->n_meth = n_samples; s->ld = ld;
     /* the index (unique-probe slots, work items) depends on the row count only: it survives a new matrix of the
      * same shape; everything computed from the old values does not */
@@ -370,10 +409,18 @@ int epx_session_set_expression(epx_session *s, const double *expr, int64_t n_gen
     int rc = check_samples(s, n_samples, err, errlen);
     if (rc) return rc;
     EPX_CUDA(cudaSetDevice(s->device));
+    /* results, intermediates and pooled groups of the previous expression matrix are void from here on: fetch /
+     * result_device_ptr / run_pairs / run_groups answer EPX_ESTATE until the next run (their sizes follow G and n) */
+    s->prepared = false; s->ran = false; s->n_groups = -1;
+    s->G = 0; s->n = 0;
     EPX_CUDA(s->expr.reserve((size_t)(n_genes * n_samples)));
+    EPX_CUDA(arm_finite_check(s, s->stream));
     EPX_CUDA(cudaMemcpyAsync(s->expr.p, expr, (size_t)(n_genes * n_samples) * 8,
                              is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream));
+    EPX_CUDA(launch_check_finite(s->expr.p, n_genes, n_samples, n_samples, s->first_bad.p, s->stream));
     EPX_CUDA(cudaStreamSynchronize(s->stream));
+    rc = finite_check_result(s, "expression", "gene", n_samples, err, errlen);
+    if (rc) return rc;
     s->G = n_genes; s->n = n_samples;
     return EPX_OK;
 }

@@ -149,10 +149,15 @@ cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_
 cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st);
 /* dst[p*ld + s0 + j] = src[j*P + p], j < ns : sample-major chunk -> probe-major rows */
+/* every upload kernel records in *first_bad (atomicMin) the smallest row * n + sample whose value is NaN or infinite */
 cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,
-                                  cudaStream_t st);
-/* dst[r*ld + j] = src[r*n + j]: re-space contiguous rows to the padded leading dimension */
-cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, cudaStream_t st);
+                                  int64_t n_all, unsigned long long *first_bad, cudaStream_t st);
+/* dst[r*ld + j] = src[r*n + j]: re-space contiguous rows to the padded leading dimension (row0 = first row's number) */
+cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, int64_t row0,
+                                unsigned long long *first_bad, cudaStream_t st);
+/* finite test alone, for matrices that need no re-spacing */
+cudaError_t launch_check_finite(const double *a, int64_t rows, int64_t n, int64_t ld, unsigned long long *first_bad,
+                                cudaStream_t st);
 /* one-time kernel attribute setup (dynamic shared memory opt-in) */
 cudaError_t kernels_init();
 

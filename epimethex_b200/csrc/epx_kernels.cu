@@ -11,6 +11,7 @@
  *   k_pair_stats      per (gene, probe) pair: the gather (:299-302) fused with Analysis
  *                     (R/Functions.R:85-132) and corr.test (:404-417)
  */
+#include <atomic>
 #include "epx_device.cuh"
 #include "epx_internal.h"
 #include "epx_warpsort.cuh"
@@ -1271,8 +1272,17 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
 
 /* ============================================================ transpose (sample-major upload) */
 
+/* Every upload path also looks at the values it moves: a NaN (the reference drops such probes / samples with na.omit,
+ * R/EpimethexAnalysis.R:114,278) or an infinity has no place in the sort keys (key_of) or the moments, so the C ABI
+ * refuses the matrix instead of returning undefined medians. first_bad: smallest (row * n + sample) that is not finite. */
+__device__ __forceinline__ void note_nonfinite(double v, unsigned long long where, unsigned long long *first_bad)
+{
+    if ((__double2hiint(v) & 0x7ff00000) == 0x7ff00000) atomicMin(first_bad, where);
+}
+
 __global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict__ src, double *__restrict__ dst,
-                                                        int64_t P, int ns, int64_t s0, int64_t ld)
+                                                        int64_t P, int ns, int64_t s0, int64_t ld, int64_t n_all,
+                                                        unsigned long long *first_bad)
 {
     __shared__ double tile[32][33];
     const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -1281,7 +1291,11 @@ __global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict
     for (int r = ty; r < 32; r += 8) {
         int j = j0 + r;
         int64_t pp = p0 + tx;
-        if (j < ns && pp < P) tile[r][tx] = src[(int64_t)j * P + pp];
+        if (j < ns && pp < P) {
+            const double v = src[(int64_t)j * P + pp];
+            tile[r][tx] = v;
+            note_nonfinite(v, (unsigned long long)(pp * n_all + s0 + j), first_bad);
+        }
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -1292,21 +1306,43 @@ __global__ void __launch_bounds__(256) k_transpose_cols(const double *__restrict
 }
 
 __global__ void __launch_bounds__(256) k_respace_rows(const double *__restrict__ src, double *__restrict__ dst, int64_t rows,
-                                                      int n, int64_t ld)
+                                                      int n, int64_t ld, int64_t row0, unsigned long long *first_bad)
 {
     const int64_t total = rows * n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n;
-        dst[r * ld + (i - r * n)] = src[i];
+        const double v = src[i];
+        dst[r * ld + (i - r * n)] = v;
+        note_nonfinite(v, (unsigned long long)(row0 * n + i), first_bad);
+    }
+}
+
+/* the same test for matrices that arrive without a re-spacing pass (padded host rows, device pointers, expression) */
+__global__ void __launch_bounds__(256) k_check_finite(const double *__restrict__ a, int64_t rows, int n, int64_t ld,
+                                                      unsigned long long *first_bad)
+{
+    const int64_t total = rows * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n;
+        note_nonfinite(a[r * ld + (i - r * n)], (unsigned long long)i, first_bad);
     }
 }
 
 /* ============================================================ launchers */
 
-cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, cudaStream_t st)
+cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, int64_t row0,
+                                unsigned long long *first_bad, cudaStream_t st)
 {
     if (rows <= 0) return cudaSuccess;
-    k_respace_rows<<<148 * 8, 256, 0, st>>>(src, dst, rows, (int)n, ld);
+    k_respace_rows<<<148 * 8, 256, 0, st>>>(src, dst, rows, (int)n, ld, row0, first_bad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_check_finite(const double *a, int64_t rows, int64_t n, int64_t ld, unsigned long long *first_bad,
+                                cudaStream_t st)
+{
+    if (rows <= 0) return cudaSuccess;
+    k_check_finite<<<148 * 8, 256, 0, st>>>(a, rows, (int)n, ld, first_bad);
     return cudaGetLastError();
 }
 
@@ -1452,7 +1488,7 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
         return cudaGetLastError();
     }
     if (p.n > 512 && (p.ldo & 7) == 0 && ((uintptr_t)p.ord & 15) == 0) { /* two 512-value halves + one merge per warp */
-        static int per_sm2 = 0;
+        static std::atomic<int> per_sm2{0}; /* written by one host thread per device (epx_multi_*): the value is the same */
         const size_t smem = (size_t)RANK2_WARPS * RANK2_WARP_SMEM;
         if (per_sm2 == 0) {
             int nb = 0;
@@ -1469,7 +1505,7 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
     case E: {                                                                                \
         constexpr int RW = rank_warps<E>();                                                  \
         /* persistent grid of exactly one wave: a grid of 8 CTAs per SM with 3 resident ran 2.67 waves */ \
-        static int per_sm = 0;                                                               \
+        static std::atomic<int> per_sm{0};                                                   \
         if (per_sm == 0) {                                                                   \
             int nb = 0;                                                                      \
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w<E>, RW * 32, 0) != cudaSuccess || nb < 1) nb = 1; \
@@ -1560,10 +1596,10 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
 }
 
 cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,
-                                  cudaStream_t st)
+                                  int64_t n_all, unsigned long long *first_bad, cudaStream_t st)
 {
     dim3 grid((unsigned)((P + 31) / 32), (unsigned)((ns + 31) / 32));
-    k_transpose_cols<<<grid, 256, 0, st>>>(src, dst, P, ns, s0, ld);
+    k_transpose_cols<<<grid, 256, 0, st>>>(src, dst, P, ns, s0, ld, n_all, first_bad);
     return cudaGetLastError();
 }
 

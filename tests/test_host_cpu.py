@@ -69,6 +69,24 @@ def test_explode_sort_dedup_semantics():
     assert idx.island[idx.output_order].tolist()[:3] == ["N_Shore_chr1:5-9", "N_Shore_chr1:5-9", "_"]
 
 
+def test_strsplit_trailing_separator_and_frame_wide_pairing():
+    """base::strsplit drops ONE trailing empty field ("A;B;" has two elements) and data.frame(gene = unlist(s),
+    position = unlist(s2)) pairs entries by their place in the whole frame (R/EpimethexAnalysis.R:248-257)."""
+    assert annotation._strsplit("A;B;") == ["A", "B"] and annotation._strsplit(";A") == ["", "A"]
+    assert annotation._strsplit("A;;B") == ["A", "", "B"] and annotation._strsplit("") == [] and annotation._strsplit("A") == ["A"]
+    dfa = _ann([["cg1", "Island", "x", "NM;NM", "1", "5", "A;B;", "Body;TSS200;"],       # trailing ';' on both: 2 entries
+                ["cg2", "Island", "x", "NM", "1", "7", "A;", "Body"]])                    # on one only: still 1 entry
+    idx = annotation.build_probe_index(dfa, ["A", "B"], ["cg1", "cg2"])
+    rows = [(idx.cg[i], idx.position[i], ["A", "B"][idx.pair_gene[i]]) for i in idx.output_order]
+    assert rows == [("cg1", "Body", "A"), ("cg2", "Body", "A"), ("cg1", "TSS200", "B")]
+    # per-probe counts differ but the totals agree: R pairs them across probes without complaint
+    dfa = _ann([["cg1", "Island", "x", "NM", "1", "5", "A;B", "Body"], ["cg2", "Island", "x", "NM", "1", "7", "A", "TSS200;3'UTR"]])
+    cg, _, gene, pos, _ = annotation.explode_annotation(dfa)
+    assert list(zip(cg, gene, pos)) == [("cg1", "A", "Body"), ("cg1", "B", "TSS200"), ("cg2", "A", "3'UTR")]
+    with pytest.raises(ValueError, match="differing number of rows"):
+        annotation.explode_annotation(_ann([["cg1", "Island", "x", "NM", "1", "5", "A;B", "Body"]]))
+
+
 def test_numeric_coordinates_sort_numerically():
     dfa = _ann([["cg1", "Island", "x", "NM", "1", 300, "A", "Body"], ["cg2", "Island", "x", "NM", "1", 1000, "A", "Body"]])
     idx = annotation.build_probe_index(dfa, ["A"], ["cg1", "cg2"])
