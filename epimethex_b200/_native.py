@@ -320,12 +320,13 @@ class Session:
     def _alloc_result(self, full: bool, pinned: bool = False):
         Np, G, n = self.n_pairs, self.n_genes, self.n_samples
         if pinned and not full:
-            key = (Np, G)
-            if getattr(self, "_pinned_key", None) != key:
-                self._pinned = (pinned_empty((Np, PAIR_COLS)), pinned_empty((Np,), np.uint16),
-                                pinned_empty((G, GENE_COLS)), pinned_empty((G,), np.uint16))
-                self._pinned_key = key
-            pr, pn, gn, gm = self._pinned
+            cap = getattr(self, "_pinned_cap", (0, 0))
+            if Np > cap[0] or G > cap[1]:          # grow only: page-locking 40 MB costs tens of milliseconds
+                cap = (max(Np, cap[0]), max(G, cap[1]))
+                self._pinned = (pinned_empty((cap[0], PAIR_COLS)), pinned_empty((cap[0],), np.uint16),
+                                pinned_empty((cap[1], GENE_COLS)), pinned_empty((cap[1],), np.uint16))
+                self._pinned_cap = cap
+            pr, pn, gn, gm = (self._pinned[0][:Np], self._pinned[1][:Np], self._pinned[2][:G], self._pinned[3][:G])
             res = Result(pair=pr, pair_na=pn, pair_stat=np.empty((0, 3)), ks_dnum=np.empty((0, 3), np.int32), gene=gn,
                          gene_na=gm, gene_ks_dnum=np.empty((0, 3), np.int32), perm=np.empty((0, n), np.uint16))
             r = _Result()
