@@ -25,7 +25,7 @@ EXPORTS = [
     "epx_host_free", "epx_session_create", "epx_session_destroy", "epx_session_set_methylation_rows",
     "epx_session_set_methylation_cols", "epx_session_set_methylation_device", "epx_session_set_expression",
     "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
-    "epx_session_pairs_chunk", "epx_session_fetch", "epx_session_timing",
+    "epx_session_pairs_chunk", "epx_session_wait", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
     "epx_multi_set_methylation_rows", "epx_multi_set_methylation_cols", "epx_multi_set_methylation_sliced",
     "epx_multi_analyze", "epx_multi_groups", "epx_session_run_groups", "epx_session_fetch_groups",
@@ -105,6 +105,7 @@ def lib():
     L.epx_session_run_prepare.argtypes = [vp, C.POINTER(Options), vp] + e
     L.epx_session_run_pairs.argtypes = [vp, C.c_int, C.c_int, vp] + e
     L.epx_session_pairs_chunk.argtypes = [vp, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)] + e
+    L.epx_session_wait.argtypes = [vp, vp] + e
     L.epx_session_fetch.argtypes = [vp, C.POINTER(_Result), vp] + e
     L.epx_session_timing.argtypes = [vp, C.POINTER(Timing)] + e
     L.epx_session_result_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)] + e
@@ -306,6 +307,10 @@ class Session:
         first, count, b = C.c_int64(), C.c_int64(), _errbuf()
         _check(lib().epx_session_pairs_chunk(self._h, chunk, n_chunks, C.byref(first), C.byref(count), b, len(b)), b)
         return first.value, count.value
+
+    def wait(self, stream: int | None = None):
+        b = _errbuf()
+        _check(lib().epx_session_wait(self._h, C.c_void_p(stream or 0), b, len(b)), b)
 
     def timing(self) -> dict:
         t, b = Timing(), _errbuf()

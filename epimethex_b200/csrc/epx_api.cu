@@ -669,6 +669,14 @@ int epx_session_run(epx_session *s, const epx_options *opt, void *stream, char *
     return epx_session_run_pairs(s, 0, 1, stream, err, errlen);
 }
 
+int epx_session_wait(epx_session *s, void *stream, char *err, size_t errlen)
+{
+    if (!s) return fail(err, errlen, EPX_EINVAL, "session is NULL");
+    EPX_CUDA(cudaSetDevice(s->device));
+    EPX_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : s->stream));
+    return EPX_OK;
+}
+
 int epx_session_fetch(epx_session *s, epx_result *out, void *stream, char *err, size_t errlen)
 {
     if (!s || !out) return fail(err, errlen, EPX_EINVAL, "NULL argument");

@@ -163,6 +163,10 @@ int  epx_session_run_prepare(epx_session *s, const epx_options *opt, void *strea
 int  epx_session_run_pairs(epx_session *s, int chunk, int n_chunks, void *stream, char *err, size_t errlen);
 int  epx_session_pairs_chunk(epx_session *s, int chunk, int n_chunks, int64_t *first_pair, int64_t *n_pairs,
                              char *err, size_t errlen);
+/* Block until everything launched so far on `stream` (NULL = the session's own stream) has finished. For callers that
+ * cut a run into slices (run_pairs chunks) and want to look at something between them: the R shim polls
+ * R_CheckUserInterrupt() there (threading row). */
+int  epx_session_wait(epx_session *s, void *stream, char *err, size_t errlen);
 /* Wait for `stream` and copy the result tables to the host. */
 int  epx_session_fetch(epx_session *s, epx_result *out, void *stream, char *err, size_t errlen);
 /* Timing of the last run (synchronises the events). */

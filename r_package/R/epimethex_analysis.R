@@ -17,6 +17,7 @@ epimethex.analysis <- function(dfExpressions, dfGpl, dfMethylation, minRangeGene
     x <- x[, keep, drop = FALSE]; genes <- genes[keep]
     x <- x[stats::complete.cases(x), , drop = FALSE]
     samples <- rownames(x)
+    storage.mode(x) <- "double"                                  # the shim takes doubles only (integer counts arrive as INTSXP)
     # --- :93-100, :248-265, :287-291: annotation explode, keep analysed genes, order, dedup on (cg, position) ---
     dfGpl <- dfGpl[!(is.na(dfGpl$UCSC_RefGene_Name) | dfGpl$UCSC_RefGene_Name == ""), ]
     island <- paste(dfGpl$Relation_to_UCSC_CpG_Island, dfGpl$UCSC_CpG_Islands_Name, sep = "_")
