@@ -79,8 +79,10 @@ struct epx_session {
     /* per-gene and per-probe intermediates */
     DevBuf<uint16_t> perm, ord;
     DevBuf<uint8_t> lab8;
-    DevBuf<double> xc, gene_aux, lut, pt_tab;
+    DevBuf<double> xc, gene_aux, lut, pt_tab, wt_tab;
     int pt_n = 0;
+    int wt_m = -1, wt_N = 0, wt_ld = 0, wt_K = 0;   /* Welch (df, r) table of the pair kernel's t mode, built for group size wt_m */
+    double wt_df0 = 0.0, wt_ddf = 1.0;
     DevBuf<int32_t> nuniq, scal; /* scal: counts[3], ref_gene, status */
     int64_t ldl = 0, ldx = 0, ldo = 0;
     int lut_m = -1, lut_n = -1;
@@ -241,7 +243,7 @@ void epx_session_destroy(epx_session *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->meth_own.release(); s->expr.release(); s->probe_idx.release(); s->pair_slot.release();
     s->uniq_probe.release(); s->items.release(); s->pair_gene.release(); s->perm.release(); s->ord.release(); s->lab8.release();
-    s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->nuniq.release(); s->scal.release();
+    s->xc.release(); s->gene_aux.release(); s->lut.release(); s->pt_tab.release(); s->wt_tab.release(); s->nuniq.release(); s->scal.release();
     s->pair.release(); s->pair_stat.release(); s->gene.release(); s->pair_na.release(); s->gene_na.release();
     s->pair_dnum.release(); s->gene_dnum.release();
     s->g_desc.release(); s->g_blocks.release(); s->g_tiles.release(); s->g_pairs.release(); s->g_guard.release(); s->g_multi.release();
@@ -526,6 +528,32 @@ static int build_ks_lut(epx_session *s, int n, int m, cudaStream_t st, char *err
     return EPX_OK;
 }
 
+/* The Welch p-value table of the pair kernel's t mode (epx_welch_p_tab): h(r; df) on a (df, r) grid covering
+ * m - 1 <= df <= 2(m - 1), built with the same epx_math.h code the kernels use, once per group size. */
+static int build_welch_table(epx_session *s, int m, cudaStream_t st, char *err, size_t errlen)
+{
+    if (m < 30) { s->wt_m = -1; return EPX_OK; }      /* small groups keep the continued fraction */
+    if (s->wt_m == m) return EPX_OK;
+    int N, K;
+    double df0, ddf;
+    epx_welch_grid(m, &N, &K, &df0, &ddf);
+    const int ld = (N + 4) & ~3;
+    std::vector<double> tab((size_t)K * (size_t)ld, 0.0);
+    std::vector<std::thread> th;
+    const int nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    for (int w = 0; w < nt; w++)
+        th.emplace_back([&, w]() {
+            for (int k = w; k < K; k += nt)
+                for (int i = 0; i <= N; i++) tab[(size_t)k * ld + i] = epx_pearson_h((double)i / (double)N, df0 + k * ddf);
+        });
+    for (auto &t : th) t.join();
+    EPX_CUDA(s->wt_tab.reserve(tab.size()));
+    EPX_CUDA(cudaMemcpyAsync(s->wt_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, st));
+    EPX_CUDA(cudaStreamSynchronize(st));
+    s->wt_m = m; s->wt_N = N; s->wt_ld = ld; s->wt_K = K; s->wt_df0 = df0; s->wt_ddf = ddf;
+    return EPX_OK;
+}
+
 int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *stream, char *err, size_t errlen)
 {
     if (!s) return fail(err, errlen, EPX_EINVAL, "session is NULL");
@@ -563,6 +591,10 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
     EPX_CUDA(s->pair_dnum.reserve((size_t)(Np * 3)));
     int rc = build_ks_lut(s, n, m, st, err, errlen);
     if (rc) return rc;
+    if (opt.test_meth_t) {
+        rc = build_welch_table(s, m, st, err, errlen);
+        if (rc) return rc;
+    }
 
     GeneParams gp;
     gp.expr = s->expr.p; gp.n = n; gp.G = (int)G; gp.npad = next_pow2(n); gp.m = m;
@@ -588,6 +620,9 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
     pp.warp_smem = 0;
     pp.pt_tab = s->pt_tab.p; pp.pt_n = s->pt_n;
     pp.lut_exact = s->lut.p; pp.lut_asym = s->lut.p + (m + 1);
+    const bool wt = opt.test_meth_t && s->wt_m == m;
+    pp.wt_tab = wt ? s->wt_tab.p : nullptr;
+    pp.wt_N = s->wt_N; pp.wt_ld = s->wt_ld; pp.wt_K = s->wt_K; pp.wt_df0 = s->wt_df0; pp.wt_inv_ddf = 1.0 / s->wt_ddf;
     pp.pair = s->pair.p; pp.pair_na = s->pair_na.p; pp.pair_stat = s->pair_stat.p; pp.pair_dnum = s->pair_dnum.p;
 
     /* The gene-level kernels depend on the expression matrix only and the probe ranking on the methylation

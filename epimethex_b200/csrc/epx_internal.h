@@ -87,6 +87,10 @@ struct PairParams {
     unsigned warp_smem;     /* k_pair_stats2: bytes of shared memory per warp */
     const double *pt_tab;   /* [pt_n + 1] epx_pearson_h on the grid r = i / pt_n (see epx_math.h) */
     int pt_n;
+    /* t mode: Welch p-values by the (df, r) table of epx_welch_p_tab (epx_math.h); NULL = continued fraction (m < 30) */
+    const double *wt_tab;
+    int wt_N, wt_ld, wt_K;
+    double wt_df0, wt_inv_ddf;
     const double *lut_exact; /* [m+1] p-value for max|cA-cB| = d */
     const double *lut_asym;  /* [m+1] */
     double *pair;           /* [Np][11] */

@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_stats(PairParams p)
             int col = EPX_PEARSON_P;
             if (TMODE && slot < 3) {
                 const double t = s_t[jj * 3 + slot];
-                if (!isnan(t)) pq = epx_t_two_sided_p(t, s_df[jj * 3 + slot]);
+                if (!isnan(t)) pq = welch_p(p, t, s_df[jj * 3 + slot]);
                 col = EPX_P_UP_MID + slot;
             } else {
                 const double rr = s_r[jj];
@@ -1097,7 +1097,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
                         bool ok = false;
                         if (((gbits >> (2 * c)) & 3) - 1 == 1)
                             ok = epx_welch(mg[ga_[c]], vg[ga_[c]], dm, mg[gb_[c]], vg[gb_[c]], dm, &stat[c], &df) == 0;
-                        if (ok) pv[c] = epx_t_two_sided_p(stat[c], df);
+                        if (ok) pv[c] = welch_p(p, stat[c], df);
                         else { na |= 1u << (EPX_P_UP_MID + c); stat[c] = EPX_NAN; }
                     }
                 } else {

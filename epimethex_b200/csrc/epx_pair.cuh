@@ -35,6 +35,13 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr)
  * the kernel past the instruction cache */
 __device__ __noinline__ double t_two_sided_p_call(double t, double df) { return epx_t_two_sided_p(t, df); }
 
+/* Welch p-value of the t mode: the (df, r) table when the session built one (m >= 30), else the continued fraction */
+__device__ __forceinline__ double welch_p(const PairParams &p, double t, double df)
+{
+    if (p.wt_tab) return epx_welch_p_tab(t, df, p.wt_tab, p.wt_N, p.wt_ld, p.wt_K, p.wt_df0, p.wt_inv_ddf);
+    return t_two_sided_p_call(t, df);
+}
+
 constexpr int PAIR2_WARPS = 4;
 
 /* sorted walk: two running words of two biased 16-bit fields each, ra = [cUP-cMID | cUP-cDOWN],
@@ -542,7 +549,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                         const double A = s_va[jj * 3 + ga], B = s_va[jj * 3 + gb], se2 = A + B;
                         t = (s_mg[jj * 3 + ga] - s_mg[jj * 3 + gb]) / sqrt(se2);
                         const double df = se2 * se2 * (dm - 1.0) / (A * A + B * B);
-                        pq = t_two_sided_p_call(t, df);
+                        pq = welch_p(p, t, df);
                     }
                     p.pair_stat[(int64_t)(item.begin + jj) * 3 + slot] = t;
                     col = EPX_P_UP_MID + slot;

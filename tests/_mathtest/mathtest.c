@@ -14,3 +14,13 @@ int mt_welch(double mx, double vx, double nx, double my, double vy, double ny, d
 double mt_pearson_h(double r, double df) { return epx_pearson_h(r, df); }
 int mt_pearson_grid(double df) { return epx_pearson_grid(df); }
 double mt_pearson_p_tab(double r, const double *h, int N, double df) { return epx_pearson_p_tab(r, h, N, df); }
+void mt_welch_grid(int m, int *N, int *K, double *df0, double *ddf) { epx_welch_grid(m, N, K, df0, ddf); }
+double mt_welch_p_tab(double t, double df, const double *tab, int N, int ld, int K, double df0, double inv_ddf)
+{ return epx_welch_p_tab(t, df, tab, N, ld, K, df0, inv_ddf); }
+void mt_welch_table(int m, double *tab, int ld)
+{
+    int N, K; double df0, ddf;
+    epx_welch_grid(m, &N, &K, &df0, &ddf);
+    for (int k = 0; k < K; k++)
+        for (int i = 0; i <= N; i++) tab[(long long)k * ld + i] = epx_pearson_h((double)i / (double)N, df0 + k * ddf);
+}

@@ -110,7 +110,7 @@ def test_synthetic_slice_with_missing_probes_groups_and_integer_columns(tm):
 
 def test_interrupt_between_slices_of_the_pair_kernel():
     """more than 200,000 pairs: the shim cuts the pair kernel into 8 slices and polls R_CheckUserInterrupt between them"""
-    n, G, P = 30, 4000, 200000
+    n, G, P = 30, 4000, 230000
     ann = synth.annotation(P, G)
     x = synth.expression(G, n)
     y = synth.methylation(P, n, ann, threads=8)

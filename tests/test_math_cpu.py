@@ -103,3 +103,30 @@ def test_pearson_p_table_vs_mpmath(mt):
             if want > 1e-300:
                 assert abs(got - oracle.pearson_p_from_r(float(r), n)) <= 1e-10 + 1e-8 * want
         assert mt.mt_pearson_p_tab(1.0, ptr, N, df) == 0.0 and mt.mt_pearson_p_tab(-1.0, ptr, N, df) == 0.0
+
+
+def test_welch_p_table_vs_mpmath(mt):
+    """t mode of the pair kernel: p(t, df) by 4 x 4 Lagrange interpolation of the (df, r) table of h(r; df) over the
+    Welch-Satterthwaite range m - 1 <= df <= 2(m - 1); must stay far inside 1e-10 abs / 1e-8 rel everywhere"""
+    mt.mt_welch_p_tab.restype = C.c_double
+    mt.mt_welch_p_tab.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    dp = C.POINTER(C.c_double)
+    mp.mp.dps = 30
+    rng = np.random.default_rng(3)
+    for m in (30, 157, 333, 3000):
+        N, K, df0, ddf = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        mt.mt_welch_grid(m, C.byref(N), C.byref(K), C.byref(df0), C.byref(ddf))
+        ld = N.value + 1
+        tab = np.empty((K.value, ld))
+        mt.mt_welch_table(m, tab.ctypes.data_as(dp), ld)
+        assert df0.value < m - 1 and df0.value + (K.value - 2) * ddf.value >= 2 * (m - 1)
+        cases = [(0.0, m - 1.0), (1e-9, 2.0 * (m - 1)), (40.0, 1.5 * m), (-3.0, m - 1.0), (2.5, 2.0 * (m - 1))]
+        for _ in range(150):
+            cases.append((float(rng.choice([rng.normal(0, 1.5), rng.normal(0, 6), rng.random() * 0.01])), (m - 1) * (1 + rng.random())))
+        for t, df in cases:
+            want = mp.betainc(mp.mpf(df) / 2, mp.mpf(1) / 2, 0, mp.mpf(df) / (mp.mpf(df) + mp.mpf(t) ** 2), regularized=True)
+            got = mt.mt_welch_p_tab(t, df, tab.ctypes.data_as(dp), N.value, ld, K.value, df0.value, 1.0 / ddf.value)
+            assert abs(got - want) <= 0.02 * (1e-10 + 1e-8 * want), (m, t, df, got, want)
+            assert abs(got - mt.mt_t_two_sided_p(t, df)) <= 1e-10 + 1e-8 * want     # the continued fraction it replaces
+        assert mt.mt_welch_p_tab(float("inf"), 200.0, tab.ctypes.data_as(dp), N.value, ld, K.value, df0.value, 1.0 / ddf.value) == 0.0
+        assert np.isnan(mt.mt_welch_p_tab(float("nan"), 200.0, tab.ctypes.data_as(dp), N.value, ld, K.value, df0.value, 1.0 / ddf.value))
