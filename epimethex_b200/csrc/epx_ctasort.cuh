@@ -116,7 +116,7 @@ __device__ unsigned short *cta_sort_row(const double *s_val, const int n, unsign
         }
         unsigned short out[CTASORT_EPS];
         WarpSort<CTASORT_EPS>::template order<DESC>(khi, klo, nc, lane, s_b + c * CTASORT_CHUNK,
-                                           [&](int i) { return s_val[base + i]; }, (unsigned short)0xffffu, one, out);
+                                           [&](int i) { return s_val[base + i]; }, one, out);
 #pragma unroll
         for (int r = 0; r < CTASORT_EPS; r++) {
             const int k = lane * CTASORT_EPS + r;

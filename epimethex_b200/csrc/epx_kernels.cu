@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(SORT_WARPS * 32, (EPS <= 16 ? 3 : 2)) k_gene_s
         const double mean = warp_sum(sum) / (double)n;
         unsigned short out[EPS];
         WarpSort<EPS>::template order<true>(khi, klo, n, lane, s_ord[warp], [&](int i) { return __ldg(x + i); },
-                                            (unsigned short)0xffffu, p.one, out);
+                                            p.one, out);
         int ties = 0;
         uint16_t *perm = p.perm + (int64_t)g * n;
         uint8_t *lab8 = p.lab8 + (int64_t)g * p.ldl;
@@ -552,32 +552,72 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p
 
 /* k_probe_rank, one warp per referenced probe */
 template <int EPS> __host__ __device__ constexpr int rank_warps() { return SORT_WARPS; }
+/* per-warp shared memory: 2 row stages of 32*EPS doubles | 2 mbarriers | 32*EPS uint16 of sort scratch */
+template <int EPS> __host__ __device__ constexpr size_t rank_warp_smem() { return (size_t)2 * 32 * EPS * 8 + 16 + (size_t)32 * EPS * 2; }
 
 template <int EPS>
 __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k_probe_rank_w(RankParams p)
 {
     constexpr int RW = rank_warps<EPS>();
-    __shared__ unsigned short s_ord[RW][32 * EPS];
+    constexpr int N = 32 * EPS;
+    extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
+    unsigned char *base = smem + (size_t)warp * rank_warp_smem<EPS>();
+    double *stage0 = (double *)base;                         /* stage s at stage0 + s * N */
+    uint64_t *bar = (uint64_t *)(base + (size_t)2 * N * 8);
+    unsigned short *s_ord = (unsigned short *)(base + (size_t)2 * N * 8 + 16);
     const int nw = (int)gridDim.x * RW;
+    /* The row comes in as ONE bulk copy (cp.async.bulk, SASS UBLKCP) into a two-stage ring: the copy of the NEXT row is
+     * in flight while this one is sorted, the 16 loads of a lane become conflict-free LDS with immediate offsets, and
+     * the values the exact path needs (ties) are already on chip. Rows must be 16-byte aligned with a 16-byte multiple
+     * length (the session's layout: ld % 2 == 0); otherwise the lanes copy the row themselves. */
+    const bool bulk = ((((uintptr_t)p.meth) | ((uintptr_t)p.ld * 8u)) & 15u) == 0 && p.ld <= N;
+    const uint32_t rowb = (uint32_t)p.ld * 8u;
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    __syncwarp();
+    uint32_t ph0 = 0, ph1 = 0;
+    int fill = 0, use = 0;
+    auto issue = [&](int64_t slot) {
+        const double *row = p.meth + (int64_t)__ldg(p.uniq_probe + slot) * p.ld;
+        double *dst = stage0 + (fill ? N : 0);
+        if (bulk) {
+            if (lane == 0) { mbar_expect_tx(&bar[fill], rowb); bulk_g2s(dst, row, rowb, &bar[fill]); }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPS; e++) if (lane + 32 * e < n) dst[lane + 32 * e] = __ldg(row + lane + 32 * e);
+        }
+        fill ^= 1;
+    };
     /* Rows are handed out by a ticket counter: rows with tied or nearly tied values take the longer exact path, and
-     * a static split of a one-wave grid lost 6 % to that imbalance (a grid of 8 CTAs per SM, 3 resident, lost more
-     * in its partial last wave). The other warps of the SM cover the latency of the ticket. */
+     * a static split of a one-wave grid lost 6 % to that imbalance. The ticket of the row after next is drawn while
+     * this row is sorted, so neither the counter nor the copy is ever waited for. */
     int64_t slot = (int64_t)blockIdx.x * RW + warp;
+    if (slot < p.U) issue(slot);
     while (slot < p.U) {
-        const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
+        int nslot = 0;
+        if (lane == 0) nslot = nw + atomicAdd(p.queue, 1);
+        const int64_t next = __shfl_sync(FULL, nslot, 0);
+        __syncwarp(); /* every lane is done with the stage about to be refilled */
+        if (next < p.U) issue(next);
+        const double *row = stage0 + (use ? N : 0);
+        if (bulk) { if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; } }
+        else __syncwarp();
+        use ^= 1;
         unsigned khi[EPS], klo[EPS];
 #pragma unroll
-        for (int e = 0; e < EPS; e++) key_halves(__ldg(row + min(lane + 32 * e, n - 1)), khi[e], klo[e]);
+        for (int e = 0; e < EPS; e++) {
+            /* slots past the row (upper half of the slots only) take element 0: any real key of the row will do */
+            const int s = lane + 32 * e;
+            key_halves(row[(2 * e < EPS || s < n) ? s : 0], khi[e], klo[e]);
+        }
         unsigned short out[EPS];
         /* pad positions (k >= n) carry index n: the pair kernel's inert table entry */
-        WarpSort<EPS>::template order<false>(khi, klo, n, lane, s_ord[warp], [&](int i) { return __ldg(row + i); },
-                                             (unsigned short)n, p.one, out);
+        WarpSort<EPS>::template order<false>(khi, klo, n, lane, s_ord, [&](int i) { return row[i]; }, p.one, out);
         uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
         if (EPS >= 8) {
 #pragma unroll
             for (int c = 0; c < EPS / 8; c++) {
-                if (lane * EPS + c * 8 < p.ldo) {
+                if (p.ldo == N || lane * EPS + c * 8 < p.ldo) {
                     uint4 q;
                     q.x = out[c * 8 + 0] | ((unsigned)out[c * 8 + 1] << 16);
                     q.y = out[c * 8 + 2] | ((unsigned)out[c * 8 + 3] << 16);
@@ -591,9 +631,7 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
             for (int r = 0; r < EPS; r++)
                 if (lane * EPS + r < p.ldo) o[r] = out[r];
         }
-        int nslot = 0;
-        if (lane == 0) nslot = nw + atomicAdd(p.queue, 1);
-        slot = __shfl_sync(FULL, nslot, 0);
+        slot = next;
     }
     if (lane == 0) { /* the last warp to leave re-arms the queue for the next launch */
         __threadfence();
@@ -637,7 +675,7 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
             for (int e = 0; e < 16; e++) key_halves(vals[base + min(lane + 32 * e, nc - 1)], khi[e], klo[e]);
             unsigned short out[16];
             WarpSort<16>::template order<false>(khi, klo, nc, lane, scratch, [&](int i) { return vals[base + i]; },
-                                                (unsigned short)0xffffu, p.one, out);
+                                                p.one, out);
 #pragma unroll
             for (int r = 0; r < 16; r++) {
                 const int k = lane * 16 + r;
@@ -1390,6 +1428,9 @@ cudaError_t kernels_init()
 #undef EPX_PAIR2_ATTR
     if ((e = allow_max_dynamic_smem(k_group_blocksort)) != cudaSuccess) return e;
     if ((e = allow_max_dynamic_smem(k_probe_rank_w2)) != cudaSuccess) return e;
+#define EPX_RANK_ATTR(E) if ((e = allow_max_dynamic_smem(k_probe_rank_w<E>)) != cudaSuccess) return e;
+    EPX_FOR_SORT_VARIANTS(EPX_RANK_ATTR)
+#undef EPX_RANK_ATTR
     return cudaSuccess;
 }
 
@@ -1504,16 +1545,17 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
 #define EPX_CASE(E)                                                                          \
     case E: {                                                                                \
         constexpr int RW = rank_warps<E>();                                                  \
+        const size_t smem = rank_warp_smem<E>() * RW;                                        \
         /* persistent grid of exactly one wave: a grid of 8 CTAs per SM with 3 resident ran 2.67 waves */ \
         static std::atomic<int> per_sm{0};                                                   \
         if (per_sm == 0) {                                                                   \
             int nb = 0;                                                                      \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w<E>, RW * 32, 0) != cudaSuccess || nb < 1) nb = 1; \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w<E>, RW * 32, smem) != cudaSuccess || nb < 1) nb = 1; \
             per_sm = nb;                                                                     \
         }                                                                                    \
         int64_t grid = (p.U + RW - 1) / RW;                                                  \
         if (grid > (int64_t)sm_count * per_sm) grid = (int64_t)sm_count * per_sm;            \
-        k_probe_rank_w<E><<<(unsigned)grid, RW * 32, 0, st>>>(p);                            \
+        k_probe_rank_w<E><<<(unsigned)grid, RW * 32, smem, st>>>(p);                         \
         break;                                                                               \
     }
         EPX_FOR_SORT_VARIANTS(EPX_CASE)

@@ -54,12 +54,13 @@ constexpr unsigned WALK_A2 = 0xffffffffu, WALK_B2 = 0xffff0000u; /* Down:    0 -
 
 __host__ __device__ inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-/* per-warp shared memory: 2 mbarriers | 2 x (row, order) | label table | median owners [32][6] u16 (+ pad) |
- * (t-mode) Pearson r [32], group means and var/m [32][3] each, defined-test bits [32] */
+/* per-warp shared memory: 2 mbarriers | 2 x (row, order) | label table | median owners [32][6] u16 (+ pad).
+ * The t mode needs no more: the Welch t and df of a pair wait for the item's second stage in the pair's own result
+ * rows (pair_stat and the p-value columns of `pair`), so both modes keep four CTAs = 16 warps per SM. */
 __host__ __device__ inline size_t pair2_warp_smem(int n, int64_t ld, int64_t ldo, bool tmode)
 {
-    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 8) + ITEM_PAIRS * 6 * 2 + 128 +
-                   (tmode ? (size_t)ITEM_PAIRS * 8 + (size_t)ITEM_PAIRS * 6 * 8 + (size_t)ITEM_PAIRS * 4 : 0));
+    (void)tmode;
+    return round16(16 + 2 * ((size_t)ld * 8 + (size_t)ldo * 2) + round16((size_t)(n + 1) * 8) + ITEM_PAIRS * 6 * 2 + 128);
 }
 
 template <int EPL, bool TMODE>
@@ -79,10 +80,6 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
     const uint32_t tab_sa = smem_u32(tab);
     /* per pair of the item: (lane << 6 | rank inside the lane) of the lower/upper middle element of each group */
     unsigned short *s_own = (unsigned short *)((unsigned char *)tab + round16((size_t)(n + 1) * 8));
-    double *s_r = (double *)(s_own + ITEM_PAIRS * 6 + 64); /* t mode: Pearson r [ITEM_PAIRS] */
-    double *s_mg = s_r + ITEM_PAIRS;          /* t mode: group means [ITEM_PAIRS][3] */
-    double *s_va = s_mg + 3 * ITEM_PAIRS;     /* t mode: var_g / m   [ITEM_PAIRS][3] */
-    int *s_ok = (int *)(s_va + 3 * ITEM_PAIRS); /* t mode: bit c = Welch test c is defined */
 
     if (lane == 0) {
         mbar_init(&bar[0], 1);
@@ -400,9 +397,17 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 st_ks = (unsigned)d01 | ((unsigned)d02 << 9) | ((unsigned)d12 << 18) | (tiebits << 27);
             }
             if (TMODE && lane < 3) {
+                /* stats::t.test(var.equal = FALSE) of comparison `lane` (UPvsMID, UPvsDOWN, MIDvsDOWN): se^2 = vx/nx + vy/ny,
+                 * Welch-Satterthwaite df; "data are essentially constant" -> NaN. t waits in pair_stat and df in the
+                 * p-value column it belongs to; the item's second stage turns them into p-values, 32 at a time. */
                 const double sc = 1.0 / (dm * (dm - 1.0));
-                s_mg[jj * 3 + lane] = lane == 0 ? mg0 : (lane == 1 ? mg1 : mg2);
-                s_va[jj * 3 + lane] = (lane == 0 ? ss0 : (lane == 1 ? ss1 : ss2)) * sc; /* var_g / m */
+                const double ma = lane == 2 ? mg1 : mg0, mb = lane == 0 ? mg1 : mg2;
+                const double A = (lane == 2 ? ss1 : ss0) * sc, B = (lane == 0 ? ss1 : ss2) * sc, se2 = A + B;
+                const double thr = 10.0 * 2.220446049250313e-16 * fmax(fabs(ma), fabs(mb));
+                const bool ok = m >= 2 && !(se2 < thr * thr);
+                const int64_t j = (int64_t)item.begin + jj;
+                p.pair_stat[j * 3 + lane] = ok ? (ma - mb) / sqrt(se2) : EPX_NAN;
+                p.pair[j * PAIR_COLS + EPX_P_UP_MID + lane] = se2 * se2 * (dm - 1.0) / (A * A + B * B);
             }
         }
 
@@ -410,6 +415,7 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
 
         /* ---- epilogue of the item, one pair per lane: medians, guard, tests, p-values, result rows ---- */
         __syncwarp();
+        double r_keep = EPX_NAN; /* t mode: this lane's pair's Pearson r, for the second stage */
         if (lane < item.count) {
             const int64_t j = (int64_t)item.begin + lane;
             double *orow = p.pair + j * PAIR_COLS;
@@ -419,7 +425,6 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
 #pragma unroll
                 for (int c = 0; c < 3; c++) { p.pair_stat[j * 3 + c] = EPX_NAN; p.pair_dnum[j * 3 + c] = -1; }
                 p.pair_na[j] = (uint16_t)((1u << PAIR_COLS) - 1);
-                if (TMODE) { s_r[lane] = EPX_NAN; s_ok[lane] = 0; }
             } else {
                 const double *grow = p.meth + (int64_t)my_pi * p.ld;
                 const uint16_t *gord = p.ord + (int64_t)my_slot * p.ldo;
@@ -498,21 +503,15 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 orow[3] = medUP - medMID; orow[4] = medUP - medDOWN; orow[5] = medMID - medDOWN;
                 orow[9] = r;
                 if (TMODE) {
-                    /* Welch t, df and p follow in the second stage (one comparison per lane); here only what
-                     * decides NA: the guard, at least two observations, and t.test's "data are essentially constant" */
-                    const double mg[3] = { s_mg[lane * 3], s_mg[lane * 3 + 1], s_mg[lane * 3 + 2] };
-                    const double va[3] = { s_va[lane * 3], s_va[lane * 3 + 1], s_va[lane * 3 + 2] };
-                    const int ga_[3] = { 0, 0, 1 }, gb_[3] = { 1, 2, 2 };
-                    int okbits = 0;
+                    /* the Welch p-values follow in the second stage (one comparison per lane); here only what decides
+                     * NA: the guard (t.test's own stops were folded into t = NaN when it was computed) */
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        const double thr = 10.0 * 2.220446049250313e-16 * fmax(fabs(mg[ga_[c]]), fabs(mg[gb_[c]]));
-                        const bool ok = guard[c] == 1 && m >= 2 && !(va[ga_[c]] + va[gb_[c]] < thr * thr);
-                        if (ok) okbits |= 1 << c; else na |= 1u << (EPX_P_UP_MID + c);
+                        const bool ok = guard[c] == 1 && !isnan(__ldcg(p.pair_stat + j * 3 + c));
+                        if (!ok) { na |= 1u << (EPX_P_UP_MID + c); p.pair_stat[j * 3 + c] = EPX_NAN; }
                         p.pair_dnum[j * 3 + c] = -1;
                     }
-                    s_ok[lane] = okbits;
-                    s_r[lane] = r;
+                    r_keep = r;
                 } else {
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
@@ -535,29 +534,22 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
         }
 
         if (TMODE) {
-            /* ---- second stage: Student-t tails of the whole item, one per lane ---- */
+            /* ---- second stage: the p-values of the whole item, one per lane (3 Welch + 1 Pearson per pair) ---- */
             __syncwarp();
-            for (int q = lane; q < item.count * 4; q += 32) {
-                const int jj = q / 4, slot = q % 4;
-                double pq = EPX_NAN;
-                int col = EPX_PEARSON_P;
-                if (slot < 3) {
-                    /* stats::t.test(var.equal = FALSE): se^2 = vx/nx + vy/ny, Welch-Satterthwaite df */
-                    const int ga = slot == 2 ? 1 : 0, gb = slot == 0 ? 1 : 2;
-                    double t = EPX_NAN;
-                    if ((s_ok[jj] >> slot) & 1) {
-                        const double A = s_va[jj * 3 + ga], B = s_va[jj * 3 + gb], se2 = A + B;
-                        t = (s_mg[jj * 3 + ga] - s_mg[jj * 3 + gb]) / sqrt(se2);
-                        const double df = se2 * se2 * (dm - 1.0) / (A * A + B * B);
-                        pq = welch_p(p, t, df);
-                    }
-                    p.pair_stat[(int64_t)(item.begin + jj) * 3 + slot] = t;
-                    col = EPX_P_UP_MID + slot;
-                } else {
-                    const double rr = s_r[jj];
-                    if (!isnan(rr)) pq = epx_pearson_p_tab(rr, p.pt_tab, p.pt_n, dn_ - 2.0);
+            for (int q0 = 0; q0 < item.count * 4; q0 += 32) {
+                const int q = q0 + lane, jj = q >> 2, slot = q & 3;
+                const double rr = __shfl_sync(FULL, r_keep, jj & 31);
+                if (q < item.count * 4) {
+                    const int64_t j = (int64_t)item.begin + jj;
+                    double pq = EPX_NAN;
+                    int col = EPX_PEARSON_P;
+                    if (slot < 3) {
+                        col = EPX_P_UP_MID + slot;
+                        const double t = __ldcg(p.pair_stat + j * 3 + slot);
+                        if (!isnan(t)) pq = welch_p(p, t, __ldcg(p.pair + j * PAIR_COLS + col));
+                    } else if (!isnan(rr)) pq = epx_pearson_p_tab(rr, p.pt_tab, p.pt_n, dn_ - 2.0);
+                    p.pair[j * PAIR_COLS + col] = pq;
                 }
-                p.pair[(int64_t)(item.begin + jj) * PAIR_COLS + col] = pq;
             }
         }
         __syncwarp();

@@ -2,8 +2,8 @@
  * epx_warpsort.cuh — one warp orders one row (n <= 32*EPS values) entirely in registers.
  *
  * The row's doubles are mapped to order-preserving 64-bit keys, the bits all keys share are stripped,
- * and the leading (32 - IDXB) remaining bits ("coarse key") are packed above the sample index into ONE
- * 32-bit word per element.  A direction-free bitonic network then sorts the words with one VIMNMX per
+ * and the leading (31 - IDXB) remaining bits ("coarse key") are packed above the sample index, below a pad
+ * flag, into ONE 32-bit word per element.  A direction-free bitonic network then sorts the words with one VIMNMX per
  * compare-exchange half: strides below EPS stay inside a thread, larger strides are one SHFL each.
  * Only rows in which two neighbours of the sorted order share a coarse key (exact ties, or values closer
  * than ~2^-22 of the row's key range) take the exact path: an odd-even transposition on the full keys,
@@ -111,20 +111,26 @@ template <int EPS> struct WarpSort {
     }
 
     /*
-     * Orders one row. (khi[e], klo[e]) = key_halves() of the element with sample index min(lane + 32*e, n-1)
-     * (callers clamp the load index, so every slot holds a real key and nothing here needs a validity test
-     * until the words are packed). Ascending by (key, index); pass complemented halves and DESC = true for a
-     * descending order. Returns in out[r] the sample index at sorted position lane*EPS + r, with bit 15 set when
-     * the NEXT position holds an equal value (tie mark); positions >= n hold `padval`. s_ord: N uint16 of
-     * per-warp shared scratch; value(idx) returns the double of a sample (only called for positions whose
-     * neighbour shares their coarse key).
+     * Orders one row. (khi[e], klo[e]) = key_halves() of the element with sample index lane + 32*e; slots with an
+     * index >= n may hold ANY real key of the row (callers clamp the load index or substitute element 0) so that the
+     * common-prefix scan needs no validity test. Ascending by (key, index); pass complemented halves and DESC = true
+     * for a descending order. Returns in out[r] the sample index at sorted position lane*EPS + r, with bit 15 set when
+     * the NEXT position holds an equal value (tie mark); positions >= n hold n. s_ord: N uint16 of per-warp shared
+     * scratch; value(idx) returns the double of a sample (only called for positions whose neighbour shares their
+     * coarse key).
+     *
+     * Word layout: [pad flag | CB coarse-key bits | IDXB index bits]. Pads carry the flag, a running number in the
+     * coarse field and n in the index field: they sort behind every real word, no two words of a row are ever equal,
+     * and two neighbours of the sorted order share a coarse key exactly when their words differ by less than 2^IDXB
+     * ... or are one coarse step apart with a falling index, which only sends a row down the exact path for nothing.
+     * So the common case (no ties, no near-ties) is decided by ONE subtraction and half a min3 per element.
      */
     template <bool DESC, typename ValueOf>
     __device__ __forceinline__ static void order(const unsigned (&khi)[EPS], const unsigned (&klo)[EPS], const int n,
-                                                 const int lane, unsigned short *s_ord, ValueOf value,
-                                                 const unsigned short padval, const unsigned one,
+                                                 const int lane, unsigned short *s_ord, ValueOf value, const unsigned one,
                                                  unsigned short (&out)[EPS])
     {
+        constexpr unsigned CMASK = 0x7fffffffu & ~IDXM;
         /* bits shared by all keys: OR of (key ^ key0) tells where they start to differ */
         const unsigned h0 = __shfl_sync(FULL, khi[0], 0), l0 = __shfl_sync(FULL, klo[0], 0);
         unsigned dhi = 0, dlo = 0;
@@ -137,39 +143,62 @@ template <int EPS> struct WarpSort {
         dlo = __reduce_or_sync(FULL, dlo);
         const int lz = dhi ? __clz(dhi) : 32 + (dlo ? __clz(dlo) : 32); /* 64: all keys equal */
         unsigned v[EPS];
-        if (lz < 32) {
+        /* the coarse key = the CB bits from the first differing bit on, placed below the pad flag: a funnel shift by
+         * lz - 1 leaves one (common) bit on top, which the mask clears */
+        if (lz >= 1 && lz < 32) {
 #pragma unroll
-            for (int e = 0; e < EPS; e++) {
-                const int s = lane + 32 * e;
-                v[e] = s < n ? ((__funnelshift_l(klo[e], khi[e], lz) & ~IDXM) | (unsigned)s) : 0xffffffffu;
-            }
+            for (int e = 0; e < EPS; e++) v[e] = (__funnelshift_l(klo[e], khi[e], lz - 1) & CMASK) | (unsigned)(lane + 32 * e);
+        } else if (lz == 0) {
+#pragma unroll
+            for (int e = 0; e < EPS; e++) v[e] = ((khi[e] >> 1) & CMASK) | (unsigned)(lane + 32 * e);
         } else {
-            const int sh = lz - 32; /* 0..32 */
+            const int sh = lz - 33; /* -1 (lz = 32: the low word from its top bit) .. 31 */
 #pragma unroll
             for (int e = 0; e < EPS; e++) {
+                const unsigned w = sh < 0 ? (klo[e] >> 1) : (sh < 32 ? (klo[e] << sh) : 0u);
+                v[e] = (w & CMASK) | (unsigned)(lane + 32 * e);
+            }
+        }
+        /* slots past the row: normally only the upper half of the slots can be (a row uses the smallest instantiation
+         * that holds it); short chunks of the CTA-level sorts take the warp-uniform branch */
+#pragma unroll
+        for (int e = EPS / 2; e < EPS; e++) {
+            const int s = lane + 32 * e;
+            if (s >= n) v[e] = 0x80000000u | ((unsigned)(s - n) << IDXB) | (unsigned)n;
+        }
+        if (n <= 16 * EPS) {
+#pragma unroll
+            for (int e = 0; e < (EPS + 1) / 2; e++) {
                 const int s = lane + 32 * e;
-                const unsigned w = sh < 32 ? (klo[e] << sh) : 0u;
-                v[e] = s < n ? ((w & ~IDXM) | (unsigned)s) : 0xffffffffu;
+                if (s >= n) v[e] = 0x80000000u | ((unsigned)(s - n) << IDXB) | (unsigned)n;
             }
         }
         sort(v, lane, one, 0u - one);
 
+        /* smallest difference between neighbours of the sorted order */
+        unsigned nx0 = __shfl_down_sync(FULL, v[0], 1);
+        if (lane == 31) nx0 = 0xffffffffu;
+        unsigned gap = nx0 - v[EPS - 1];
+#pragma unroll
+        for (int r = 0; r + 1 < EPS; r++) gap = min(gap, v[r + 1] - v[r]);
+        if (__reduce_min_sync(FULL, gap) > IDXM) {
+#pragma unroll
+            for (int r = 0; r < EPS; r++) out[r] = (unsigned short)(v[r] & IDXM);
+            return;
+        }
+        unsigned eqm = 0;
+#pragma unroll
+        for (int r = 0; r < EPS; r++) {
+            const unsigned nxt = r + 1 < EPS ? v[r + 1] : nx0;
+            if (((v[r] ^ nxt) & ~IDXM) == 0) eqm |= 1u << r;   /* a pad never shares its upper bits with any word */
+        }
         /* Neighbours that share a coarse key are either exact ties (common: rounded or clipped data) or
          * values closer than the coarse resolution (rare). Fetch the values of just those positions:
          * equal -> tie mark (the packed index already orders ties by sample index); inverted -> the rare
          * transposition pass below. */
-        const int nv = n - lane * EPS; /* positions r < nv of this lane are real */
-        unsigned eqm = 0;
-        const unsigned nx0 = __shfl_down_sync(FULL, v[0], 1);
+        if (!__any_sync(FULL, eqm != 0)) { /* one coarse step apart with a falling index: no collision after all */
 #pragma unroll
-        for (int r = 0; r < EPS; r++) {
-            const unsigned nxt = r + 1 < EPS ? v[r + 1] : nx0;
-            if (((v[r] ^ nxt) & ~IDXM) == 0 && r + 1 < nv) eqm |= 1u << r;
-        }
-        if (lane == 31) eqm &= ~(1u << (EPS - 1));
-        if (!__any_sync(FULL, eqm != 0)) {
-#pragma unroll
-            for (int r = 0; r < EPS; r++) out[r] = r < nv ? (unsigned short)(v[r] & IDXM) : padval;
+            for (int r = 0; r < EPS; r++) out[r] = (unsigned short)(v[r] & IDXM);
             return;
         }
         {
@@ -192,7 +221,7 @@ template <int EPS> struct WarpSort {
             if (!__any_sync(FULL, bad)) {
 #pragma unroll
                 for (int r = 0; r < EPS; r++)
-                    out[r] = r < nv ? (unsigned short)((v[r] & IDXM) | (((ties >> r) & 1u) << 15)) : padval;
+                    out[r] = (unsigned short)((v[r] & IDXM) | (((ties >> r) & 1u) << 15));
                 return;
             }
         }
@@ -228,7 +257,7 @@ template <int EPS> struct WarpSort {
 #pragma unroll
         for (int r = 0; r < EPS; r++) {
             const int k = lane * EPS + r;
-            unsigned short o = padval;
+            unsigned short o = (unsigned short)n;
             if (k < n) {
                 o = s_ord[k];
                 if (((eqm >> r) & 1u) && value(o) == value(s_ord[k + 1])) o |= 0x8000u;
