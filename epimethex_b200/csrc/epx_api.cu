@@ -227,7 +227,7 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = s->scal.reserve(16);
-    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 16 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel; [8], [9]: of the rank kernel */
+    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 16 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel; [8], [9]: of the expression-row kernel; [10], [11]: of the probe-rank kernel; [12]-[13]: reference-gene maximum */
     if (e != cudaSuccess) {
         epx_session_destroy(s);
         return fail(err, errlen, EPX_ECUDA, "session setup: %s", cudaGetErrorString(e));
@@ -609,7 +609,13 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
 
     RankParams rp;
     rp.meth = s->meth; rp.ld = s->ld; rp.uniq_probe = s->uniq_probe.p; rp.U = s->U; rp.n = n; rp.npad = next_pow2(n);
-    rp.ord = s->ord.p; rp.ldo = s->ldo; rp.one = 1u; rp.queue = s->scal.p + 8;
+    rp.ord = s->ord.p; rp.ldo = s->ldo; rp.one = 1u; rp.queue = s->scal.p + 10; rp.gene_queue = s->scal.p + 8;
+    /* n <= 512: the expression rows go through the row kernel too (launch_gene_rows), whose last warp picks the
+     * bin.var reference gene */
+    const bool fuse_sort = probe_rank_takes_genes(n);
+    rp.genes = gp;
+    rp.nuniq_in = s->nuniq.p; rp.counts = tp.counts; rp.ref_gene = tp.ref_gene; rp.status = tp.status;
+    rp.best = (unsigned long long *)(s->scal.p + 12);
 
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;
@@ -634,9 +640,10 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
     EPX_CUDA(cudaEventRecord(s->ev[0], st));
     if (overlap) EPX_CUDA(cudaStreamWaitEvent(gs, s->ev[0], 0));
     EPX_CUDA(cudaEventRecord(s->ev[5], gs));
-    EPX_CUDA(launch_gene_sort(gp, s->sm_count, gs)); s->launches++;
+    if (fuse_sort) { EPX_CUDA(launch_gene_rows(rp, s->sm_count, gs)); s->launches++; } /* order + reference pick */
+    else { EPX_CUDA(launch_gene_sort(gp, s->sm_count, gs)); s->launches++; }
     EPX_CUDA(cudaEventRecord(s->ev[1], gs));
-    EPX_CUDA(launch_pick_reference(tp, gs)); s->launches++;
+    if (!fuse_sort) { EPX_CUDA(launch_pick_reference(tp, gs)); s->launches++; }
     EPX_CUDA(launch_gene_tests(tp, s->sm_count, gs)); s->launches++;
     EPX_CUDA(cudaEventRecord(s->ev[2], gs));
     EPX_CUDA(cudaEventRecord(s->ev[6], st));

@@ -61,6 +61,13 @@ struct RankParams {
     int64_t ldo;
     unsigned one;           /* = 1, opaque to the compiler (see ce_fma) */
     int32_t *queue;         /* k_probe_rank_w: {next ticket, warps done}, both 0 between launches */
+    int32_t *gene_queue;    /* the same for its expression-row instantiation (the two launches run side by side) */
+    /* k_probe_rank_w<EPS, true> (launch_gene_rows) orders the expression rows with the same loop and its last warp
+     * picks the bin.var reference gene: the gene-level work of R/EpimethexAnalysis.R:117-139 */
+    GeneParams genes;
+    const int32_t *nuniq_in; /* = genes.nuniq */
+    int32_t *counts, *ref_gene, *status;
+    unsigned long long *best;   /* max over genes of (distinct values << 32 | ~gene); 0 between launches */
 };
 
 struct PairParams {
@@ -151,7 +158,11 @@ cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
 cudaError_t launch_pick_reference(const GeneTestParams &p, cudaStream_t st);
 cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_gene_rows(const RankParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st);
+/* sample counts whose expression rows go through launch_gene_rows (else launch_gene_sort + launch_pick_reference) */
+bool probe_rank_takes_genes(int n);
+
 /* dst[p*ld + s0 + j] = src[j*P + p], j < ns : sample-major chunk -> probe-major rows */
 /* every upload kernel records in *first_bad (atomicMin) the smallest row * n + sample whose value is NaN or infinite */
 cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int ns, int64_t s0, int64_t ld,

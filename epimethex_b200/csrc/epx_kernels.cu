@@ -393,161 +393,185 @@ __global__ void __launch_bounds__(SORT_WARPS * 32, (EPS <= 16 ? 3 : 2)) k_gene_s
     }
 }
 
-/* k_gene_tests, one warp per gene: the column in the gene's descending order is staged in shared memory */
+/* k_gene_tests, one warp per gene: the column in the gene's descending order is staged in shared memory.
+ * gene_tests_row is the work of one gene.
+ * xs: 32*EPS + 2 doubles of per-warp shared memory (sorted column, later psmirnov scratch). */
 constexpr int GT_WARPS = 4;
+
+template <int EPS, bool DEFER_T>
+__device__ __noinline__ void gene_tests_row(const GeneTestParams &p, const int g, const int lane, double *xs)
+{
+    const int n = p.n;
+    const int nUP = p.counts[0], nM = p.counts[1], nD = p.counts[2];
+    const int off[3] = { 0, nUP, nUP + nM };
+    const int len[3] = { nUP, nM, nD };
+    const int ca[3] = { 0, 0, 1 }, cb[3] = { 1, 2, 2 };
+    const double *x = p.expr + (int64_t)g * n;
+    const uint16_t *perm = p.perm + (int64_t)g * n;
+    __syncwarp();
+    /* position k = lane + 32*e of the sorted column; group by position block */
+    double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int e = 0; e < EPS; e++) {
+        const int k = lane + 32 * e;
+        if (k < n) {
+            const double v = __ldg(x + perm[k]);
+            xs[k] = v;
+            if (k < off[1]) s0 += v; else if (k < off[2]) s1 += v; else s2 += v;
+        }
+    }
+    __syncwarp();
+    double mean[3], var[3];
+    mean[0] = len[0] > 0 ? warp_sum(s0) / (double)len[0] : EPX_NAN;
+    mean[1] = len[1] > 0 ? warp_sum(s1) / (double)len[1] : EPX_NAN;
+    mean[2] = len[2] > 0 ? warp_sum(s2) / (double)len[2] : EPX_NAN;
+    double q0 = 0, q1 = 0, q2 = 0;
+    int dmaxv[3] = { 0, 0, 0 }, tiev[3] = { 0, 0, 0 }, differs[3] = { 0, 0, 0 };
+#pragma unroll
+    for (int e = 0; e < EPS; e++) {
+        const int k = lane + 32 * e;
+        if (k < n) {
+            const double v = xs[k];
+            if (k < off[1]) { const double d = v - mean[0]; q0 += d * d; }
+            else if (k < off[2]) { const double d = v - mean[1]; q1 += d * d; }
+            else { const double d = v - mean[2]; q2 += d * d; }
+            if (!p.test_t) {
+                /* KS: the column is globally sorted, so counts are closed forms of the position; evaluate at
+                 * the end of every tie run of the whole column (extra thresholds cannot exceed the sup) */
+                const bool run_end = (k == n - 1) || (v != xs[k + 1]);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int la = len[ca[c]], lb = len[cb[c]], a0 = off[ca[c]], b0 = off[cb[c]];
+                    if (run_end) {
+                        const int cA = min(max(k + 1 - a0, 0), la), cB = min(max(k + 1 - b0, 0), lb);
+                        const int z = cA * lb - cB * la;
+                        dmaxv[c] = max(dmaxv[c], z < 0 ? -z : z);
+                    } else {
+                        const bool in_i = (k >= a0 && k < a0 + la) || (k >= b0 && k < b0 + lb);
+                        const bool in_n = (k + 1 >= a0 && k + 1 < a0 + la) || (k + 1 >= b0 && k + 1 < b0 + lb);
+                        if (in_i && in_n) tiev[c] = 1;
+                    }
+                }
+            }
+        }
+    }
+    var[0] = len[0] > 1 ? warp_sum(q0) / (double)(len[0] - 1) : EPX_NAN;
+    var[1] = len[1] > 1 ? warp_sum(q1) / (double)(len[1] - 1) : EPX_NAN;
+    var[2] = len[2] > 1 ? warp_sum(q2) / (double)(len[2] - 1) : EPX_NAN;
+    /* guard, R/Functions.R:193: sd(mapply('-', a, b)) with recycling of the shorter argument */
+    int guard[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int la = len[ca[c]], lb = len[cb[c]];
+        const double *A = xs + off[ca[c]], *B = xs + off[cb[c]];
+        const int L = la > lb ? la : lb;
+        if (la > 0 && lb > 0 && L >= 2) {
+            const double d0 = A[0] - B[0];
+            if (la == lb) {
+                for (int i = 1 + lane; i < L; i += 32)
+                    if (A[i] - B[i] != d0) differs[c] = 1;
+            } else {
+                for (int i = 1 + lane; i < L; i += 32)
+                    if (A[i % la] - B[i % lb] != d0) differs[c] = 1;
+            }
+        }
+        guard[c] = (la == 0 || lb == 0 || L < 2) ? -1 : (__any_sync(FULL, differs[c]) ? 1 : 0);
+    }
+    if (!p.test_t) {
+        /* UP vs D with the whole M block tied to both neighbours */
+        if (lane == 0 && nM > 0 && nUP > 0 && nD > 0 && xs[off[1] - 1] == xs[off[2]]) tiev[1] = 1;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { dmaxv[c] = warp_max_i(dmaxv[c]); tiev[c] = __any_sync(FULL, tiev[c]); }
+    }
+    __syncwarp(); /* all reads of xs are done: lane 0 may reuse it as psmirnov scratch */
+    if (lane == 0) {
+        double *o = p.gene + (int64_t)g * GENE_COLS;
+        /* from the staged sorted column: the global x[perm[.]] form is six dependent DRAM round trips on one lane */
+        const double q33 = quantile7_desc(xs, n, 0.33), q66 = quantile7_desc(xs, n, 0.66),
+                     q99 = quantile7_desc(xs, n, 0.99);
+        /* calcFC reads the last three rows = perc99/perc66/perc33 (reference quirk) */
+        const double fu = p.fc_from_means ? mean[0] : q99, fm = p.fc_from_means ? mean[1] : q66,
+                     fd = p.fc_from_means ? mean[2] : q33;
+        if (p.data_linear) { o[0] = epx_linear_fc(fu, fm); o[1] = epx_linear_fc(fu, fd); o[2] = epx_linear_fc(fm, fd); }
+        else { o[0] = epx_log_fc(fu, fm); o[1] = epx_log_fc(fu, fd); o[2] = epx_log_fc(fm, fd); }
+        o[9] = q33; o[10] = q66; o[11] = q99;
+        o[12] = mean[2]; o[13] = mean[1]; o[14] = mean[0];
+    }
+    /* the three p-values on three lanes at once */
+    uint16_t na = 0;
+    if (lane < 3) {
+        const int c = lane;
+        const int la = len[ca[c]], lb = len[cb[c]];
+        double stat = EPX_NAN, pv = EPX_NAN;
+        int dn = -1;
+        bool ok = false;
+        const int gd = c == 0 ? guard[0] : (c == 1 ? guard[1] : guard[2]);
+        if (p.test_t) {
+            if (gd == 1) {
+                double t, df;
+                const double ma = c == 2 ? mean[1] : mean[0], va = c == 2 ? var[1] : var[0];
+                const double mb = c == 0 ? mean[1] : mean[2], vb = c == 0 ? var[1] : var[2];
+                if (epx_welch(ma, va, (double)la, mb, vb, (double)lb, &t, &df) == 0) {
+                    /* DEFER_T: the caller turns (t, df) into the p-value later, one test per lane for a block of genes
+                     * (the continued fraction is a long dependent chain: three lanes of a warp per gene left it to
+                     * latency); df waits in the p-value's own cell */
+                    stat = t; pv = DEFER_T ? df : epx_t_two_sided_p(t, df); ok = true;
+                }
+            }
+        } else if (gd != 0 && la > 0 && lb > 0) {
+            dn = c == 0 ? dmaxv[0] : (c == 1 ? dmaxv[1] : dmaxv[2]);
+            const int tv = c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]);
+            stat = (double)dn / ((double)la * (double)lb);
+            ok = true;
+            if ((double)la * (double)lb < 10000.0 && !tv) pv = EPX_NAN; /* exact: done serially below */
+            else pv = epx_ks_p_asym((double)dn, (double)la, (double)lb);
+        }
+        double *o = p.gene + (int64_t)g * GENE_COLS;
+        const bool exact_pending = !p.test_t && ok && (double)la * (double)lb < 10000.0 &&
+                                   !(c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]));
+        if (!exact_pending) o[3 + c] = pv; /* otherwise lane 0 writes it below */
+        o[6 + c] = stat;
+        p.gene_dnum[(int64_t)g * 3 + c] = dn;
+        if (!ok) na = (uint16_t)((1u << (3 + c)) | (1u << (6 + c)));
+    }
+    if (!p.test_t) {
+        /* exact KS p-values (small groups, no pooled ties): psmirnov2x needs the shared scratch -> serial */
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int la = len[ca[c]], lb = len[cb[c]];
+            if (guard[c] != 0 && la > 0 && lb > 0 && (double)la * (double)lb < 10000.0 && !tiev[c]) {
+                if (lane == 0) p.gene[(int64_t)g * GENE_COLS + 3 + c] = epx_ks_p_exact((double)dmaxv[c], la, lb, xs);
+            }
+        }
+    }
+    na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 1);
+    na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 2);
+    if (lane == 0) p.gene_na[g] = na;
+}
 
 template <int EPS>
 __global__ void __launch_bounds__(GT_WARPS * 32) k_gene_tests_w(GeneTestParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     if (*p.status != ST_OK) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
-    double *xs = (double *)smem + (size_t)warp * (32 * EPS + 2); /* sorted descending; later psmirnov scratch */
-    const int nUP = p.counts[0], nM = p.counts[1], nD = p.counts[2];
-    const int off[3] = { 0, nUP, nUP + nM };
-    const int len[3] = { nUP, nM, nD };
-    const int ca[3] = { 0, 0, 1 }, cb[3] = { 1, 2, 2 };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *xs = (double *)smem + (size_t)warp * (32 * EPS + 2);
     const int nw = gridDim.x * GT_WARPS;
-    for (int g = blockIdx.x * GT_WARPS + warp; g < p.G; g += nw) {
-        const double *x = p.expr + (int64_t)g * n;
-        const uint16_t *perm = p.perm + (int64_t)g * n;
-        __syncwarp();
-        /* position k = lane + 32*e of the sorted column; group by position block */
-        double s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-        for (int e = 0; e < EPS; e++) {
-            const int k = lane + 32 * e;
-            if (k < n) {
-                const double v = __ldg(x + perm[k]);
-                xs[k] = v;
-                if (k < off[1]) s0 += v; else if (k < off[2]) s1 += v; else s2 += v;
-            }
-        }
-        __syncwarp();
-        double mean[3], var[3];
-        mean[0] = len[0] > 0 ? warp_sum(s0) / (double)len[0] : EPX_NAN;
-        mean[1] = len[1] > 0 ? warp_sum(s1) / (double)len[1] : EPX_NAN;
-        mean[2] = len[2] > 0 ? warp_sum(s2) / (double)len[2] : EPX_NAN;
-        double q0 = 0, q1 = 0, q2 = 0;
-        int dmaxv[3] = { 0, 0, 0 }, tiev[3] = { 0, 0, 0 }, differs[3] = { 0, 0, 0 };
-#pragma unroll
-        for (int e = 0; e < EPS; e++) {
-            const int k = lane + 32 * e;
-            if (k < n) {
-                const double v = xs[k];
-                if (k < off[1]) { const double d = v - mean[0]; q0 += d * d; }
-                else if (k < off[2]) { const double d = v - mean[1]; q1 += d * d; }
-                else { const double d = v - mean[2]; q2 += d * d; }
-                if (!p.test_t) {
-                    /* KS: the column is globally sorted, so counts are closed forms of the position; evaluate at
-                     * the end of every tie run of the whole column (extra thresholds cannot exceed the sup) */
-                    const bool run_end = (k == n - 1) || (v != xs[k + 1]);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const int la = len[ca[c]], lb = len[cb[c]], a0 = off[ca[c]], b0 = off[cb[c]];
-                        if (run_end) {
-                            const int cA = min(max(k + 1 - a0, 0), la), cB = min(max(k + 1 - b0, 0), lb);
-                            const int z = cA * lb - cB * la;
-                            dmaxv[c] = max(dmaxv[c], z < 0 ? -z : z);
-                        } else {
-                            const bool in_i = (k >= a0 && k < a0 + la) || (k >= b0 && k < b0 + lb);
-                            const bool in_n = (k + 1 >= a0 && k + 1 < a0 + la) || (k + 1 >= b0 && k + 1 < b0 + lb);
-                            if (in_i && in_n) tiev[c] = 1;
-                        }
-                    }
-                }
-            }
-        }
-        var[0] = len[0] > 1 ? warp_sum(q0) / (double)(len[0] - 1) : EPX_NAN;
-        var[1] = len[1] > 1 ? warp_sum(q1) / (double)(len[1] - 1) : EPX_NAN;
-        var[2] = len[2] > 1 ? warp_sum(q2) / (double)(len[2] - 1) : EPX_NAN;
-        /* guard, R/Functions.R:193: sd(mapply('-', a, b)) with recycling of the shorter argument */
-        int guard[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const int la = len[ca[c]], lb = len[cb[c]];
-            const double *A = xs + off[ca[c]], *B = xs + off[cb[c]];
-            const int L = la > lb ? la : lb;
-            if (la > 0 && lb > 0 && L >= 2) {
-                const double d0 = A[0] - B[0];
-                if (la == lb) {
-                    for (int i = 1 + lane; i < L; i += 32)
-                        if (A[i] - B[i] != d0) differs[c] = 1;
-                } else {
-                    for (int i = 1 + lane; i < L; i += 32)
-                        if (A[i % la] - B[i % lb] != d0) differs[c] = 1;
-                }
-            }
-            guard[c] = (la == 0 || lb == 0 || L < 2) ? -1 : (__any_sync(FULL, differs[c]) ? 1 : 0);
-        }
-        if (!p.test_t) {
-            /* UP vs D with the whole M block tied to both neighbours */
-            if (lane == 0 && nM > 0 && nUP > 0 && nD > 0 && xs[off[1] - 1] == xs[off[2]]) tiev[1] = 1;
-#pragma unroll
-            for (int c = 0; c < 3; c++) { dmaxv[c] = warp_max_i(dmaxv[c]); tiev[c] = __any_sync(FULL, tiev[c]); }
-        }
-        __syncwarp(); /* all reads of xs are done: lane 0 may reuse it as psmirnov scratch */
-        if (lane == 0) {
-            double *o = p.gene + (int64_t)g * GENE_COLS;
-            /* from the staged sorted column: the global x[perm[.]] form is six dependent DRAM round trips on one lane */
-            const double q33 = quantile7_desc(xs, n, 0.33), q66 = quantile7_desc(xs, n, 0.66),
-                         q99 = quantile7_desc(xs, n, 0.99);
-            /* calcFC reads the last three rows = perc99/perc66/perc33 (reference quirk) */
-            const double fu = p.fc_from_means ? mean[0] : q99, fm = p.fc_from_means ? mean[1] : q66,
-                         fd = p.fc_from_means ? mean[2] : q33;
-            if (p.data_linear) { o[0] = epx_linear_fc(fu, fm); o[1] = epx_linear_fc(fu, fd); o[2] = epx_linear_fc(fm, fd); }
-            else { o[0] = epx_log_fc(fu, fm); o[1] = epx_log_fc(fu, fd); o[2] = epx_log_fc(fm, fd); }
-            o[9] = q33; o[10] = q66; o[11] = q99;
-            o[12] = mean[2]; o[13] = mean[1]; o[14] = mean[0];
-        }
-        /* the three p-values on three lanes at once */
-        uint16_t na = 0;
-        if (lane < 3) {
-            const int c = lane;
-            const int la = len[ca[c]], lb = len[cb[c]];
-            double stat = EPX_NAN, pv = EPX_NAN;
-            int dn = -1;
-            bool ok = false;
-            const int gd = c == 0 ? guard[0] : (c == 1 ? guard[1] : guard[2]);
-            if (p.test_t) {
-                if (gd == 1) {
-                    double t, df;
-                    const double ma = c == 2 ? mean[1] : mean[0], va = c == 2 ? var[1] : var[0];
-                    const double mb = c == 0 ? mean[1] : mean[2], vb = c == 0 ? var[1] : var[2];
-                    if (epx_welch(ma, va, (double)la, mb, vb, (double)lb, &t, &df) == 0) {
-                        stat = t; pv = epx_t_two_sided_p(t, df); ok = true;
-                    }
-                }
-            } else if (gd != 0 && la > 0 && lb > 0) {
-                dn = c == 0 ? dmaxv[0] : (c == 1 ? dmaxv[1] : dmaxv[2]);
-                const int tv = c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]);
-                stat = (double)dn / ((double)la * (double)lb);
-                ok = true;
-                if ((double)la * (double)lb < 10000.0 && !tv) pv = EPX_NAN; /* exact: done serially below */
-                else pv = epx_ks_p_asym((double)dn, (double)la, (double)lb);
-            }
-            double *o = p.gene + (int64_t)g * GENE_COLS;
-            const bool exact_pending = !p.test_t && ok && (double)la * (double)lb < 10000.0 &&
-                                       !(c == 0 ? tiev[0] : (c == 1 ? tiev[1] : tiev[2]));
-            if (!exact_pending) o[3 + c] = pv; /* otherwise lane 0 writes it below */
-            o[6 + c] = stat;
-            p.gene_dnum[(int64_t)g * 3 + c] = dn;
-            if (!ok) na = (uint16_t)((1u << (3 + c)) | (1u << (6 + c)));
-        }
-        if (!p.test_t) {
-            /* exact KS p-values (small groups, no pooled ties): psmirnov2x needs the shared scratch -> serial */
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const int la = len[ca[c]], lb = len[cb[c]];
-                if (guard[c] != 0 && la > 0 && lb > 0 && (double)la * (double)lb < 10000.0 && !tiev[c]) {
-                    if (lane == 0) p.gene[(int64_t)g * GENE_COLS + 3 + c] = epx_ks_p_exact((double)dmaxv[c], la, lb, xs);
-                }
-            }
-        }
-        na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 1);
-        na |= (uint16_t)__shfl_xor_sync(FULL, (int)na, 2);
-        if (lane == 0) p.gene_na[g] = na;
-    }
+    for (int g = blockIdx.x * GT_WARPS + warp; g < p.G; g += nw) gene_tests_row<EPS, true>(p, g, lane, xs);
+}
+
+/* the Student-t tails k_gene_tests_w left behind as (t in the statistic column, df in the p-value column): one test per
+ * THREAD. The continued fraction is a long dependent chain; on three lanes of a warp per gene it left the kernel to
+ * latency (0.18 ms for 20 k genes), here 3 G of them run side by side. */
+__global__ void __launch_bounds__(128) k_gene_tails(GeneTestParams p)
+{
+    if (*p.status != ST_OK) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 3 * p.G) return;
+    double *o = p.gene + (int64_t)(q / 3) * GENE_COLS;
+    const int c = q % 3;
+    const double t = o[EPX_G_STAT_UP_MID + c];
+    if (!isnan(t)) o[EPX_G_P_UP_MID + c] = epx_t_two_sided_p(t, o[EPX_G_P_UP_MID + c]);
 }
 
 /* k_probe_rank, one warp per referenced probe */
@@ -555,7 +579,55 @@ template <int EPS> __host__ __device__ constexpr int rank_warps() { return SORT_
 /* per-warp shared memory: 2 row stages of 32*EPS doubles | 2 mbarriers | 32*EPS uint16 of sort scratch */
 template <int EPS> __host__ __device__ constexpr size_t rank_warp_smem() { return (size_t)2 * 32 * EPS * 8 + 16 + (size_t)32 * EPS * 2; }
 
-template <int EPS>
+/* the bin.var reference gene and its group sizes (R/EpimethexAnalysis.R:134-139), by ONE warp: the last warp to leave
+ * k_probe_rank_w, which by then sees the order and the distinct-value count of every gene (same result as
+ * k_pick_reference, which the other sample-count ranges still launch) */
+__device__ __noinline__ void pick_reference_warp(const RankParams &p, const int lane)
+{
+    const GeneParams &gp = p.genes;
+    const int n = gp.n;
+    /* which.max(#distinct values): every gene row left (count << 32 | ~gene) in *p.best with an atomicMax, so the
+     * first gene with the largest count is one load away (a scan of 20 k counts by one warp cost 0.2 ms of tail) */
+    const unsigned long long key = __ldcg(p.best);
+    const int ref = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+    if (lane == 0) *p.best = 0ull; /* re-armed for the next launch */
+    const double *x = gp.expr + (int64_t)ref * n;
+    const uint16_t *perm = gp.perm + (int64_t)ref * n;
+    /* bin.var: cut(x, quantile(x, seq(0,1,1/3)), include.lowest=TRUE); type 7 on the ascending order, whose element k
+     * is x[perm[n-1-k]] */
+    double b[4] = { 0, 0, 0, 0 };
+    if (lane < 4) {
+        const double third = 1.0 / 3.0;
+        const double prob = lane == 0 ? 0.0 : (lane == 1 ? third : (lane == 2 ? 2.0 * third : 1.0));
+        const double index = 1.0 + (double)(n - 1) * prob;
+        const double lo = floor(index), hi = ceil(index);
+        double qs = x[__ldcg(perm + n - (int)lo)];
+        const double xh = x[__ldcg(perm + n - (int)hi)];
+        if (index > lo && xh != qs) { const double h = index - lo; qs = (1.0 - h) * qs + h * xh; }
+        b[0] = qs;
+    }
+    b[3] = __shfl_sync(FULL, b[0], 3); b[2] = __shfl_sync(FULL, b[0], 2); b[1] = __shfl_sync(FULL, b[0], 1);
+    b[0] = __shfl_sync(FULL, b[0], 0);
+    int nup = 0, nm = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double v = x[i];
+        if (v > b[2]) nup++;
+        else if (v > b[1]) nm++;
+    }
+    nup = __reduce_add_sync(FULL, nup);
+    nm = __reduce_add_sync(FULL, nm);
+    if (lane == 0) {
+        p.counts[0] = nup; p.counts[1] = nm; p.counts[2] = n - nup - nm;
+        *p.ref_gene = ref;
+        *p.status = (b[0] < b[1] && b[1] < b[2] && b[2] < b[3]) ? ST_OK : ST_BREAKS_NOT_UNIQUE;
+    }
+}
+
+/* GENES = false: the referenced methylation rows, ascending (the order rows of the pair kernel). GENES = true: the
+ * expression rows, descending, with everything k_gene_sort_w wrote, and the last warp picks the bin.var reference gene.
+ * Two instantiations of one loop rather than one kernel for both: with both row kinds in one kernel its code outgrew
+ * the instruction cache and every row paid for it (measured: 0.93 -> 1.15 ms). */
+template <int EPS, bool GENES>
 __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k_probe_rank_w(RankParams p)
 {
     constexpr int RW = rank_warps<EPS>();
@@ -567,75 +639,147 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
     uint64_t *bar = (uint64_t *)(base + (size_t)2 * N * 8);
     unsigned short *s_ord = (unsigned short *)(base + (size_t)2 * N * 8 + 16);
     const int nw = (int)gridDim.x * RW;
+    const int64_t G = GENES ? p.genes.G : 0, total = GENES ? G : p.U;
+    int32_t *const queue = GENES ? p.gene_queue : p.queue;
     /* The row comes in as ONE bulk copy (cp.async.bulk, SASS UBLKCP) into a two-stage ring: the copy of the NEXT row is
      * in flight while this one is sorted, the 16 loads of a lane become conflict-free LDS with immediate offsets, and
      * the values the exact path needs (ties) are already on chip. Rows must be 16-byte aligned with a 16-byte multiple
-     * length (the session's layout: ld % 2 == 0); otherwise the lanes copy the row themselves. */
-    const bool bulk = ((((uintptr_t)p.meth) | ((uintptr_t)p.ld * 8u)) & 15u) == 0 && p.ld <= N;
+     * length (the session's methylation layout: ld % 2 == 0); expression rows (n doubles apart: not aligned when n is
+     * odd) and unaligned borrowed matrices are copied by the lanes. */
+    const bool bulk = !GENES && ((((uintptr_t)p.meth) | ((uintptr_t)p.ld * 8u)) & 15u) == 0 && p.ld <= N;
     const uint32_t rowb = (uint32_t)p.ld * 8u;
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
     __syncwarp();
     uint32_t ph0 = 0, ph1 = 0;
     int fill = 0, use = 0;
+    unsigned by_bulk = 0;    /* bit s: stage s was filled by a bulk copy (its mbarrier has to be waited for) */
     auto issue = [&](int64_t slot) {
-        const double *row = p.meth + (int64_t)__ldg(p.uniq_probe + slot) * p.ld;
         double *dst = stage0 + (fill ? N : 0);
-        if (bulk) {
+        if (!GENES && bulk) {
+            const double *row = p.meth + (int64_t)__ldg(p.uniq_probe + slot) * p.ld;
             if (lane == 0) { mbar_expect_tx(&bar[fill], rowb); bulk_g2s(dst, row, rowb, &bar[fill]); }
+            by_bulk |= 1u << fill;
         } else {
+            const double *row = GENES ? p.genes.expr + slot * n : p.meth + (int64_t)__ldg(p.uniq_probe + slot) * p.ld;
 #pragma unroll
             for (int e = 0; e < EPS; e++) if (lane + 32 * e < n) dst[lane + 32 * e] = __ldg(row + lane + 32 * e);
+            by_bulk &= ~(1u << fill);
         }
         fill ^= 1;
     };
-    /* Rows are handed out by a ticket counter: rows with tied or nearly tied values take the longer exact path, and
-     * a static split of a one-wave grid lost 6 % to that imbalance. The ticket of the row after next is drawn while
-     * this row is sorted, so neither the counter nor the copy is ever waited for. */
+    /* Rows are handed out by a ticket counter (tickets 0 .. G-1: expression rows, then the referenced probes): rows
+     * with tied or nearly tied values take the longer exact path, and a static split of a one-wave grid lost 6 % to
+     * that imbalance. The ticket of the row after next is drawn while this row is sorted, so neither the counter
+     * nor the copy is ever waited for. */
     int64_t slot = (int64_t)blockIdx.x * RW + warp;
-    if (slot < p.U) issue(slot);
-    while (slot < p.U) {
+    if (slot < total) issue(slot);
+    while (slot < total) {
         int nslot = 0;
-        if (lane == 0) nslot = nw + atomicAdd(p.queue, 1);
+        if (lane == 0) nslot = nw + atomicAdd(queue, 1);
         const int64_t next = __shfl_sync(FULL, nslot, 0);
         __syncwarp(); /* every lane is done with the stage about to be refilled */
-        if (next < p.U) issue(next);
+        if (next < total) issue(next);
         const double *row = stage0 + (use ? N : 0);
-        if (bulk) { if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; } }
+        if ((by_bulk >> use) & 1u) { if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; } }
         else __syncwarp();
         use ^= 1;
+        constexpr bool gene = GENES; /* descending order for expression rows (R/EpimethexAnalysis.R:117-122) */
         unsigned khi[EPS], klo[EPS];
+        if (!gene) {
 #pragma unroll
-        for (int e = 0; e < EPS; e++) {
-            /* slots past the row (upper half of the slots only) take element 0: any real key of the row will do */
-            const int s = lane + 32 * e;
-            key_halves(row[(2 * e < EPS || s < n) ? s : 0], khi[e], klo[e]);
-        }
-        unsigned short out[EPS];
-        /* pad positions (k >= n) carry index n: the pair kernel's inert table entry */
-        WarpSort<EPS>::template order<false>(khi, klo, n, lane, s_ord, [&](int i) { return row[i]; }, p.one, out);
-        uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
-        if (EPS >= 8) {
-#pragma unroll
-            for (int c = 0; c < EPS / 8; c++) {
-                if (p.ldo == N || lane * EPS + c * 8 < p.ldo) {
-                    uint4 q;
-                    q.x = out[c * 8 + 0] | ((unsigned)out[c * 8 + 1] << 16);
-                    q.y = out[c * 8 + 2] | ((unsigned)out[c * 8 + 3] << 16);
-                    q.z = out[c * 8 + 4] | ((unsigned)out[c * 8 + 5] << 16);
-                    q.w = out[c * 8 + 6] | ((unsigned)out[c * 8 + 7] << 16);
-                    *reinterpret_cast<uint4 *>(o + c * 8) = q;
-                }
+            for (int e = 0; e < EPS; e++) {
+                /* slots past the row (upper half of the slots only) take element 0: any real key of the row will do */
+                const int s = lane + 32 * e;
+                key_halves(row[(2 * e < EPS || s < n) ? s : 0], khi[e], klo[e]);
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < EPS; r++)
-                if (lane * EPS + r < p.ldo) o[r] = out[r];
+            for (int e = 0; e < EPS; e++) {
+                const int s = lane + 32 * e;
+                key_halves(row[(2 * e < EPS || s < n) ? s : 0], khi[e], klo[e]);
+                khi[e] = ~khi[e]; klo[e] = ~klo[e];
+            }
+        }
+        unsigned short out[EPS];
+        /* pad positions (k >= n) carry index n: the pair kernel's inert table entry */
+        WarpSort<EPS>::template order<GENES>(khi, klo, n, lane, s_ord, [&](int i) { return row[i]; }, p.one, out);
+        if (!gene) {
+            uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
+            if (EPS >= 8) {
+#pragma unroll
+                for (int c = 0; c < EPS / 8; c++) {
+                    if (p.ldo == N || lane * EPS + c * 8 < p.ldo) {
+                        uint4 q;
+                        q.x = out[c * 8 + 0] | ((unsigned)out[c * 8 + 1] << 16);
+                        q.y = out[c * 8 + 2] | ((unsigned)out[c * 8 + 3] << 16);
+                        q.z = out[c * 8 + 4] | ((unsigned)out[c * 8 + 5] << 16);
+                        q.w = out[c * 8 + 6] | ((unsigned)out[c * 8 + 7] << 16);
+                        *reinterpret_cast<uint4 *>(o + c * 8) = q;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < EPS; r++)
+                    if (lane * EPS + r < p.ldo) o[r] = out[r];
+            }
+        } else {
+            /* what k_gene_sort_w writes: the order, the methylation-side labels by rank (:323-325), the centred row and
+             * its sums for Pearson (:404-417), the distinct-value count for the reference pick */
+            const GeneParams &gp = p.genes;
+            const int64_t g = slot;
+            const int m1 = gp.m, m2 = 2 * gp.m, m3 = 3 * gp.m;
+            int ties = 0;
+            uint16_t *perm = gp.perm + g * n;
+            uint8_t *lab8 = gp.lab8 + g * gp.ldl;
+            double sum = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPS; e++) { const int s = lane + 32 * e; if (s < n) sum += row[s]; }
+#pragma unroll
+            for (int r = 0; r < EPS; r++) {
+                const int k = lane * EPS + r;
+                if (k < n) {
+                    const int s = out[r] & 0x7fff;
+                    ties += (out[r] >> 15) & 1;
+                    perm[k] = (uint16_t)s;
+                    lab8[s] = (uint8_t)((k >= m1) + (k >= m2) + (k >= m3)); /* = min(k / m, 3); m = 0 only for n < 3 (refused) */
+                }
+            }
+            ties = __reduce_add_sync(FULL, ties);
+            const double mean = warp_sum(sum) / (double)n;
+            double sxx = 0.0, sxc = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPS; e++) {
+                const int s = lane + 32 * e;
+                if (s < n) {
+                    const double d = row[s] - mean;
+                    gp.xc[g * gp.ldx + s] = d;
+                    sxx += d * d;
+                    sxc += d;
+                }
+            }
+            sxx = warp_sum(sxx);
+            sxc = warp_sum(sxc);
+            if (lane == 0) {
+                const int u = n - ties;
+                gp.nuniq[g] = u;
+                atomicMax(p.best, ((unsigned long long)(unsigned)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)g));
+                double *ga = gp.gene_aux + 4 * g;
+                ga[0] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
+                ga[1] = mean; ga[2] = sxc; ga[3] = (u == 1 || sxx == 0.0) ? 0.0 : rsqrt(sxx);
+            }
         }
         slot = next;
     }
-    if (lane == 0) { /* the last warp to leave re-arms the queue for the next launch */
+    /* the last warp to leave re-arms the queue for the next launch and, with every gene ordered, picks the reference */
+    int last = 0;
+    if (lane == 0) {
         __threadfence();
-        if (atomicAdd(p.queue + 1, 1) == nw - 1) { p.queue[0] = 0; p.queue[1] = 0; }
+        last = atomicAdd(queue + 1, 1) == nw - 1;
+        if (last) { queue[0] = 0; queue[1] = 0; }
+    }
+    if (GENES && G > 0 && __shfl_sync(FULL, last, 0)) {
+        __threadfence();
+        pick_reference_warp(p, lane);
     }
 }
 
@@ -1428,7 +1572,9 @@ cudaError_t kernels_init()
 #undef EPX_PAIR2_ATTR
     if ((e = allow_max_dynamic_smem(k_group_blocksort)) != cudaSuccess) return e;
     if ((e = allow_max_dynamic_smem(k_probe_rank_w2)) != cudaSuccess) return e;
-#define EPX_RANK_ATTR(E) if ((e = allow_max_dynamic_smem(k_probe_rank_w<E>)) != cudaSuccess) return e;
+#define EPX_RANK_ATTR(E)                                                                      \
+    if ((e = allow_max_dynamic_smem(k_probe_rank_w<E, false>)) != cudaSuccess) return e;      \
+    if ((e = allow_max_dynamic_smem(k_probe_rank_w<E, true>)) != cudaSuccess) return e;
     EPX_FOR_SORT_VARIANTS(EPX_RANK_ATTR)
 #undef EPX_RANK_ATTR
     return cudaSuccess;
@@ -1510,7 +1656,41 @@ cudaError_t launch_gene_tests(const GeneTestParams &p, int sm_count, cudaStream_
 #undef EPX_CASE
     default: return cudaErrorInvalidValue;
     }
+    if (p.test_t) k_gene_tails<<<(3 * p.G + 127) / 128, 128, 0, st>>>(p);
     return cudaGetLastError();
+}
+
+bool probe_rank_takes_genes(int n) { return n <= 512; }
+
+template <int E, bool GENES> static cudaError_t launch_rows_w(const RankParams &p, int sm_count, cudaStream_t st)
+{
+    constexpr int RW = rank_warps<E>();
+    const size_t smem = rank_warp_smem<E>() * RW;
+    /* persistent grid of exactly one wave: a grid of 8 CTAs per SM with 3 resident ran 2.67 waves */
+    static std::atomic<int> per_sm{0};
+    if (per_sm == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w<E, GENES>, RW * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+        per_sm = nb;
+    }
+    const int64_t rows = GENES ? p.genes.G : p.U;
+    if (rows <= 0) return cudaSuccess;
+    int64_t grid = (rows + RW - 1) / RW;
+    if (grid > (int64_t)sm_count * per_sm) grid = (int64_t)sm_count * per_sm;
+    k_probe_rank_w<E, GENES><<<(unsigned)grid, RW * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+/* the expression rows through the row kernel (n <= 512): order, labels, centred rows, reference pick; replaces
+ * k_gene_sort_w + k_pick_reference for those sample counts */
+cudaError_t launch_gene_rows(const RankParams &p, int sm_count, cudaStream_t st)
+{
+    switch (sort_eps(p.n)) {
+#define EPX_CASE(E) case E: return launch_rows_w<E, true>(p, sm_count, st);
+        EPX_FOR_SORT_VARIANTS(EPX_CASE)
+#undef EPX_CASE
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st)
@@ -1542,27 +1722,11 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
         return cudaGetLastError();
     }
     switch (sort_eps(p.n)) {
-#define EPX_CASE(E)                                                                          \
-    case E: {                                                                                \
-        constexpr int RW = rank_warps<E>();                                                  \
-        const size_t smem = rank_warp_smem<E>() * RW;                                        \
-        /* persistent grid of exactly one wave: a grid of 8 CTAs per SM with 3 resident ran 2.67 waves */ \
-        static std::atomic<int> per_sm{0};                                                   \
-        if (per_sm == 0) {                                                                   \
-            int nb = 0;                                                                      \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_rank_w<E>, RW * 32, smem) != cudaSuccess || nb < 1) nb = 1; \
-            per_sm = nb;                                                                     \
-        }                                                                                    \
-        int64_t grid = (p.U + RW - 1) / RW;                                                  \
-        if (grid > (int64_t)sm_count * per_sm) grid = (int64_t)sm_count * per_sm;            \
-        k_probe_rank_w<E><<<(unsigned)grid, RW * 32, smem, st>>>(p);                         \
-        break;                                                                               \
-    }
+#define EPX_CASE(E) case E: return launch_rows_w<E, false>(p, sm_count, st);
         EPX_FOR_SORT_VARIANTS(EPX_CASE)
 #undef EPX_CASE
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 template <int EPL, int EPW>
@@ -1598,6 +1762,16 @@ static cudaError_t launch_pair2(PairParams p, int sm_count, cudaStream_t st)
     return cudaGetLastError();
 }
 
+static bool pair2_eligible(const PairParams &p)
+{
+    if (p.n > MAX_WARP_SAMPLES) return false;
+    const int epl = (p.n + 31) / 32;
+    if (!(epl <= 16 || epl == 32)) return false;
+    /* bulk-copy path: rows and order rows must be 16-byte aligned with a 16-byte multiple length */
+    const bool aligned = (((uintptr_t)p.meth) & 15) == 0 && (p.ld & 1) == 0 && (((uintptr_t)p.ord) & 15) == 0 && (p.ldo & 7) == 0;
+    return aligned && pair2_warp_smem(p.n, p.ld, p.ldo, p.test_t != 0) * PAIR2_WARPS <= 200 * 1024;
+}
+
 cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st)
 {
     if (p.n_items <= 0) return cudaSuccess;
@@ -1621,9 +1795,7 @@ cudaError_t launch_pair_stats(const PairParams &p, int sm_count, cudaStream_t st
         return cudaGetLastError();
     }
     const int epl = (p.n + 31) / 32;
-    /* bulk-copy path: rows and order rows must be 16-byte aligned with a 16-byte multiple length */
-    const bool aligned = (((uintptr_t)p.meth) & 15) == 0 && (p.ld & 1) == 0 && (((uintptr_t)p.ord) & 15) == 0 && (p.ldo & 7) == 0;
-    if (aligned && pair2_warp_smem(p.n, p.ld, p.ldo, p.test_t != 0) * PAIR2_WARPS <= 200 * 1024) {
+    if (pair2_eligible(p)) {
         switch (epl) {
 #define EPX_CASE2(E) case E: return launch_pair2<E>(p, sm_count, st);
             EPX_FOR_PAIR2_VARIANTS(EPX_CASE2)

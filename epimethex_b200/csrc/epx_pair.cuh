@@ -44,6 +44,7 @@ __device__ __forceinline__ double welch_p(const PairParams &p, double t, double 
 
 constexpr int PAIR2_WARPS = 4;
 
+
 /* sorted walk: two running words of two biased 16-bit fields each, ra = [cUP-cMID | cUP-cDOWN],
  * rb = [cMID-cDOWN | cUP]; the table holds, per sample, what its label adds to them (32-bit wrap-around sums:
  * a field value stays within bias +- 1024, so no carry ever crosses a field in the decoded value) */

@@ -130,6 +130,16 @@ template <int EPS> struct WarpSort {
                                                  const int lane, unsigned short *s_ord, ValueOf value, const unsigned one,
                                                  unsigned short (&out)[EPS])
     {
+        order_rt(khi, klo, n, lane, s_ord, value, DESC, one, out);
+    }
+
+    /* the same with the direction as a (warp-uniform) run-time value: one copy of the network for kernels that order
+     * rows both ways (k_probe_rank_w: expression rows descending, methylation rows ascending) */
+    template <typename ValueOf>
+    __device__ __forceinline__ static void order_rt(const unsigned (&khi)[EPS], const unsigned (&klo)[EPS], const int n,
+                                                    const int lane, unsigned short *s_ord, ValueOf value, const bool DESC,
+                                                    const unsigned one, unsigned short (&out)[EPS])
+    {
         constexpr unsigned CMASK = 0x7fffffffu & ~IDXM;
         /* bits shared by all keys: OR of (key ^ key0) tells where they start to differ */
         const unsigned h0 = __shfl_sync(FULL, khi[0], 0), l0 = __shfl_sync(FULL, klo[0], 0);

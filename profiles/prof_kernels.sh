@@ -8,5 +8,5 @@ CMD="python bench.py --workload $WL --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 4 -c 2 -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none -k regex:"$KRE" -s 2 -c ${NCAP:-1} -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "prof rc=$?"; ls -la gpurun_out/${TAG}_*
