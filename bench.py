@@ -286,6 +286,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-one-process", dest="one_process", action="store_false",
+                    help="N > 1: skip the one-process epx_multi_analyze measurement on rank 0")
     ap.add_argument("--no-other-mode", dest="other_mode", action="store_false",
                     help="skip the second timing with the other methylation test (KS <-> Welch t)")
     ap.add_argument("--pooled", default="", choices=["", "gene", "position", "island"],
@@ -383,10 +385,14 @@ def main():
             else:
                 pdst = [torch.empty_like(pair_t) for _ in range(world)] if rank == 0 else None
                 gdst = [torch.empty_like(gene_t) for _ in range(world)] if rank == 0 else None
-            gather_plan = (pair_t, pdst, gene_t, gdst, torch.cuda.Event())
-        pair_t, pdst, gene_t, gdst, ev_gene = gather_plan
-        tstream.wait_stream(gstream)              # previous pair-table gather done before the table is overwritten
+            # the gather reads a COPY of the pair table (41.8 MB device to device, ~15 us): the pair kernel of the next
+            # step then never waits for the previous gather, only the next copy does -- a whole step later
+            gather_plan = (pair_t, pdst, gene_t, gdst, torch.cuda.Event(), torch.empty_like(pair_t))
+        pair_t, pdst, gene_t, gdst, ev_gene, pair_copy = gather_plan
         sess.run_pairs(0, 1, stream)
+        tstream.wait_stream(gstream)              # the previous gather has read the copy
+        pair_copy.copy_(pair_t)
+        pair_t = pair_copy
         gstream.wait_stream(tstream)
         with torch.cuda.stream(gstream):
             if strong:
@@ -433,7 +439,7 @@ def main():
     # (64-bit wrap-around sum of the table's bit patterns: order-independent, so it is exact)
     shards = None
     if world > 1:
-        pair_t, pdst, gene_t, gdst, _ = gather_plan
+        pair_t, pdst, gene_t, gdst = gather_plan[:4]
         mine = torch.stack([pair_t.view(torch.int64).sum(), gene_t.view(torch.int64).sum(),
                             torch.tensor(pair_t.shape[0], device="cuda"), torch.tensor(gene_t.shape[0], device="cuda")])
         sums = [torch.empty_like(mine) for _ in range(world)]
@@ -520,6 +526,7 @@ def main():
     e2e_ms = []
     e2e_upload_ms = []
     e2e_pairs = []
+    e2e_call_ms = []
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         rp_i, pi_i = variants[i & 1]
         torch.cuda.synchronize()
@@ -532,10 +539,12 @@ def main():
             e2e_ms.append(dt * 1e3)
             e2e_upload_ms.append((t1 - t0) * 1e3)
             e2e_pairs.append(int(rp_i[-1]))
+            e2e_call_ms.append((dt - (t1 - t0)) * 1e3)
     e2e_t = float(np.median(e2e_ms)) if e2e_ms else float("nan")  # median: host-side outliers (page faults, PCIe neighbours)
     if args.e2e_steps <= 0:
         e2e_t = float("nan")
     e2e_frac = float(np.mean(e2e_pairs)) / Np if e2e_pairs and Np else 1.0   # pairs actually analysed per e2e step
+    e2e_analyze_ms = float(np.median(e2e_call_ms)) if e2e_call_ms else float("nan")   # the epx_analyze call alone (matrix resident)
     if world > 1:
         tmax = torch.tensor([e2e_t], device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -580,6 +589,38 @@ def main():
             got2 = sess.analyze(wl["expr"][sel2], ptr2, pi2, _native.make_options(True, wl["w"]["te"], tm2), full=True)
             modes["tt" if tm2 else "ks"]["parity"] = parity_report(got2, ref2, f"{sel2.size} genes, {int(ptr2[-1])} pairs")
 
+    # ---- the multi-GPU path the R API can reach: ONE process drives all N GPUs (R is a single process;
+    # epx_multi_analyze replaces the PSOCK cluster of R/EpimethexAnalysis.R:333-352). The ranks have finished their own
+    # measurement; they free their GPUs and wait while rank 0 analyses ITS cohort once more across all N devices: genes
+    # cut into N ranges of equal pair counts, every device writes its rows straight into the caller's host tables. ----
+    one_process = None
+    if world > 1 and not strong and args.one_process:
+        single = sess.analyze(wl["expr"], idx.row_ptr, idx.probe_idx, opts, full=True) if rank == 0 else None
+        sess.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            t0 = time.perf_counter()
+            ms_ = _native.MultiSession(list(range(world)))
+            ms_.set_methylation(wl["meth"])
+            up_s = time.perf_counter() - t0
+            calls = []
+            for i in range(1 + 5):
+                t0 = time.perf_counter()
+                multi = ms_.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts)
+                calls.append((time.perf_counter() - t0) * 1e3)
+            same = all(np.array_equal(getattr(single, k), getattr(multi, k), equal_nan=True)
+                       for k in ("pair", "pair_stat", "gene")) and all(
+                np.array_equal(getattr(single, k), getattr(multi, k)) for k in ("ks_dnum", "pair_na", "gene_na", "perm"))
+            call_ms = float(np.median(calls[1:]))
+            one_process = {"what": "epx_multi_analyze: one host process, %d GPUs, one cohort (strong scaling of a single call), "
+                                   "host buffers in and out, methylation replicas resident" % world,
+                           "ms_per_call": round(call_ms, 3), "pairs_per_s": Np / (call_ms * 1e-3), "calls_ms": [round(v, 2) for v in calls[1:]],
+                           "methylation_upload_s": round(up_s, 3), "single_gpu_call_ms": None,
+                           "identical_to_single_gpu_tables": bool(same)}
+            ms_.close()
+        dist.barrier()
+
     if rank == 0:
         peak, peak_src = peaks()
         # algorithmic bytes per launch: pair kernel N_p*(8n+88); rank kernel U*(8n read + 2n written)
@@ -606,7 +647,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "index_rebuilt_every_step": True,
                     "ms_per_step": e2e_t, "steps": len(e2e_ms), "ms_each": [round(v, 2) for v in e2e_ms],
-                    "methylation_upload_ms": round(float(np.median(e2e_upload_ms)), 2) if e2e_upload_ms else None, "pinned_host_buffers": bool(wl["pinned"]),
+                    "methylation_upload_ms": round(float(np.median(e2e_upload_ms)), 2) if e2e_upload_ms else None,
+                    "analyze_call_ms": round(e2e_analyze_ms, 2) if e2e_analyze_ms == e2e_analyze_ms else None, "pinned_host_buffers": bool(wl["pinned"]),
                     "h2d_gbs": round(h2d / (e2e_t * 1e-3) / 1e9, 1) if e2e_t == e2e_t else None},
             "gpu_launches": int(tim["kernel_launches"]) * args.steps,
             "clocks": clocks,
@@ -620,6 +662,9 @@ def main():
             line["gathered_shards"] = shards
         if modes:
             line["modes"] = modes
+        if one_process:
+            one_process["single_gpu_call_ms"] = round(e2e_analyze_ms, 3) if e2e_analyze_ms == e2e_analyze_ms else None
+            line["one_process"] = one_process
         if cb is not None and world == 1:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         assert int(total_pairs) == wl["total_pairs"], (total_pairs, wl["total_pairs"])

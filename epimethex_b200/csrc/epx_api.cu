@@ -100,7 +100,8 @@ struct epx_session {
     void *staging = nullptr; /* pinned */
     size_t staging_bytes = 0;
     /* pooled probe groups (epx_session_run_groups) */
-    std::vector<int32_t> h_probe_idx, h_pair_gene; /* host copies of the index, to validate group lists */
+    const int32_t *h_probe_idx = nullptr, *h_pair_gene = nullptr; /* host copies of the index (in `staging`), to validate group lists */
+    std::vector<int32_t> slot_of;                   /* [P] order row of a methylation row while an index is built, else -1 */
     std::vector<int64_t> h_row_ptr;
     DevBuf<double> upload_stage;                    /* 2 x 64 MB: flat H2D chunks before re-spacing */
     cudaEvent_t ev_up[3] = { nullptr, nullptr, nullptr };
@@ -440,60 +441,84 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
      * from it is still on the device */
     if (s->G_index == n_genes && s->Np == Np && s->h_row_ptr.size() == (size_t)n_genes + 1 && s->index_P == s->P &&
         memcmp(s->h_row_ptr.data(), row_ptr, ((size_t)n_genes + 1) * sizeof(int64_t)) == 0 &&
-        (Np == 0 || memcmp(s->h_probe_idx.data(), probe_idx, (size_t)Np * sizeof(int32_t)) == 0))
+        (Np == 0 || memcmp(s->h_probe_idx, probe_idx, (size_t)Np * sizeof(int32_t)) == 0))
         return EPX_OK;
     EPX_CUDA(cudaSetDevice(s->device));
 
-    std::vector<int32_t> slot_of((size_t)s->P, -1), pair_slot((size_t)Np), pair_gene((size_t)Np), uniq;
-    std::vector<Item> items;
+    /* Host bookkeeping of a new index. The reference is called once per gene range (README.md:90), so this runs on
+     * every call: everything lives in buffers the session keeps -- one page-locked block for what goes to the device
+     * (probe_idx | pair_slot | pair_gene | uniq | items: the copies are truly asynchronous and no fresh pages are
+     * touched), a slot table that is reset entry by entry -- instead of five vectors allocated and faulted in per call. */
+    const size_t max_items = (size_t)Np / 4 + (size_t)n_genes + 1;
+    const size_t need = (size_t)Np * 4 * 4 + max_items * sizeof(Item) + 64;
+    if (need > s->staging_bytes) {
+        if (s->staging) cudaFreeHost(s->staging);
+        s->staging = nullptr; s->staging_bytes = 0;
+        EPX_CUDA(cudaHostAlloc(&s->staging, need + need / 4, cudaHostAllocDefault));
+        s->staging_bytes = need + need / 4;
+    }
+    int32_t *h_pi = (int32_t *)s->staging, *pair_slot = h_pi + Np, *pair_gene = pair_slot + Np, *uniq = pair_gene + Np;
+    Item *items = (Item *)(((uintptr_t)(uniq + Np) + 15) & ~(uintptr_t)15);
+    if (s->slot_of.size() < (size_t)s->P) s->slot_of.assign((size_t)s->P, -1);
+    int32_t *slot_of = s->slot_of.data();
+    size_t n_uniq = 0, n_items = 0;
     /* work items of the pair kernel: up to ITEM_PAIRS consecutive pairs of one gene. Small jobs (a 1000-gene
      * range is ~23 k pairs for ~2400 resident warps) get smaller items so that every warp has several. */
     int64_t item_pairs = Np / ((int64_t)s->sm_count * 16 * 4);
     if (item_pairs < 4) item_pairs = 4;
     if (item_pairs > ITEM_PAIRS) item_pairs = ITEM_PAIRS;
-    for (int64_t g = 0; g < n_genes; g++) {
+    int bad_code = 0;
+    int64_t bad_at = 0;
+    for (int64_t g = 0; g < n_genes && !bad_code; g++) {
         const int64_t b = row_ptr[g], e = row_ptr[g + 1];
-        if (e < b || e > Np) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)g);
+        if (e < b || e > Np) { bad_code = 1; bad_at = g; break; }
         for (int64_t j = b; j < e; j++) {
             const int32_t pi = probe_idx[j];
-            pair_gene[(size_t)j] = (int32_t)g;
-            if (pi >= s->P) return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d >= n_probes %lld", (long long)j, pi, (long long)s->P);
-            if (pi < 0) { pair_slot[(size_t)j] = -1; continue; }
-            if (slot_of[(size_t)pi] < 0) { slot_of[(size_t)pi] = (int32_t)uniq.size(); uniq.push_back(pi); }
-            pair_slot[(size_t)j] = slot_of[(size_t)pi];
+            h_pi[j] = pi;
+            pair_gene[j] = (int32_t)g;
+            if (pi >= s->P) { bad_code = 2; bad_at = j; break; }
+            if (pi < 0) { pair_slot[j] = -1; continue; }
+            if (slot_of[pi] < 0) { slot_of[pi] = (int32_t)n_uniq; uniq[n_uniq++] = pi; }
+            pair_slot[j] = slot_of[pi];
         }
         for (int64_t j = b; j < e; j += item_pairs) {
             Item it;
             it.gene = (int32_t)g; it.begin = (int32_t)j;
             it.count = (int32_t)((e - j) < item_pairs ? (e - j) : item_pairs); it.pad = 0;
-            items.push_back(it);
+            items[n_items++] = it;
         }
+    }
+    for (size_t u = 0; u < n_uniq; u++) slot_of[uniq[u]] = -1;   /* the table is clean again for the next index */
+    if (bad_code) {
+        s->G_index = -1;                                          /* the staging block no longer mirrors a valid index */
+        if (bad_code == 1) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)bad_at);
+        return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d >= n_probes %lld", (long long)bad_at, probe_idx[bad_at], (long long)s->P);
     }
     EPX_CUDA(s->probe_idx.reserve((size_t)Np));
     EPX_CUDA(s->pair_slot.reserve((size_t)Np));
     EPX_CUDA(s->pair_gene.reserve((size_t)Np));
-    EPX_CUDA(s->uniq_probe.reserve(uniq.size()));
-    EPX_CUDA(s->items.reserve(items.size()));
+    EPX_CUDA(s->uniq_probe.reserve(n_uniq));
+    EPX_CUDA(s->items.reserve(n_items));
     if (Np) {
-        EPX_CUDA(cudaMemcpyAsync(s->probe_idx.p, probe_idx, (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
-        EPX_CUDA(cudaMemcpyAsync(s->pair_slot.p, pair_slot.data(), (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
-        EPX_CUDA(cudaMemcpyAsync(s->pair_gene.p, pair_gene.data(), (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(cudaMemcpyAsync(s->probe_idx.p, h_pi, (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(cudaMemcpyAsync(s->pair_slot.p, pair_slot, (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
+        EPX_CUDA(cudaMemcpyAsync(s->pair_gene.p, pair_gene, (size_t)Np * 4, cudaMemcpyHostToDevice, s->stream));
     }
-    if (!uniq.empty())
-        EPX_CUDA(cudaMemcpyAsync(s->uniq_probe.p, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    if (!items.empty())
-        EPX_CUDA(cudaMemcpyAsync(s->items.p, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, s->stream));
-    EPX_CUDA(cudaStreamSynchronize(s->stream)); /* the vectors die with this scope */
-    s->item_begin.resize(items.size() + 1);
-    for (size_t i = 0; i < items.size(); i++) s->item_begin[i] = items[i].begin;
-    s->item_begin[items.size()] = (int32_t)Np;
-    s->h_probe_idx.assign(probe_idx, probe_idx + Np);
+    if (n_uniq) EPX_CUDA(cudaMemcpyAsync(s->uniq_probe.p, uniq, n_uniq * 4, cudaMemcpyHostToDevice, s->stream));
+    if (n_items) EPX_CUDA(cudaMemcpyAsync(s->items.p, items, n_items * sizeof(Item), cudaMemcpyHostToDevice, s->stream));
+    s->item_begin.resize(n_items + 1);
+    for (size_t i = 0; i < n_items; i++) s->item_begin[i] = items[i].begin;
+    s->item_begin[n_items] = (int32_t)Np;
     s->h_row_ptr.assign(row_ptr, row_ptr + n_genes + 1);
+    s->h_probe_idx = h_pi;          /* host copies for the group-list checks: they live in the staging block */
+    s->h_pair_gene = pair_gene;
     s->index_P = s->P;
-    s->h_pair_gene.swap(pair_gene);
+    /* the copies read the staging block: it is rewritten by the next set_index only, which runs after this stream has
+     * been synchronised by the run / fetch in between -- but a caller may set two indices back to back */
+    EPX_CUDA(cudaStreamSynchronize(s->stream));
     s->n_groups = -1;
     s->prepared = false;
-    s->Np = Np; s->U = (int64_t)uniq.size(); s->n_items = (int64_t)items.size(); s->G_index = n_genes;
+    s->Np = Np; s->U = (int64_t)n_uniq; s->n_items = (int64_t)n_items; s->G_index = n_genes;
     return EPX_OK;
 }
 
