@@ -630,6 +630,10 @@ def main():
         for k, t in kern.items():
             gbs = alg[k] / (t * 1e-3) / 1e9 if t > 0 else 0.0
             kernels[k[:-3]] = {"ms": round(t, 4), "algorithmic_bytes": int(alg[k]), "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        # rows whose bucket placement failed its check and went through the full sorting network (a performance
+        # counter of the rank kernel, cumulative over the session's runs; the results are the same either way)
+        runs = args.warmup + args.steps + reps
+        kernels["probe_rank"]["rows_through_full_network_per_run"] = round(int(tim.get("sort_full_rows", 0)) / max(runs, 1), 1)
         dom = max(kern, key=lambda k: kern[k])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")

@@ -65,7 +65,7 @@ class Timing(C.Structure):
                 ("probe_rank_ms", C.c_float), ("pair_stats_ms", C.c_float),
                 ("n_pairs", C.c_int64), ("n_unique_probes", C.c_int64), ("n_genes", C.c_int64),
                 ("n_samples", C.c_int64), ("algorithmic_bytes", C.c_int64), ("kernel_launches", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("sort_full_rows", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -228,7 +228,7 @@ int epx_session_create(int device, epx_session **out, char *err, size_t errlen)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = s->scal.reserve(16);
-    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 16 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel; [8], [9]: of the expression-row kernel; [10], [11]: of the probe-rank kernel; [12]-[13]: reference-gene maximum */
+    if (e == cudaSuccess) e = cudaMemset(s->scal.p, 0, 16 * sizeof(int32_t)); /* [6], [7]: work queue of the pair kernel; [8], [9]: of the expression-row kernel; [10], [11]: of the probe-rank kernel; [12]-[13]: reference-gene maximum; [14]: rows sorted by the full network after a failed bucket placement (since the session was created) */
     if (e != cudaSuccess) {
         epx_session_destroy(s);
         return fail(err, errlen, EPX_ECUDA, "session setup: %s", cudaGetErrorString(e));
@@ -641,6 +641,7 @@ int epx_session_run_prepare(epx_session *s, const epx_options *opt_in, void *str
     rp.genes = gp;
     rp.nuniq_in = s->nuniq.p; rp.counts = tp.counts; rp.ref_gene = tp.ref_gene; rp.status = tp.status;
     rp.best = (unsigned long long *)(s->scal.p + 12);
+    rp.full_rows = s->scal.p + 14;
 
     PairParams pp;
     pp.meth = s->meth; pp.ld = s->ld; pp.ord = s->ord.p; pp.ldo = s->ldo; pp.probe_idx = s->probe_idx.p;
@@ -784,6 +785,7 @@ int epx_session_timing(epx_session *s, epx_timing *out, char *err, size_t errlen
     out->n_pairs = s->Np; out->n_unique_probes = s->U; out->n_genes = s->G; out->n_samples = s->n;
     out->algorithmic_bytes = s->Np * (8 * s->n + 88) + s->G * (10 * s->n + 48);
     out->kernel_launches = s->launches;
+    EPX_CUDA(cudaMemcpy(&out->sort_full_rows, s->scal.p + 14, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return EPX_OK;
 }
 

@@ -68,6 +68,7 @@ struct RankParams {
     const int32_t *nuniq_in; /* = genes.nuniq */
     int32_t *counts, *ref_gene, *status;
     unsigned long long *best;   /* max over genes of (distinct values << 32 | ~gene); 0 between launches */
+    int32_t *full_rows;         /* rows whose bucket placement failed its check and went through the full network (may be NULL) */
 };
 
 struct PairParams {

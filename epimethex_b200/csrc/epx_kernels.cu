@@ -577,7 +577,12 @@ __global__ void __launch_bounds__(128) k_gene_tails(GeneTestParams p)
 /* k_probe_rank, one warp per referenced probe */
 template <int EPS> __host__ __device__ constexpr int rank_warps() { return SORT_WARPS; }
 /* per-warp shared memory: 2 row stages of 32*EPS doubles | 2 mbarriers | 32*EPS uint16 of sort scratch */
-template <int EPS> __host__ __device__ constexpr size_t rank_warp_smem() { return (size_t)2 * 32 * EPS * 8 + 16 + (size_t)32 * EPS * 2; }
+/* rows of 257..512 values are placed by buckets before a short network (WarpSort::order_bucket) */
+template <int EPS> __host__ __device__ constexpr bool rank_by_buckets() { return EPS == 16; }
+template <int EPS> __host__ __device__ constexpr size_t rank_warp_smem()
+{
+    return (size_t)2 * 32 * EPS * 8 + 16 + (rank_by_buckets<EPS>() ? WarpSort<EPS>::BUCKET_SMEM : (size_t)32 * EPS * 2);
+}
 
 /* the bin.var reference gene and its group sizes (R/EpimethexAnalysis.R:134-139), by ONE warp: the last warp to leave
  * k_probe_rank_w, which by then sees the order and the distinct-value count of every gene (same result as
@@ -628,10 +633,11 @@ __device__ __noinline__ void pick_reference_warp(const RankParams &p, const int 
  * Two instantiations of one loop rather than one kernel for both: with both row kinds in one kernel its code outgrew
  * the instruction cache and every row paid for it (measured: 0.93 -> 1.15 ms). */
 template <int EPS, bool GENES>
-__global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k_probe_rank_w(RankParams p)
+__global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 && !rank_by_buckets<EPS>() ? 3 : 2)) k_probe_rank_w(RankParams p)
 {
     constexpr int RW = rank_warps<EPS>();
     constexpr int N = 32 * EPS;
+    constexpr bool BUCKETS = rank_by_buckets<EPS>();
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
     unsigned char *base = smem + (size_t)warp * rank_warp_smem<EPS>();
@@ -649,6 +655,8 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
     const bool bulk = !GENES && ((((uintptr_t)p.meth) | ((uintptr_t)p.ld * 8u)) & 15u) == 0 && p.ld <= N;
     const uint32_t rowb = (uint32_t)p.ld * 8u;
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_ord), *s_srt = s_cnt + WarpSort<EPS>::NB; /* BUCKETS: counters | slots */
+    if constexpr (BUCKETS) { for (int i = lane; i < WarpSort<EPS>::NB; i += 32) s_cnt[i] = 0u; }
     __syncwarp();
     uint32_t ph0 = 0, ph1 = 0;
     int fill = 0, use = 0;
@@ -684,6 +692,16 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
         else __syncwarp();
         use ^= 1;
         constexpr bool gene = GENES; /* descending order for expression rows (R/EpimethexAnalysis.R:117-122) */
+        unsigned short out[EPS];
+        if constexpr (BUCKETS) {
+            double x[EPS];
+#pragma unroll
+            for (int e = 0; e < EPS; e++) {
+                const int s = lane + 32 * e;
+                x[e] = row[(2 * e < EPS || s < n) ? s : 0];
+            }
+            WarpSort<EPS>::order_bucket(x, n, lane, s_cnt, s_srt, [&](int i) { return row[i]; }, GENES, p.one, out, p.full_rows);
+        } else {
         unsigned khi[EPS], klo[EPS];
         if (!gene) {
 #pragma unroll
@@ -700,9 +718,9 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 ? 3 : 2)) k
                 khi[e] = ~khi[e]; klo[e] = ~klo[e];
             }
         }
-        unsigned short out[EPS];
         /* pad positions (k >= n) carry index n: the pair kernel's inert table entry */
         WarpSort<EPS>::template order<GENES>(khi, klo, n, lane, s_ord, [&](int i) { return row[i]; }, p.one, out);
+        }
         if (!gene) {
             uint16_t *o = p.ord + slot * p.ldo + lane * EPS;
             if (EPS >= 8) {

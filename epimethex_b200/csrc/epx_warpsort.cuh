@@ -34,6 +34,17 @@ __device__ __forceinline__ void ce_half(unsigned &v, const unsigned t, const uns
     asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@!p min.u32 %0, %0, %1;\n\t@p max.u32 %0, %0, %1;\n\t}" : "+r"(v) : "r"(t), "r"(upper));
 }
 
+/* shared-memory counter bumps under a predicate instead of a branch (the C form costs a BSSY/BRA/BSYNC per element) */
+__device__ __forceinline__ void smem_inc_if(const uint32_t addr, const bool p)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ unsigned smem_take_if(const uint32_t addr, const bool p, unsigned otherwise)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(otherwise) : "r"(addr), "r"((unsigned)p) : "memory");
+    return otherwise;
+}
+
 template <int EPS> struct WarpSort {
     static constexpr int N = 32 * EPS;
     static constexpr int IDXB = (EPS == 1 ? 5 : EPS == 2 ? 6 : EPS == 4 ? 7 : EPS == 8 ? 8 : EPS == 16 ? 9 : 10);
@@ -67,7 +78,8 @@ template <int EPS> struct WarpSort {
      * index keeps the minimum) followed by half-cleaners (i <-> i ^ j). Phases that fit a thread are unrolled;
      * the five cross-lane phases run as a loop (same code for every phase: the body stays in the instruction
      * cache) with the lane masks as run-time values. */
-    __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane, const unsigned one, const unsigned minus1)
+    /* the stages that stay inside a thread: on return every lane's EPS words ascend */
+    __device__ __forceinline__ static void sort_thread(unsigned (&v)[EPS], const unsigned one, const unsigned minus1)
     {
 #pragma unroll
         for (int k = 2; k <= EPS; k <<= 1) {
@@ -82,6 +94,11 @@ template <int EPS> struct WarpSort {
             }
             thread_tail(v, k / 4, one, minus1);
         }
+    }
+
+    __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane, const unsigned one, const unsigned minus1)
+    {
+        sort_thread(v, one, minus1);
 #pragma unroll 1
         for (int q = 1; q < 32; q <<= 1) { /* phase k = 2*EPS*q */
             {
@@ -184,7 +201,180 @@ template <int EPS> struct WarpSort {
             }
         }
         sort(v, lane, one, 0u - one);
+        finish(v, n, lane, s_ord, value, DESC, out);
+    }
 
+    /* ---------------------------------------------------------------------------------------------------------
+     * Bucket placement in front of a SHORT network (order_bucket). The full network above costs 45 compare-exchange
+     * phases per row; most of them only move values over long distances. Here every value is first dropped near its
+     * final position by a counting pass in shared memory -- bucket = linear map of the value over the row's range,
+     * 1.25 buckets per slot, counters bumped with shared-memory atomics (ATOMS: ~2.7 cycles per warp instruction on
+     * B200 when the 32 addresses differ, profiles/micro/hist_micro.cu) -- so that what is left out of order are the
+     * few values that share a bucket. Those are settled by the EPS-value network inside each thread plus one merge
+     * across the thread boundaries (runs of up to EPS/2 + 1 values are put right). Whether that was enough is CHECKED
+     * (one comparison per neighbour pair); a row that fails (a bucket that was too full: heavy ties in the middle of
+     * the range, extreme outliers) goes through the full network, so the result never depends on the data's shape.
+     * The word sorted is [pad flag | q | sample index] with q = round((x - first) * scale): monotone in x, ~2^21
+     * levels over the row's range; neighbours with equal q are settled on the full values by finish() as before.
+     * -------------------------------------------------------------------------------------------------------- */
+    static constexpr int BK = EPS + 4;             /* counters (and padded slots) per lane: 16-byte chunks at an ODD chunk stride, so the
+                                                    * LDS.128 / STS.128 of 8 consecutive lanes touch 8 different bank groups */
+    static constexpr int NB = 32 * BK;             /* buckets */
+    static constexpr int QSH = 31 - IDXB - (EPS == 8 ? 9 : EPS == 16 ? 10 : 11); /* q >> QSH = bucket; NB << QSH < 2^(31 - IDXB) */
+    static constexpr unsigned QMAX = (unsigned)NB << QSH;
+    static constexpr size_t BUCKET_SMEM = (size_t)2 * NB * 4; /* counters | padded slots (later the 16-bit scratch of finish()) */
+
+    template <typename ValueOf>
+    __device__ __forceinline__ static void order_bucket(const double (&x)[EPS], const int n, const int lane, unsigned *s_cnt,
+                                                        unsigned *s_srt, ValueOf value, const bool DESC, const unsigned one,
+                                                        unsigned short (&out)[EPS], int32_t *full_rows)
+    {
+        static_assert(EPS >= 8, "bucket placement is instantiated for 8, 16 and 32 values per lane");
+        static_assert(((unsigned long long)NB << QSH) < (1ull << (31 - IDXB)), "q must fit below the pad flag");
+        /* range of the row from the high words of its keys (order-preserving transform of key_halves) */
+        unsigned tmin = 0xffffffffu, tmax = 0u;
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int h = __double2hiint(x[e]);
+            const unsigned t = (unsigned)h ^ ((unsigned)(h >> 31) | 0x80000000u);
+            tmin = min(tmin, t);
+            tmax = max(tmax, t);
+        }
+        tmin = __reduce_min_sync(FULL, tmin);
+        tmax = __reduce_max_sync(FULL, tmax);
+        unsigned lmin = 0u, lmax = 0xffffffffu;
+        if (tmax - tmin < 64u) { /* narrow row (rare): the low words matter */
+            lmin = 0xffffffffu; lmax = 0u;
+#pragma unroll
+            for (int e = 0; e < EPS; e++) {
+                unsigned hi, lo;
+                key_halves(x[e], hi, lo);
+                if (hi <= tmin) lmin = min(lmin, lo);
+                if (hi >= tmax) lmax = max(lmax, lo);
+            }
+            lmin = __reduce_min_sync(FULL, lmin);
+            lmax = __reduce_max_sync(FULL, lmax);
+        }
+        double xlo, xhi;
+        {
+            const unsigned m0 = (tmin & 0x80000000u) ? 0u : 0xffffffffu, m1 = (tmax & 0x80000000u) ? 0u : 0xffffffffu;
+            xlo = __hiloint2double((int)(tmin ^ (m0 | 0x80000000u)), (int)(lmin ^ m0));
+            xhi = __hiloint2double((int)(tmax ^ (m1 | 0x80000000u)), (int)(lmax ^ m1));
+        }
+        /* q = round((x - first) * scale) + (2^QSH - 8): the row's first value lands at the TOP of bucket 0 and its last
+         * value at the BOTTOM of bucket NB - 1, so a pile of values clipped to the row's minimum or maximum (beta values
+         * at a detection limit, zero expression counts) has a bucket of its own: its members arrive in index order,
+         * which is their final order, and the values next to the pile do not share its bucket */
+        constexpr unsigned QOFF = (1u << QSH) - 8u;
+        const double first = DESC ? xhi : xlo, span = DESC ? xlo - xhi : xhi - xlo;
+        double scale = (double)(((unsigned)(NB - 2) << QSH) + 16u) / span;
+        if (!(fabs(scale) < 1e300)) scale = 0.0; /* constant row (span 0), or a span beyond the exponent range: one bucket, settled by finish() */
+        const double c0 = fma(-first, scale, 6755399441055744.0 + (double)QOFF); /* 2^52 + 2^51: the low word of the sum is the integer */
+
+        const uint32_t cnt_a = smem_u32(s_cnt);
+        unsigned v[EPS];
+        uint32_t ba[EPS]; /* shared-memory address of each value's counter */
+#pragma unroll
+        for (int e = 0; e < EPS; e++) {
+            const int s = lane + 32 * e;
+            unsigned q = (unsigned)__double2loint(fma(x[e], scale, c0));
+            q = min(q, QMAX - 1u); /* memory safety only: a q out of range means the row fails the check below */
+            const bool real = (2 * e < EPS && n > 16 * EPS) || s < n;
+            v[e] = real ? ((q << IDXB) | (unsigned)s) : (0x80000000u | ((unsigned)(s - n) << IDXB) | (unsigned)n);
+            ba[e] = cnt_a + ((q >> (QSH - 2)) & ~3u);
+            smem_inc_if(ba[e], real);
+        }
+        __syncwarp();
+        /* exclusive scan of the counters: BK consecutive ones per lane */
+        {
+            uint4 *c4 = reinterpret_cast<uint4 *>(s_cnt + lane * BK);
+            unsigned c[BK];
+#pragma unroll
+            for (int i = 0; i < BK / 4; i++) {
+                const uint4 w = c4[i];
+                c[4 * i] = w.x; c[4 * i + 1] = w.y; c[4 * i + 2] = w.z; c[4 * i + 3] = w.w;
+            }
+            unsigned tot = 0;
+#pragma unroll
+            for (int i = 0; i < BK; i++) tot += c[i];
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            unsigned run = incl - tot;
+#pragma unroll
+            for (int i = 0; i < BK; i++) { const unsigned t = c[i]; c[i] = run; run += t; }
+#pragma unroll
+            for (int i = 0; i < BK / 4; i++) c4[i] = make_uint4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+        }
+        __syncwarp();
+        /* every value to the next free slot of its bucket; pads straight to their final slots. Slot k lives at word
+         * k + 4 * (k / EPS): the same padded spacing as the counters, for the 16-byte reads below */
+        {
+            const uint32_t srt_a = smem_u32(s_srt);
+#pragma unroll
+            for (int e = 0; e < EPS; e++) {
+                const int s = lane + 32 * e;
+                const bool real = (2 * e < EPS && n > 16 * EPS) || s < n;
+                const unsigned pos = smem_take_if(ba[e], real, (unsigned)s);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(srt_a + 4u * pos + 16u * (pos / EPS)), "r"(v[e]) : "memory");
+            }
+        }
+        __syncwarp();
+        {
+            const uint4 *w4 = reinterpret_cast<const uint4 *>(s_srt + lane * BK);
+#pragma unroll
+            for (int i = 0; i < EPS / 4; i++) {
+                const uint4 w = w4[i];
+                v[4 * i] = w.x; v[4 * i + 1] = w.y; v[4 * i + 2] = w.z; v[4 * i + 3] = w.w;
+            }
+            uint4 *c4 = reinterpret_cast<uint4 *>(s_cnt + lane * BK);
+#pragma unroll
+            for (int i = 0; i < BK / 4; i++) c4[i] = make_uint4(0u, 0u, 0u, 0u); /* counters clean for the next row */
+        }
+        __syncwarp();
+        const unsigned minus1 = 0u - one;
+        sort_thread(v, one, minus1);
+        { /* merge across the thread boundaries: upper half of lane L with the lower half of lane L + 1 */
+            constexpr int H = EPS / 2;
+            unsigned tdn[H], tup[H];
+#pragma unroll
+            for (int j = 0; j < H; j++) {
+                tdn[j] = __shfl_down_sync(FULL, v[j], 1);
+                tup[j] = __shfl_up_sync(FULL, v[H + j], 1);
+            }
+            if (lane != 31) {
+#pragma unroll
+                for (int i = 0; i < H; i++) v[H + i] = min(v[H + i], tdn[H - 1 - i]);
+            }
+            if (lane != 0) {
+#pragma unroll
+                for (int j = 0; j < H; j++) v[j] = max(v[j], tup[H - 1 - j]);
+            }
+            thread_tail(v, H / 2, one, minus1);
+        }
+        { /* the check: ascending everywhere (no two words of a row are equal) */
+            unsigned nx0 = __shfl_down_sync(FULL, v[0], 1);
+            if (lane == 31) nx0 = 0xffffffffu;
+            bool bad = v[EPS - 1] > nx0;
+#pragma unroll
+            for (int r = 0; r + 1 < EPS; r++) bad = bad || (v[r] > v[r + 1]);
+            if (__any_sync(FULL, bad)) {
+                if (lane == 0 && full_rows) atomicAdd(full_rows, 1);
+                sort(v, lane, one, minus1);
+            }
+        }
+        finish(v, n, lane, reinterpret_cast<unsigned short *>(s_srt), value, DESC, out);
+    }
+
+    /* v[] sorted (position k = lane*EPS + r) -> out[]: sample indices with tie marks; neighbours that share a coarse
+     * key are settled on the full values (see order()) */
+    template <typename ValueOf>
+    __device__ __forceinline__ static void finish(const unsigned (&v)[EPS], const int n, const int lane, unsigned short *s_ord,
+                                                  ValueOf value, const bool DESC, unsigned short (&out)[EPS])
+    {
         /* smallest difference between neighbours of the sorted order */
         unsigned nx0 = __shfl_down_sync(FULL, v[0], 1);
         if (lane == 31) nx0 = 0xffffffffu;

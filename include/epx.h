@@ -107,7 +107,8 @@ typedef struct epx_timing {
     int64_t n_pairs, n_unique_probes, n_genes, n_samples;
     int64_t algorithmic_bytes; /* N_p*(8n+88) + G*(10n+48), SURVEY 8(d) */
     int32_t kernel_launches;   /* kernels launched by the last run */
-    int32_t reserved;
+    int32_t sort_full_rows;    /* rows (since the session was created) whose bucket placement failed its check and that
+                                * went through the full sorting network instead: a performance counter, results are the same */
 } epx_timing;
 
 typedef struct epx_session epx_session;

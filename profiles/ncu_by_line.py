@@ -8,7 +8,10 @@ from collections import Counter, defaultdict
 rep, kre, mangled, units = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kre], capture_output=True, text=True).stdout
+# NCU_SKIP=<k>: take the (k+1)-th captured launch of the report instead of the first one that matches the regex
+skip = os.environ.get('NCU_SKIP')
+sel = ['--launch-skip', skip, '--launch-count', '1'] if skip else ['--kernel-name', 'regex:' + kre]
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = next(i for i, r in enumerate(rows) if 'Source' in r and 'Instructions Executed' in r)
 hdr = rows[h]; ia, isrc, ie, iss = hdr.index('Address'), hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('# Samples')
