@@ -575,7 +575,8 @@ __global__ void __launch_bounds__(128) k_gene_tails(GeneTestParams p)
 }
 
 /* k_probe_rank, one warp per referenced probe */
-template <int EPS> __host__ __device__ constexpr int rank_warps() { return SORT_WARPS; }
+template <int EPS> __host__ __device__ constexpr bool rank_by_buckets();
+template <int EPS> __host__ __device__ constexpr int rank_warps() { return rank_by_buckets<EPS>() ? 4 : SORT_WARPS; }
 /* per-warp shared memory: 2 row stages of 32*EPS doubles | 2 mbarriers | 32*EPS uint16 of sort scratch */
 /* rows of 257..512 values are placed by buckets before a short network (WarpSort::order_bucket) */
 template <int EPS> __host__ __device__ constexpr bool rank_by_buckets() { return EPS == 16; }
@@ -633,7 +634,7 @@ __device__ __noinline__ void pick_reference_warp(const RankParams &p, const int 
  * Two instantiations of one loop rather than one kernel for both: with both row kinds in one kernel its code outgrew
  * the instruction cache and every row paid for it (measured: 0.93 -> 1.15 ms). */
 template <int EPS, bool GENES>
-__global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 && !rank_by_buckets<EPS>() ? 3 : 2)) k_probe_rank_w(RankParams p)
+__global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_buckets<EPS>() ? 96 : (EPS <= 16 ? 80 : 128)) k_probe_rank_w(RankParams p)
 {
     constexpr int RW = rank_warps<EPS>();
     constexpr int N = 32 * EPS;
@@ -655,8 +656,8 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 && !rank_by
     const bool bulk = !GENES && ((((uintptr_t)p.meth) | ((uintptr_t)p.ld * 8u)) & 15u) == 0 && p.ld <= N;
     const uint32_t rowb = (uint32_t)p.ld * 8u;
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
-    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_ord), *s_srt = s_cnt + WarpSort<EPS>::NB; /* BUCKETS: counters | slots */
-    if constexpr (BUCKETS) { for (int i = lane; i < WarpSort<EPS>::NB; i += 32) s_cnt[i] = 0u; }
+    unsigned *s_bkt = reinterpret_cast<unsigned *>(s_ord); /* BUCKETS: counters, then slots */
+    if constexpr (BUCKETS) s_bkt[WarpSort<EPS>::NB + lane] = 0u;
     __syncwarp();
     uint32_t ph0 = 0, ph1 = 0;
     int fill = 0, use = 0;
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32, (EPS <= 16 && !rank_by
                 const int s = lane + 32 * e;
                 x[e] = row[(2 * e < EPS || s < n) ? s : 0];
             }
-            WarpSort<EPS>::order_bucket(x, n, lane, s_cnt, s_srt, [&](int i) { return row[i]; }, GENES, p.one, out, p.full_rows);
+            WarpSort<EPS>::order_bucket(x, n, lane, s_bkt, [&](int i) { return row[i]; }, GENES, p.one, out, p.full_rows);
         } else {
         unsigned khi[EPS], klo[EPS];
         if (!gene) {

@@ -222,15 +222,23 @@ template <int EPS> struct WarpSort {
     static constexpr int NB = 32 * BK;             /* buckets */
     static constexpr int QSH = 31 - IDXB - (EPS == 8 ? 9 : EPS == 16 ? 10 : 11); /* q >> QSH = bucket; NB << QSH < 2^(31 - IDXB) */
     static constexpr unsigned QMAX = (unsigned)NB << QSH;
-    static constexpr size_t BUCKET_SMEM = (size_t)2 * NB * 4; /* counters | padded slots (later the 16-bit scratch of finish()) */
+    static constexpr size_t BUCKET_SMEM = (size_t)(NB + 32) * 4; /* counters, later the padded slots, later the 16-bit scratch of
+                                                                  * finish(); + one idle counter per lane for the pad slots */
 
+    /* x[e]: value of sample lane + 32*e (any real value of the row for the slots past n). 16*EPS < n <= 32*EPS (a row
+     * takes the smallest instantiation that holds it), so only the upper half of the slots can be pads. */
     template <typename ValueOf>
-    __device__ __forceinline__ static void order_bucket(const double (&x)[EPS], const int n, const int lane, unsigned *s_cnt,
-                                                        unsigned *s_srt, ValueOf value, const bool DESC, const unsigned one,
+    __device__ __forceinline__ static void order_bucket(const double (&x)[EPS], const int n, const int lane, unsigned *s_bkt,
+                                                        ValueOf value, const bool DESC, const unsigned one,
                                                         unsigned short (&out)[EPS], int32_t *full_rows)
     {
         static_assert(EPS >= 8, "bucket placement is instantiated for 8, 16 and 32 values per lane");
         static_assert(((unsigned long long)NB << QSH) < (1ull << (31 - IDXB)), "q must fit below the pad flag");
+        {   /* clean counters (the previous row left its slots, or finish() its scratch, in them) */
+            uint4 *c4 = reinterpret_cast<uint4 *>(s_bkt + lane * BK);
+#pragma unroll
+            for (int i = 0; i < BK / 4; i++) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         /* range of the row from the high words of its keys (order-preserving transform of key_halves) */
         unsigned tmin = 0xffffffffu, tmax = 0u;
 #pragma unroll
@@ -271,23 +279,29 @@ template <int EPS> struct WarpSort {
         if (!(fabs(scale) < 1e300)) scale = 0.0; /* constant row (span 0), or a span beyond the exponent range: one bucket, settled by finish() */
         const double c0 = fma(-first, scale, 6755399441055744.0 + (double)QOFF); /* 2^52 + 2^51: the low word of the sum is the integer */
 
-        const uint32_t cnt_a = smem_u32(s_cnt);
+        const uint32_t cnt_a = smem_u32(s_bkt), idle_a = cnt_a + 4u * (unsigned)(NB + lane);
         unsigned v[EPS];
-        uint32_t ba[EPS]; /* shared-memory address of each value's counter */
+        uint32_t ba[EPS]; /* shared-memory address of each value's counter; later its slot */
+        __syncwarp();
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
             const int s = lane + 32 * e;
             unsigned q = (unsigned)__double2loint(fma(x[e], scale, c0));
             q = min(q, QMAX - 1u); /* memory safety only: a q out of range means the row fails the check below */
-            const bool real = (2 * e < EPS && n > 16 * EPS) || s < n;
-            v[e] = real ? ((q << IDXB) | (unsigned)s) : (0x80000000u | ((unsigned)(s - n) << IDXB) | (unsigned)n);
+            v[e] = (q << IDXB) | (unsigned)s;
             ba[e] = cnt_a + ((q >> (QSH - 2)) & ~3u);
-            smem_inc_if(ba[e], real);
+            unsigned inc = 1u;
+            if (2 * e >= EPS && s >= n) { /* a pad: its word, and a counter of its own that nobody reads */
+                v[e] = 0x80000000u | ((unsigned)(s - n) << IDXB) | (unsigned)n;
+                ba[e] = idle_a;
+                inc = 0u;
+            }
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ba[e]), "r"(inc) : "memory");
         }
         __syncwarp();
         /* exclusive scan of the counters: BK consecutive ones per lane */
         {
-            uint4 *c4 = reinterpret_cast<uint4 *>(s_cnt + lane * BK);
+            uint4 *c4 = reinterpret_cast<uint4 *>(s_bkt + lane * BK);
             unsigned c[BK];
 #pragma unroll
             for (int i = 0; i < BK / 4; i++) {
@@ -310,29 +324,28 @@ template <int EPS> struct WarpSort {
             for (int i = 0; i < BK / 4; i++) c4[i] = make_uint4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
         }
         __syncwarp();
-        /* every value to the next free slot of its bucket; pads straight to their final slots. Slot k lives at word
-         * k + 4 * (k / EPS): the same padded spacing as the counters, for the 16-byte reads below */
-        {
-            const uint32_t srt_a = smem_u32(s_srt);
+        /* every value draws the next free slot of its bucket (pads keep their own slot number) ... */
 #pragma unroll
-            for (int e = 0; e < EPS; e++) {
-                const int s = lane + 32 * e;
-                const bool real = (2 * e < EPS && n > 16 * EPS) || s < n;
-                const unsigned pos = smem_take_if(ba[e], real, (unsigned)s);
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(srt_a + 4u * pos + 16u * (pos / EPS)), "r"(v[e]) : "memory");
-            }
+        for (int e = 0; e < EPS; e++) {
+            const int s = lane + 32 * e;
+            unsigned pos;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(ba[e]) : "memory");
+            if (2 * e >= EPS && s >= n) pos = (unsigned)s;
+            ba[e] = cnt_a + 4u * pos + 16u * (pos / EPS);
         }
         __syncwarp();
+        /* ... and moves there, over the counters, which are no longer needed. Slot k lives at word k + 4 * (k / EPS):
+         * the same padded spacing as the counters, for the 16-byte reads below */
+#pragma unroll
+        for (int e = 0; e < EPS; e++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ba[e]), "r"(v[e]) : "memory");
+        __syncwarp();
         {
-            const uint4 *w4 = reinterpret_cast<const uint4 *>(s_srt + lane * BK);
+            const uint4 *w4 = reinterpret_cast<const uint4 *>(s_bkt + lane * BK);
 #pragma unroll
             for (int i = 0; i < EPS / 4; i++) {
                 const uint4 w = w4[i];
                 v[4 * i] = w.x; v[4 * i + 1] = w.y; v[4 * i + 2] = w.z; v[4 * i + 3] = w.w;
             }
-            uint4 *c4 = reinterpret_cast<uint4 *>(s_cnt + lane * BK);
-#pragma unroll
-            for (int i = 0; i < BK / 4; i++) c4[i] = make_uint4(0u, 0u, 0u, 0u); /* counters clean for the next row */
         }
         __syncwarp();
         const unsigned minus1 = 0u - one;
@@ -366,7 +379,7 @@ template <int EPS> struct WarpSort {
                 sort(v, lane, one, minus1);
             }
         }
-        finish(v, n, lane, reinterpret_cast<unsigned short *>(s_srt), value, DESC, out);
+        finish(v, n, lane, reinterpret_cast<unsigned short *>(s_bkt), value, DESC, out);
     }
 
     /* v[] sorted (position k = lane*EPS + r) -> out[]: sample indices with tie marks; neighbours that share a coarse
