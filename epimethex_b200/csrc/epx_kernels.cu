@@ -580,9 +580,12 @@ template <int EPS> __host__ __device__ constexpr int rank_warps() { return rank_
 /* per-warp shared memory: 2 row stages of 32*EPS doubles | 2 mbarriers | 32*EPS uint16 of sort scratch */
 /* rows of 257..512 values are placed by buckets before a short network (WarpSort::order_bucket) */
 template <int EPS> __host__ __device__ constexpr bool rank_by_buckets() { return EPS == 16; }
+/* 513..1024 values: ONE row stage per warp (8 KB); it is refilled as soon as the row's words are built, and the few
+ * values finish() needs for ties come from global memory (L2: the row was just read) */
+template <int EPS> __host__ __device__ constexpr int rank_stages() { return rank_by_buckets<EPS>() && EPS == 32 ? 1 : 2; }
 template <int EPS> __host__ __device__ constexpr size_t rank_warp_smem()
 {
-    return (size_t)2 * 32 * EPS * 8 + 16 + (rank_by_buckets<EPS>() ? WarpSort<EPS>::BUCKET_SMEM : (size_t)32 * EPS * 2);
+    return (size_t)rank_stages<EPS>() * 32 * EPS * 8 + 16 + (rank_by_buckets<EPS>() ? WarpSort<EPS>::BUCKET_SMEM : (size_t)32 * EPS * 2);
 }
 
 /* the bin.var reference gene and its group sizes (R/EpimethexAnalysis.R:134-139), by ONE warp: the last warp to leave
@@ -634,17 +637,18 @@ __device__ __noinline__ void pick_reference_warp(const RankParams &p, const int 
  * Two instantiations of one loop rather than one kernel for both: with both row kinds in one kernel its code outgrew
  * the instruction cache and every row paid for it (measured: 0.93 -> 1.15 ms). */
 template <int EPS, bool GENES>
-__global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_buckets<EPS>() ? 96 : (EPS <= 16 ? 80 : 128)) k_probe_rank_w(RankParams p)
+__global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(EPS >= 32 ? 128 : (rank_by_buckets<EPS>() ? 96 : 80)) k_probe_rank_w(RankParams p)
 {
     constexpr int RW = rank_warps<EPS>();
     constexpr int N = 32 * EPS;
     constexpr bool BUCKETS = rank_by_buckets<EPS>();
+    constexpr int STAGES = rank_stages<EPS>();
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
     unsigned char *base = smem + (size_t)warp * rank_warp_smem<EPS>();
     double *stage0 = (double *)base;                         /* stage s at stage0 + s * N */
-    uint64_t *bar = (uint64_t *)(base + (size_t)2 * N * 8);
-    unsigned short *s_ord = (unsigned short *)(base + (size_t)2 * N * 8 + 16);
+    uint64_t *bar = (uint64_t *)(base + (size_t)STAGES * N * 8);
+    unsigned short *s_ord = (unsigned short *)(base + (size_t)STAGES * N * 8 + 16);
     const int nw = (int)gridDim.x * RW;
     const int64_t G = GENES ? p.genes.G : 0, total = GENES ? G : p.U;
     int32_t *const queue = GENES ? p.gene_queue : p.queue;
@@ -674,7 +678,7 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_bu
             for (int e = 0; e < EPS; e++) if (lane + 32 * e < n) dst[lane + 32 * e] = __ldg(row + lane + 32 * e);
             by_bulk &= ~(1u << fill);
         }
-        fill ^= 1;
+        if (STAGES == 2) fill ^= 1;
     };
     /* Rows are handed out by a ticket counter (tickets 0 .. G-1: expression rows, then the referenced probes): rows
      * with tied or nearly tied values take the longer exact path, and a static split of a one-wave grid lost 6 % to
@@ -687,21 +691,31 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_bu
         if (lane == 0) nslot = nw + atomicAdd(queue, 1);
         const int64_t next = __shfl_sync(FULL, nslot, 0);
         __syncwarp(); /* every lane is done with the stage about to be refilled */
-        if (next < total) issue(next);
+        if (STAGES == 2 && next < total) issue(next);
         const double *row = stage0 + (use ? N : 0);
         if ((by_bulk >> use) & 1u) { if (use == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; } }
         else __syncwarp();
-        use ^= 1;
+        if (STAGES == 2) use ^= 1;
         constexpr bool gene = GENES; /* descending order for expression rows (R/EpimethexAnalysis.R:117-122) */
         unsigned short out[EPS];
-        if constexpr (BUCKETS) {
+        const double *vals = row; /* the row's values after the sort (expression rows: sums, centring) */
+        if constexpr (BUCKETS && STAGES == 1) {
+            /* one stage: the row is read twice from shared memory while its words are built, then the stage goes to
+             * the next row's copy; ties are settled on values fetched from global memory */
+            const double *grow = GENES ? p.genes.expr + slot * n : p.meth + (int64_t)__ldg(p.uniq_probe + slot) * p.ld;
+            WarpSort<EPS>::order_bucket([&](int e) { const int s = lane + 32 * e; return row[(2 * e < EPS || s < n) ? s : 0]; },
+                                        [&]() { __syncwarp(); if (next < total) issue(next); }, n, lane, s_bkt,
+                                        [&](int i) { return __ldg(grow + i); }, GENES, p.one, out, p.full_rows);
+            vals = grow;
+        } else if constexpr (BUCKETS) {
             double x[EPS];
 #pragma unroll
             for (int e = 0; e < EPS; e++) {
                 const int s = lane + 32 * e;
                 x[e] = row[(2 * e < EPS || s < n) ? s : 0];
             }
-            WarpSort<EPS>::order_bucket(x, n, lane, s_bkt, [&](int i) { return row[i]; }, GENES, p.one, out, p.full_rows);
+            WarpSort<EPS>::order_bucket([&](int e) { return x[e]; }, []() {}, n, lane, s_bkt, [&](int i) { return row[i]; }, GENES,
+                                        p.one, out, p.full_rows);
         } else {
         unsigned khi[EPS], klo[EPS];
         if (!gene) {
@@ -752,7 +766,7 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_bu
             uint8_t *lab8 = gp.lab8 + g * gp.ldl;
             double sum = 0.0;
 #pragma unroll
-            for (int e = 0; e < EPS; e++) { const int s = lane + 32 * e; if (s < n) sum += row[s]; }
+            for (int e = 0; e < EPS; e++) { const int s = lane + 32 * e; if (s < n) sum += vals[s]; }
 #pragma unroll
             for (int r = 0; r < EPS; r++) {
                 const int k = lane * EPS + r;
@@ -770,7 +784,7 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_bu
             for (int e = 0; e < EPS; e++) {
                 const int s = lane + 32 * e;
                 if (s < n) {
-                    const double d = row[s] - mean;
+                    const double d = vals[s] - mean;
                     gp.xc[g * gp.ldx + s] = d;
                     sxx += d * d;
                     sxc += d;
@@ -807,19 +821,22 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(rank_by_bu
  * many instructions as a 512-value one and needs 128 registers), and one merge-path pass — lane L produces outputs
  * [32L, 32L + 32) after a binary search for its split point; the left half wins ties, which keeps equal values in
  * ascending sample index — writes the order row with its tie marks. Same output as k_probe_rank_w<32>. */
-constexpr int RANK2_WARPS = 6;
-constexpr int RANK2_WARP_SMEM = 1024 * 8 + 1024 * 2 + 1024 * 2; /* values | run indices | merged (first the sort's scratch) */
+constexpr int RANK2_WARPS = 4;
+/* values | run indices | merged; the bucket scratch of the two half sorts lies over `merged` and the tail behind it */
+constexpr int RANK2_WARP_SMEM = 1024 * 8 + 1024 * 2 + (int)WarpSort<16>::BUCKET_SMEM;
+static_assert(WarpSort<16>::BUCKET_SMEM >= 1024 * 2, "the merged row must fit the scratch it shares");
 
-__global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParams p)
+__global__ void __launch_bounds__(RANK2_WARPS * 32, 4) k_probe_rank_w2(RankParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = p.n;
     double *vals = (double *)(smem + (size_t)warp * RANK2_WARP_SMEM);
     unsigned short *runs = (unsigned short *)(vals + 1024);
     unsigned short *merged = runs + 1024;
-    unsigned short *scratch = merged; /* WarpSort's 512 entries of scratch are dead before the merge starts */
+    unsigned short *scratch = merged; /* WarpSort's scratch is dead before the merge starts */
     const int nw = (int)gridDim.x * RANK2_WARPS;
-    const int la = 512, lb = n - 512;
+    const int la = (n + 1) / 2, lb = n - la; /* two halves of 257..512 values (n = 513: 257 + 256) */
+    if (lane < 32) reinterpret_cast<unsigned *>(scratch)[WarpSort<16>::NB + lane] = 0u; /* idle counters of order_bucket */
     int64_t slot = (int64_t)blockIdx.x * RANK2_WARPS + warp;
     while (slot < p.U) {
         const double *row = p.meth + (int64_t)p.uniq_probe[slot] * p.ld;
@@ -832,13 +849,21 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
         __syncwarp();
 #pragma unroll 1
         for (int c = 0; c < 2; c++) {
-            const int base = 512 * c, nc = c == 0 ? la : lb;
-            unsigned khi[16], klo[16];
-#pragma unroll
-            for (int e = 0; e < 16; e++) key_halves(vals[base + min(lane + 32 * e, nc - 1)], khi[e], klo[e]);
+            const int base = c == 0 ? 0 : la, nc = c == 0 ? la : lb;
             unsigned short out[16];
-            WarpSort<16>::template order<false>(khi, klo, nc, lane, scratch, [&](int i) { return vals[base + i]; },
-                                                p.one, out);
+            if (nc > 256) { /* bucket placement + short network (WarpSort::order_bucket) */
+                double x[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) x[e] = vals[base + min(lane + 32 * e, nc - 1)];
+                WarpSort<16>::order_bucket([&](int e) { return x[e]; }, []() {}, nc, lane, reinterpret_cast<unsigned *>(scratch),
+                                           [&](int i) { return vals[base + i]; }, false, p.one, out, p.full_rows);
+            } else { /* n = 513 only: the 256-value half */
+                unsigned khi[16], klo[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) key_halves(vals[base + min(lane + 32 * e, nc - 1)], khi[e], klo[e]);
+                WarpSort<16>::template order<false>(khi, klo, nc, lane, scratch, [&](int i) { return vals[base + i]; },
+                                                    p.one, out);
+            }
 #pragma unroll
             for (int r = 0; r < 16; r++) {
                 const int k = lane * 16 + r;
@@ -847,7 +872,7 @@ __global__ void __launch_bounds__(RANK2_WARPS * 32, 3) k_probe_rank_w2(RankParam
         }
         __syncwarp();
         /* merge path: of the first d outputs, i come from A (A wins ties) */
-        const unsigned short *A = runs, *B = runs + 512;
+        const unsigned short *A = runs, *B = runs + la;
         /* 33 outputs per lane, not 32: with 32 the lanes' 16-bit stores (and their reads of the runs) start 64 bytes
          * apart and fall on two banks */
         const int d = min(lane * 33, n), d_end = min(d + 33, n);
@@ -1727,7 +1752,7 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
         }
         return cudaGetLastError();
     }
-    if (p.n > 512 && (p.ldo & 7) == 0 && ((uintptr_t)p.ord & 15) == 0) { /* two 512-value halves + one merge per warp */
+    if (p.n > 512 && !rank_by_buckets<32>() && (p.ldo & 7) == 0 && ((uintptr_t)p.ord & 15) == 0) { /* two 512-value halves + one merge per warp */
         static std::atomic<int> per_sm2{0}; /* written by one host thread per device (epx_multi_*): the value is the same */
         const size_t smem = (size_t)RANK2_WARPS * RANK2_WARP_SMEM;
         if (per_sm2 == 0) {

@@ -225,10 +225,13 @@ template <int EPS> struct WarpSort {
     static constexpr size_t BUCKET_SMEM = (size_t)(NB + 32) * 4; /* counters, later the padded slots, later the 16-bit scratch of
                                                                   * finish(); + one idle counter per lane for the pad slots */
 
-    /* x[e]: value of sample lane + 32*e (any real value of the row for the slots past n). 16*EPS < n <= 32*EPS (a row
-     * takes the smallest instantiation that holds it), so only the upper half of the slots can be pads. */
-    template <typename ValueOf>
-    __device__ __forceinline__ static void order_bucket(const double (&x)[EPS], const int n, const int lane, unsigned *s_bkt,
+    /* xof(e): value of sample lane + 32*e (any real value of the row for the slots past n), asked for twice per slot
+     * (registers, or the staged row); x_done() is called once the last of them has been read (a caller with one row
+     * stage refills it there). value(i): the value of sample i, for the few positions finish() has to settle.
+     * 16*EPS < n <= 32*EPS (a row takes the smallest instantiation that holds it), so only the upper half of the slots
+     * can be pads. */
+    template <typename XOf, typename XDone, typename ValueOf>
+    __device__ __forceinline__ static void order_bucket(XOf xof, XDone x_done, const int n, const int lane, unsigned *s_bkt,
                                                         ValueOf value, const bool DESC, const unsigned one,
                                                         unsigned short (&out)[EPS], int32_t *full_rows)
     {
@@ -243,7 +246,7 @@ template <int EPS> struct WarpSort {
         unsigned tmin = 0xffffffffu, tmax = 0u;
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
-            const int h = __double2hiint(x[e]);
+            const int h = __double2hiint(xof(e));
             const unsigned t = (unsigned)h ^ ((unsigned)(h >> 31) | 0x80000000u);
             tmin = min(tmin, t);
             tmax = max(tmax, t);
@@ -256,7 +259,7 @@ template <int EPS> struct WarpSort {
 #pragma unroll
             for (int e = 0; e < EPS; e++) {
                 unsigned hi, lo;
-                key_halves(x[e], hi, lo);
+                key_halves(xof(e), hi, lo);
                 if (hi <= tmin) lmin = min(lmin, lo);
                 if (hi >= tmax) lmax = max(lmax, lo);
             }
@@ -286,7 +289,7 @@ template <int EPS> struct WarpSort {
 #pragma unroll
         for (int e = 0; e < EPS; e++) {
             const int s = lane + 32 * e;
-            unsigned q = (unsigned)__double2loint(fma(x[e], scale, c0));
+            unsigned q = (unsigned)__double2loint(fma(xof(e), scale, c0));
             q = min(q, QMAX - 1u); /* memory safety only: a q out of range means the row fails the check below */
             v[e] = (q << IDXB) | (unsigned)s;
             ba[e] = cnt_a + ((q >> (QSH - 2)) & ~3u);
@@ -298,6 +301,7 @@ template <int EPS> struct WarpSort {
             }
             asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(ba[e]), "r"(inc) : "memory");
         }
+        x_done();
         __syncwarp();
         /* exclusive scan of the counters: BK consecutive ones per lane */
         {
