@@ -17,6 +17,7 @@
 #include "epx_warpsort.cuh"
 #include "epx_ctasort.cuh"
 #include "epx_pair.cuh"
+#include "epx_ctabucket.cuh"
 #include "epx_group.cuh"
 
 namespace epx {
@@ -282,13 +283,14 @@ __global__ void __launch_bounds__(128) k_gene_tests(GeneTestParams p)
 
 /* ============================================================ k_probe_rank */
 
-__global__ void __launch_bounds__(CTASORT_THREADS, 2) k_probe_rank(RankParams p)
+/* long rows (n > 1024): ctab_threads(n) threads, bucket placement (epx_ctabucket.cuh); a row whose placement fails its
+ * check goes through the merge sort of epx_ctasort.cuh in the same buffers */
+__global__ void __maxnreg__(80) k_probe_rank(RankParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = p.n;
     double *s_val = (double *)smem;
-    unsigned short *s_a = (unsigned short *)(s_val + ((n + 1) & ~1));
-    unsigned short *s_b = s_a + ctasort_entries(n);
+    unsigned *region = (unsigned *)(s_val + ((n + 1) & ~1));
     /* the row comes in as ONE bulk copy (cp.async.bulk + mbarrier) when it is 16-byte aligned: a per-thread loop of
      * loads and shared stores ran as ~35 dependent round trips to DRAM and took a quarter of the kernel */
     __shared__ __align__(8) uint64_t bar;
@@ -307,8 +309,13 @@ __global__ void __launch_bounds__(CTASORT_THREADS, 2) k_probe_rank(RankParams p)
             for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
         }
         __syncthreads();
-        /* n > 1024 here, so there is a last merge pass and it leaves the tie marks in place */
-        const unsigned short *ord = cta_sort_row<false, true>(s_val, n, s_a, s_b, p.one);
+        const unsigned short *ord = cta_bucket_order<false>(s_val, n, region, p.one, p.full_rows);
+        if (!ord) {
+            unsigned short *s_a = (unsigned short *)region, *s_b = s_a + ctasort_entries(n);
+            __syncthreads();
+            /* n > 1024 here, so there is a last merge pass and it leaves the tie marks in place */
+            ord = cta_sort_row<false, true>(s_val, n, s_a, s_b, p.one);
+        }
         uint16_t *o = p.ord + slot * p.ldo;
         if ((p.ldo & 7) == 0 && (((uintptr_t)p.ord) & 15u) == 0) { /* 16 bytes per load and store */
             for (int k0 = threadIdx.x * 8; k0 < p.ldo; k0 += blockDim.x * 8) {
@@ -1742,13 +1749,16 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
     if (p.U <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
         {
-            const size_t smem = sort_smem(p.n);
+            const int threads = ctab_threads(p.n);
+            const size_t smem = (size_t)((p.n + 1) & ~1) * 8 + ctab_smem(p.n);
             int per_sm = (int)((226 * 1024) / (smem + 1024));
-            if (per_sm > 2) per_sm = 2;
+            const int by_regs = 65536 / (80 * ((threads + 127) / 128 * 128)), by_threads = 2048 / threads; /* registers come in units of four warps */
+            if (per_sm > by_regs) per_sm = by_regs;
+            if (per_sm > by_threads) per_sm = by_threads;
             if (per_sm < 1) per_sm = 1;
             int64_t grid = (int64_t)sm_count * per_sm;
             if (grid > p.U) grid = p.U;
-            k_probe_rank<<<(unsigned)grid, ctasort_threads(p.n), smem, st>>>(p);
+            k_probe_rank<<<(unsigned)grid, threads, smem, st>>>(p);
         }
         return cudaGetLastError();
     }
