@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <string>
@@ -101,7 +102,8 @@ struct epx_session {
     size_t staging_bytes = 0;
     /* pooled probe groups (epx_session_run_groups) */
     const int32_t *h_probe_idx = nullptr, *h_pair_gene = nullptr; /* host copies of the index (in `staging`), to validate group lists */
-    std::vector<int32_t> slot_of;                   /* [P] order row of a methylation row while an index is built, else -1 */
+    std::vector<int32_t> slot_of;                   /* [P] order row of a referenced methylation row (valid for the rows of the current index) */
+    std::vector<uint8_t> ref_mark;                  /* [P] scratch of set_index: row is referenced; all 0 between calls */
     std::vector<int64_t> h_row_ptr;
     DevBuf<double> upload_stage;                    /* 2 x 64 MB: flat H2D chunks before re-spacing */
     cudaEvent_t ev_up[3] = { nullptr, nullptr, nullptr };
@@ -405,8 +407,9 @@ int epx_session_set_methylation_device(epx_session *s, const double *d_rows, int
     return EPX_OK;
 }
 
-int epx_session_set_expression(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples, int is_device,
-                               char *err, size_t errlen)
+/* the expression upload in two halves, so that epx_analyze can build the index on the host while the copy runs */
+static int set_expression_begin(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples, int is_device,
+                                char *err, size_t errlen)
 {
     if (!s || !expr || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad expression arguments");
     int rc = check_samples(s, n_samples, err, errlen);
@@ -421,11 +424,24 @@ int epx_session_set_expression(epx_session *s, const double *expr, int64_t n_gen
     EPX_CUDA(cudaMemcpyAsync(s->expr.p, expr, (size_t)(n_genes * n_samples) * 8,
                              is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->stream));
     EPX_CUDA(launch_check_finite(s->expr.p, n_genes, n_samples, n_samples, s->first_bad.p, s->stream));
+    return EPX_OK;
+}
+
+static int set_expression_finish(epx_session *s, int64_t n_genes, int64_t n_samples, char *err, size_t errlen)
+{
     EPX_CUDA(cudaStreamSynchronize(s->stream));
-    rc = finite_check_result(s, "expression", "gene", n_samples, err, errlen);
+    int rc = finite_check_result(s, "expression", "gene", n_samples, err, errlen);
     if (rc) return rc;
     s->G = n_genes; s->n = n_samples;
     return EPX_OK;
+}
+
+int epx_session_set_expression(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples, int is_device,
+                               char *err, size_t errlen)
+{
+    int rc = set_expression_begin(s, expr, n_genes, n_samples, is_device, err, errlen);
+    if (rc) return rc;
+    return set_expression_finish(s, n_genes, n_samples, err, errlen);
 }
 
 int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
@@ -459,40 +475,89 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     }
     int32_t *h_pi = (int32_t *)s->staging, *pair_slot = h_pi + Np, *pair_gene = pair_slot + Np, *uniq = pair_gene + Np;
     Item *items = (Item *)(((uintptr_t)(uniq + Np) + 15) & ~(uintptr_t)15);
-    if (s->slot_of.size() < (size_t)s->P) s->slot_of.assign((size_t)s->P, -1);
-    int32_t *slot_of = s->slot_of.data();
-    size_t n_uniq = 0, n_items = 0;
     /* work items of the pair kernel: up to ITEM_PAIRS consecutive pairs of one gene. Small jobs (a 1000-gene
      * range is ~23 k pairs for ~2400 resident warps) get smaller items so that every warp has several. */
     int64_t item_pairs = Np / ((int64_t)s->sm_count * 16 * 4);
     if (item_pairs < 4) item_pairs = 4;
     if (item_pairs > ITEM_PAIRS) item_pairs = ITEM_PAIRS;
+    /* The slot (order row) of a referenced probe is its rank among the referenced probes, by row number: the rank kernel
+     * then reads the matrix front to back, and the three passes below -- mark and copy, number the marked rows, look the
+     * slots up -- split over host threads (first-appearance numbering was one serial pass of ~4 ms for 474,611 pairs,
+     * on every call: the reference is called once per gene range, README.md:90). */
+    if (s->slot_of.size() < (size_t)s->P) s->slot_of.assign((size_t)s->P, -1);
+    if (s->ref_mark.size() < (size_t)s->P) s->ref_mark.assign((size_t)s->P, 0);
+    int32_t *slot_of = s->slot_of.data();
+    uint8_t *ref = s->ref_mark.data();
+    const int64_t P = s->P;
+    int nt = (int)std::thread::hardware_concurrency();
+    if (nt > 8) nt = 8;
+    if (nt < 1 || Np < 65536) nt = 1;
+    std::vector<int64_t> cnt((size_t)nt + 1, 0), bad_at_t((size_t)nt, -1);
+    std::vector<int> bad_code_t((size_t)nt, 0);
+    std::atomic<int> arrived{0};
+    auto barrier = [&](int phase) { /* all nt workers meet here; phases are numbered 1, 2, .. */
+        arrived.fetch_add(1, std::memory_order_acq_rel);
+        while (arrived.load(std::memory_order_acquire) < phase * nt) std::this_thread::yield();
+    };
+    auto work = [&](int tid) {
+        /* pass 1: this worker's genes (cut at equal pair counts): checks, host copies, marks */
+        const int64_t *gb = std::lower_bound(row_ptr, row_ptr + n_genes, Np * tid / nt);
+        const int64_t *ge = tid + 1 == nt ? row_ptr + n_genes : std::lower_bound(row_ptr, row_ptr + n_genes, Np * (tid + 1) / nt);
+        for (int64_t g = gb - row_ptr; g < ge - row_ptr && !bad_code_t[tid]; g++) {
+            const int64_t b = row_ptr[g], e = row_ptr[g + 1];
+            if (b < 0 || e < b || e > Np) { bad_code_t[tid] = 1; bad_at_t[tid] = g; break; }
+            for (int64_t j = b; j < e; j++) {
+                const int32_t pi = probe_idx[j];
+                h_pi[j] = pi;
+                pair_gene[j] = (int32_t)g;
+                if (pi >= P) { bad_code_t[tid] = 2; bad_at_t[tid] = j; break; }
+                if (pi >= 0) __atomic_store_n(&ref[pi], (uint8_t)1, __ATOMIC_RELAXED); /* several workers may store the same 1 */
+            }
+        }
+        barrier(1);
+        /* pass 2: number the marked rows of this worker's slice of the matrix */
+        const int64_t p0 = P * tid / nt, p1 = P * (tid + 1) / nt;
+        int64_t c = 0;
+        for (int64_t q = p0; q < p1; q++) c += ref[q];
+        cnt[(size_t)tid + 1] = c;
+        barrier(2);
+        int64_t base = 0;
+        for (int k = 0; k <= tid; k++) base += cnt[(size_t)k];
+        for (int64_t q = p0; q < p1; q++)
+            if (ref[q]) { ref[q] = 0; slot_of[q] = (int32_t)base; uniq[base++] = (int32_t)q; }
+        barrier(3);
+        /* pass 3: the slot of every pair */
+        const int64_t j0 = Np * tid / nt, j1 = Np * (tid + 1) / nt;
+        for (int64_t j = j0; j < j1; j++) { const int32_t pi = h_pi[j]; pair_slot[j] = (pi < 0 || pi >= P) ? -1 : slot_of[pi]; }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 1; k < nt; k++) th.emplace_back(work, k);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    size_t n_uniq = 0, n_items = 0;
+    for (int k = 1; k <= nt; k++) n_uniq += (size_t)cnt[(size_t)k];
     int bad_code = 0;
     int64_t bad_at = 0;
-    for (int64_t g = 0; g < n_genes && !bad_code; g++) {
+    for (int k = 0; k < nt && !bad_code; k++) if (bad_code_t[k]) { bad_code = bad_code_t[k]; bad_at = bad_at_t[k]; }
+    if (!bad_code) { /* the genes must tile [0, Np) in order: the workers' slices rely on it */
+        for (int64_t g = 0; g < n_genes; g++) if (row_ptr[g + 1] < row_ptr[g]) { bad_code = 1; bad_at = g; break; }
+    }
+    if (bad_code) {
+        std::fill(s->ref_mark.begin(), s->ref_mark.end(), (uint8_t)0);
+        s->G_index = -1;                                          /* the staging block no longer mirrors a valid index */
+        if (bad_code == 1) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)bad_at);
+        return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d >= n_probes %lld", (long long)bad_at, probe_idx[bad_at], (long long)s->P);
+    }
+    for (int64_t g = 0; g < n_genes; g++) {
         const int64_t b = row_ptr[g], e = row_ptr[g + 1];
-        if (e < b || e > Np) { bad_code = 1; bad_at = g; break; }
-        for (int64_t j = b; j < e; j++) {
-            const int32_t pi = probe_idx[j];
-            h_pi[j] = pi;
-            pair_gene[j] = (int32_t)g;
-            if (pi >= s->P) { bad_code = 2; bad_at = j; break; }
-            if (pi < 0) { pair_slot[j] = -1; continue; }
-            if (slot_of[pi] < 0) { slot_of[pi] = (int32_t)n_uniq; uniq[n_uniq++] = pi; }
-            pair_slot[j] = slot_of[pi];
-        }
         for (int64_t j = b; j < e; j += item_pairs) {
             Item it;
             it.gene = (int32_t)g; it.begin = (int32_t)j;
             it.count = (int32_t)((e - j) < item_pairs ? (e - j) : item_pairs); it.pad = 0;
             items[n_items++] = it;
         }
-    }
-    for (size_t u = 0; u < n_uniq; u++) slot_of[uniq[u]] = -1;   /* the table is clean again for the next index */
-    if (bad_code) {
-        s->G_index = -1;                                          /* the staging block no longer mirrors a valid index */
-        if (bad_code == 1) return fail(err, errlen, EPX_EINVAL, "row_ptr is not monotone at gene %lld", (long long)bad_at);
-        return fail(err, errlen, EPX_EINVAL, "probe_idx[%lld] = %d >= n_probes %lld", (long long)bad_at, probe_idx[bad_at], (long long)s->P);
     }
     EPX_CUDA(s->probe_idx.reserve((size_t)Np));
     EPX_CUDA(s->pair_slot.reserve((size_t)Np));
@@ -936,9 +1001,12 @@ int epx_session_fetch_groups(epx_session *s, epx_group_result *out, void *stream
 int epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples, const int64_t *row_ptr,
                 const int32_t *probe_idx, const epx_options *opt, epx_result *out, char *err, size_t errlen)
 {
-    int rc = epx_session_set_expression(s, expr, n_genes, n_samples, 0, err, errlen);
+    /* the expression matrix is on its way to the device while the host builds the index */
+    int rc = set_expression_begin(s, expr, n_genes, n_samples, 0, err, errlen);
     if (rc) return rc;
     rc = epx_session_set_index(s, row_ptr, probe_idx, n_genes, err, errlen);
+    if (rc) { cudaStreamSynchronize(s->stream); return rc; }
+    rc = set_expression_finish(s, n_genes, n_samples, err, errlen);
     if (rc) return rc;
     rc = epx_session_run(s, opt, nullptr, err, errlen);
     if (rc) return rc;
