@@ -253,6 +253,9 @@ __global__ void __launch_bounds__(PAIR2_WARPS * 32, (EPL <= 16 ? 4 : 2)) k_pair_
                 ss0 = q0 - g0 * g0 * inv_m; ss1 = q1 - g1 * g1 * inv_m; ss2 = q2 - g2 * g2 * inv_m;
                 mg0 = K + g0 * inv_m; mg1 = K + g1 * inv_m; mg2 = K + g2 * inv_m;
                 redo = redo || (q0 > 0.0 && ss0 < 1e-7 * q0) || (q1 > 0.0 && ss1 < 1e-7 * q1) || (q2 > 0.0 && ss2 < 1e-7 * q2);
+                /* the third group's sum of squares is a difference: an outlier in another group (|d| 300 times the
+                 * rest and up) leaves it with few good digits */
+                redo = redo || q2 < 1e-5 * sdd;
             }
             if (sdd == 0.0) syy = 0.0; /* constant row: sd is exactly 0 in R -> NA */
             if (redo) {
