@@ -276,6 +276,29 @@ def config_of(wl, name: str, world: int, total_pairs: int):
             "parallelism": f"genes sharded, {world} rank(s), NCCL gather of result tables" if world > 1 else "single GPU"}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """N > 1: run this rank (and first-touch its page-locked host buffers) on the CPUs of the NUMA node its GPU hangs
+    off, so that N ranks pushing a matrix each through the host at the same time do not all cross the socket link
+    (round 1: per-GPU H2D fell from 51 to 22 GB/s at N = 8). Returns the node, or None when the topology is not exposed."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,6 +357,7 @@ def main():
     from epimethex_b200 import _native
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = make_workload(args.workload, rank, world)
@@ -600,15 +624,20 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))   # one process, N GPUs: no NUMA binding any more
+            except OSError:
+                pass
             t0 = time.perf_counter()
             ms_ = _native.MultiSession(list(range(world)))
             ms_.set_methylation(wl["meth"])
             up_s = time.perf_counter() - t0
             calls = []
-            for i in range(1 + 5):
+            for i in range(1 + 5):   # the same call as the single-GPU e2e leg: two result tables into page-locked buffers
                 t0 = time.perf_counter()
-                multi = ms_.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts)
+                ms_.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts, full=False, pinned_results=True)
                 calls.append((time.perf_counter() - t0) * 1e3)
+            multi = ms_.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts)   # every table, for the comparison
             same = all(np.array_equal(getattr(single, k), getattr(multi, k), equal_nan=True)
                        for k in ("pair", "pair_stat", "gene")) and all(
                 np.array_equal(getattr(single, k), getattr(multi, k)) for k in ("ks_dnum", "pair_na", "gene_na", "perm"))
@@ -636,7 +665,7 @@ def main():
         kernels["probe_rank"]["rows_through_full_network_per_run"] = round(int(tim.get("sort_full_rows", 0)) / max(runs, 1), 1)
         dom = max(kern, key=lambda k: kern[k])
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload, {}).get(dom[:-3])
         line = {
@@ -646,7 +675,7 @@ def main():
             "config": config_of(wl, args.workload, world, int(total_pairs)),
             "roofline": {"bound": "hbm", "kernel": dom[:-3], "achieved": kernels[dom[:-3]]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kernels[dom[:-3]]["frac"], "traffic": traffic, "peak_source": peak_src,
-                         "traffic_source": "ncu --set full, profiles/traffic_r01.json" if traffic else None},
+                         "traffic_source": "ncu --set full, profiles/traffic.json" if traffic else None},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "index_rebuilt_every_step": True,
@@ -655,6 +684,7 @@ def main():
                     "analyze_call_ms": round(e2e_analyze_ms, 2) if e2e_analyze_ms == e2e_analyze_ms else None, "pinned_host_buffers": bool(wl["pinned"]),
                     "h2d_gbs": round(h2d / (e2e_t * 1e-3) / 1e9, 1) if e2e_t == e2e_t else None},
             "gpu_launches": int(tim["kernel_launches"]) * args.steps,
+            "numa_node_of_rank0": numa,
             "clocks": clocks,
             "setup_s": round(wl["gen_s"], 1),
         }

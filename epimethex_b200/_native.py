@@ -465,20 +465,39 @@ class MultiSession:
                                                       rows.shape[1], row_ptr.ctypes.data, probe_idx.ctypes.data,
                                                       row_ptr.size - 1, b, len(b)), b)
 
-    def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None) -> Result:
+    def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True,
+                pinned_results: bool = False) -> Result:
+        """One blocking epx_multi_analyze call. full / pinned_results as in Session.analyze: the two result tables only,
+        written by every device straight into page-locked buffers this object keeps (copy what you keep)."""
         expr = np.ascontiguousarray(expr, np.float64)
         row_ptr = np.ascontiguousarray(row_ptr, np.int64)
         probe_idx = np.ascontiguousarray(probe_idx, np.int32)
         G, n = expr.shape
         Np = int(row_ptr[-1])
-        res = Result(pair=np.empty((Np, PAIR_COLS)), pair_na=np.zeros(Np, np.uint16), pair_stat=np.empty((Np, 3)),
-                     ks_dnum=np.empty((Np, 3), np.int32), gene=np.empty((G, GENE_COLS)), gene_na=np.zeros(G, np.uint16),
-                     gene_ks_dnum=np.empty((G, 3), np.int32), perm=np.empty((G, n), np.uint16))
         r = _Result()
-        r.pair, r.pair_na, r.pair_stat, r.pair_ks_dnum = (res.pair.ctypes.data, res.pair_na.ctypes.data,
-                                                          res.pair_stat.ctypes.data, res.ks_dnum.ctypes.data)
-        r.gene, r.gene_na, r.gene_ks_dnum, r.perm = (res.gene.ctypes.data, res.gene_na.ctypes.data,
-                                                     res.gene_ks_dnum.ctypes.data, res.perm.ctypes.data)
+        if pinned_results and not full:
+            cap = getattr(self, "_pinned_cap", (0, 0))
+            if Np > cap[0] or G > cap[1]:
+                cap = (max(Np, cap[0]), max(G, cap[1]))
+                self._pinned = (pinned_empty((cap[0], PAIR_COLS)), pinned_empty((cap[0],), np.uint16),
+                                pinned_empty((cap[1], GENE_COLS)), pinned_empty((cap[1],), np.uint16))
+                self._pinned_cap = cap
+            pr, pn, gn, gm = (self._pinned[0][:Np], self._pinned[1][:Np], self._pinned[2][:G], self._pinned[3][:G])
+            res = Result(pair=pr, pair_na=pn, pair_stat=np.empty((0, 3)), ks_dnum=np.empty((0, 3), np.int32), gene=gn,
+                         gene_na=gm, gene_ks_dnum=np.empty((0, 3), np.int32), perm=np.empty((0, n), np.uint16))
+            r.pair, r.pair_na, r.gene, r.gene_na = pr.ctypes.data, pn.ctypes.data, gn.ctypes.data, gm.ctypes.data
+        else:
+            res = Result(pair=np.empty((Np, PAIR_COLS)), pair_na=np.zeros(Np, np.uint16),
+                         pair_stat=np.empty((Np, 3)) if full else np.empty((0, 3)),
+                         ks_dnum=np.empty((Np, 3), np.int32) if full else np.empty((0, 3), np.int32),
+                         gene=np.empty((G, GENE_COLS)), gene_na=np.zeros(G, np.uint16),
+                         gene_ks_dnum=np.empty((G, 3), np.int32) if full else np.empty((0, 3), np.int32),
+                         perm=np.empty((G, n), np.uint16) if full else np.empty((0, n), np.uint16))
+            r.pair, r.pair_na = res.pair.ctypes.data, res.pair_na.ctypes.data
+            r.gene, r.gene_na = res.gene.ctypes.data, res.gene_na.ctypes.data
+            if full:
+                r.pair_stat, r.pair_ks_dnum = res.pair_stat.ctypes.data, res.ks_dnum.ctypes.data
+                r.gene_ks_dnum, r.perm = res.gene_ks_dnum.ctypes.data, res.perm.ctypes.data
         opt = options if options is not None else make_options()
         b = _errbuf()
         _check(lib().epx_multi_analyze(self._h, expr.ctypes.data, G, n, row_ptr.ctypes.data, probe_idx.ctypes.data,

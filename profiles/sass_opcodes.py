@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel SASS opcode histogram of the in-tree libepx.so (cuobjdump -sass), for the Blackwell-native evidence the
 judge asked to see in the tree: UBLKCP (cp.async.bulk = TMA bulk copies), SYNCS (mbarrier), VIMNMX / VIMNMX3 / .U16x2
-(the sort network and the packed KS walk), REDUX, and the absence of UTC*MMA / HMMA (no tensor cores on this path).
+(the sort networks and the packed KS walk), ATOMS (the counting pass of the bucket placement), REDUX, and the absence of UTC*MMA / HMMA (no tensor cores on this path).
 usage: python profiles/sass_opcodes.py > profiles/sass_opcodes.txt"""
 import collections
 import os
@@ -18,14 +18,14 @@ for line in out.splitlines():
         kern = re.sub(r"\(.*", "", kern).replace("void ", "")
         hist[kern] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_x]+)*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_x]+)*)", line)
     if m and kern:
         op = m.group(1)
         base = op.split(".")[0]
         hist[kern][base] += 1
         if base in ("VIMNMX", "VIMNMX3") and ("U16x2" in op or "S16x2" in op):
             hist[kern][base + ".16x2"] += 1
-KEY = ["UBLKCP", "SYNCS", "VIMNMX", "VIMNMX3", "VIMNMX.16x2", "VIMNMX3.16x2", "SHFL", "REDUX", "DFMA", "DADD", "LDS", "STS", "ATOMG", "RED",
+KEY = ["UBLKCP", "SYNCS", "VIMNMX", "VIMNMX3", "VIMNMX.16x2", "VIMNMX3.16x2", "SHFL", "REDUX", "DFMA", "DADD", "LDS", "STS", "ATOMS", "ATOMG", "RED",
        "HMMA", "UTCHMMA", "UTCQMMA", "LDTM"]
 print("kernel".ljust(64), " ".join(k.rjust(12) for k in ["total"] + KEY))
 tot = collections.Counter()
