@@ -12,8 +12,8 @@ bytes over its CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` is th
 reference, C + OpenMP, all host cores) on a bounded gene sample of the same workload.
 
 Under torchrun (N > 1) every rank runs its own cohort of the same shape (weak scaling: genes/probes shard
-with no data-path collective) and the per-rank result tables are gathered to rank 0 over NCCL inside the
-timed region, as the path's only exchange step.  `--workload pancan_full` (BASELINE configs[4]) is the one
+with no data-path collective) and the N result tables of a step are gathered over NCCL inside the timed
+region, as the path's only exchange step, on one rank that rotates with the step (rank step mod N).  `--workload pancan_full` (BASELINE configs[4]) is the one
 strong-scaling workload: one 9,000-sample cohort, genes cut into N ranges, probe-sliced methylation.
 """
 from __future__ import annotations
@@ -378,12 +378,13 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    # Result gather (the path's only exchange step): per-rank pair/gene tables -> rank 0 over NCCL, on a second
-    # stream. The gather of step i overlaps the gene kernels and the probe ranking of step i+1 (they do not touch
+    # Result gather (the path's only exchange step): per-rank pair/gene tables -> the step's collecting rank over
+    # NCCL, on a second stream. The gather of step i overlaps the gene kernels and the probe ranking of step i+1 (they do not touch
     # the pair table); the pair kernel of step i+1 waits for it. The timed region ends only when the last gather
     # has landed.
     gather_plan = None
     gstream = torch.cuda.Stream() if world > 1 else None
+    step_no, last_root = [0], [0]
 
     def step():
         nonlocal gather_plan
@@ -407,8 +408,9 @@ def main():
                 pdst = [torch.empty((a, 11), dtype=torch.float64, device="cuda") for a, _ in sizes] if rank == 0 else None
                 gdst = [torch.empty((b, 15), dtype=torch.float64, device="cuda") for _, b in sizes] if rank == 0 else None
             else:
-                pdst = [torch.empty_like(pair_t) for _ in range(world)] if rank == 0 else None
-                gdst = [torch.empty_like(gene_t) for _ in range(world)] if rank == 0 else None
+                # every rank can collect: the collector of a step is rank (step mod N), see below
+                pdst = [torch.empty_like(pair_t) for _ in range(world)]
+                gdst = [torch.empty_like(gene_t) for _ in range(world)]
             # the gather reads a COPY of the pair table (41.8 MB device to device, ~15 us): the pair kernel of the next
             # step then never waits for the previous gather, only the next copy does -- a whole step later
             gather_plan = (pair_t, pdst, gene_t, gdst, torch.cuda.Event(), torch.empty_like(pair_t))
@@ -431,9 +433,15 @@ def main():
                     req.wait()
                 ev_gene.record(gstream)
             else:
-                dist.gather(gene_t, gdst, dst=0)
+                # weak scaling = one cohort per GPU and step; the N tables of a step are collected on ONE rank, and that
+                # rank rotates with the step: with rank 0 collecting every step its inbound 7 x 41.8 MB per 1.45 ms
+                # step (~200 GB/s through NCCL send/recv) set the pace (N = 8: 85 % of 8 x one GPU, r02D)
+                root = step_no[0] % world
+                step_no[0] += 1
+                last_root[0] = root
+                dist.gather(gene_t, gdst if rank == root else None, dst=root)
                 ev_gene.record(gstream)
-                dist.gather(pair_t, pdst, dst=0)
+                dist.gather(pair_t, pdst if rank == root else None, dst=root)
 
     def finish():
         if world > 1:
@@ -468,15 +476,19 @@ def main():
                             torch.tensor(pair_t.shape[0], device="cuda"), torch.tensor(gene_t.shape[0], device="cuda")])
         sums = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(sums, mine)
-        if rank == 0:
+        verdict = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == last_root[0]:             # the collector of the last step checks what it received
             bad = []
             for r in range(world):
                 want = [int(v) for v in sums[r].tolist()]
                 have = [int(pdst[r].view(torch.int64).sum()), int(gdst[r].view(torch.int64).sum()), pdst[r].shape[0], gdst[r].shape[0]]
                 if want != have:
                     bad.append(r)
-            shards = {"ranks_checked": world, "mismatched_ranks": bad, "ok": not bad,
-                      "how": "64-bit wrap-around sum of the bit patterns of the pair and gene tables, sender vs rank 0's copy"}
+            verdict[0] = sum(1 << r for r in bad)
+        dist.broadcast(verdict, src=last_root[0])
+        bad = [r for r in range(world) if (int(verdict[0]) >> r) & 1]
+        shards = {"ranks_checked": world, "mismatched_ranks": bad, "ok": not bad, "collector_of_the_last_step": last_root[0],
+                  "how": "64-bit wrap-around sum of the bit patterns of the pair and gene tables, sender vs the collector's copy"}
     # per-kernel CUDA-event times of the last step (events recorded by the library on the same stream)
     tim = sess.timing()
     # per-kernel times: a few more steps with the kernels serialised (no overlap of the gene kernels with the probe
