@@ -96,6 +96,26 @@ template <int EPS> struct WarpSort {
         }
     }
 
+    /* 16 words inside a thread by the 60-comparator, 10-layer network (optimal size for 16 inputs; the bitonic stages above
+     * spend 80), min/max only. Checked on all 2^16 zero-one inputs (profiles/README.md, round 2). Used where the 16-value
+     * sort is the whole network (order_bucket); sort() keeps the bitonic stages its cross-lane merges continue from. */
+    __device__ __forceinline__ static void sort16_thread(unsigned (&v)[EPS])
+    {
+        static_assert(EPS == 16, "the 60-comparator network is for 16 inputs");
+#define EPX_CE(a, b) { const unsigned lo_ = min(v[a], v[b]), hi_ = max(v[a], v[b]); v[a] = lo_; v[b] = hi_; }
+        EPX_CE(0, 13) EPX_CE(1, 12) EPX_CE(2, 15) EPX_CE(3, 14) EPX_CE(4, 8) EPX_CE(5, 6) EPX_CE(7, 11) EPX_CE(9, 10)
+        EPX_CE(0, 5) EPX_CE(1, 7) EPX_CE(2, 9) EPX_CE(3, 4) EPX_CE(6, 13) EPX_CE(8, 14) EPX_CE(10, 15) EPX_CE(11, 12)
+        EPX_CE(0, 1) EPX_CE(2, 3) EPX_CE(4, 5) EPX_CE(6, 8) EPX_CE(7, 9) EPX_CE(10, 11) EPX_CE(12, 13) EPX_CE(14, 15)
+        EPX_CE(0, 2) EPX_CE(1, 3) EPX_CE(4, 10) EPX_CE(5, 11) EPX_CE(6, 7) EPX_CE(8, 9) EPX_CE(12, 14) EPX_CE(13, 15)
+        EPX_CE(1, 2) EPX_CE(3, 12) EPX_CE(4, 6) EPX_CE(5, 7) EPX_CE(8, 10) EPX_CE(9, 11) EPX_CE(13, 14)
+        EPX_CE(1, 4) EPX_CE(2, 6) EPX_CE(5, 8) EPX_CE(7, 10) EPX_CE(9, 13) EPX_CE(11, 14)
+        EPX_CE(2, 4) EPX_CE(3, 6) EPX_CE(9, 12) EPX_CE(11, 13)
+        EPX_CE(3, 5) EPX_CE(6, 8) EPX_CE(7, 9) EPX_CE(10, 12)
+        EPX_CE(3, 4) EPX_CE(5, 6) EPX_CE(7, 8) EPX_CE(9, 10) EPX_CE(11, 12)
+        EPX_CE(6, 7) EPX_CE(8, 9)
+#undef EPX_CE
+    }
+
     __device__ __forceinline__ static void sort(unsigned (&v)[EPS], const int lane, const unsigned one, const unsigned minus1)
     {
         sort_thread(v, one, minus1);
@@ -353,7 +373,7 @@ template <int EPS> struct WarpSort {
         }
         __syncwarp();
         const unsigned minus1 = 0u - one;
-        sort_thread(v, one, minus1);
+        if constexpr (EPS == 16) sort16_thread(v); else sort_thread(v, one, minus1);
         { /* merge across the thread boundaries: upper half of lane L with the lower half of lane L + 1 */
             constexpr int H = EPS / 2;
             unsigned tdn[H], tup[H];
