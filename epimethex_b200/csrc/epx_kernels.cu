@@ -24,18 +24,17 @@ namespace epx {
 
 /* ============================================================ k_gene_sort */
 
-__global__ void __launch_bounds__(CTASORT_THREADS, 2) k_gene_sort(GeneParams p)
+__global__ void __maxnreg__(80) k_gene_sort(GeneParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int g = blockIdx.x, n = p.n;
     double *s_val = (double *)smem;
-    unsigned short *s_a = (unsigned short *)(s_val + ((n + 1) & ~1));
-    unsigned short *s_b = s_a + ctasort_entries(n);
+    unsigned *region = (unsigned *)(s_val + ((n + 1) & ~1)); /* bucket placement; holds the merge sort's buffers on a fallback */
     __shared__ double red[40];
-    __shared__ int s_uniq;
+    __shared__ int s_ties;
 
     const double *x = p.expr + (int64_t)g * n;
-    if (threadIdx.x == 0) s_uniq = 1;
+    if (threadIdx.x == 0) s_ties = 0;
     double sum = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double v = x[i];
@@ -43,18 +42,25 @@ __global__ void __launch_bounds__(CTASORT_THREADS, 2) k_gene_sort(GeneParams p)
         sum += v;
     }
     __syncthreads();
-    /* value descending, ties by sample index */
-    const unsigned short *ord = cta_sort_row<true>(s_val, n, s_a, s_b, p.one);
+    /* value descending, ties by sample index: bucket placement (epx_ctabucket.cuh), else the merge sort */
+    const unsigned short *ord = cta_bucket_order<true>(s_val, n, region, p.one, nullptr);
+    bool marked = ord != nullptr;
+    if (!ord) {
+        unsigned short *s_a = (unsigned short *)region, *s_b = s_a + ctasort_entries(n);
+        __syncthreads();
+        ord = cta_sort_row<true>(s_val, n, s_a, s_b, p.one);
+    }
 
-    int uniq = 0;
+    int ties = 0; /* positions whose successor holds an equal value */
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int s = ord[i];
+        const int s = ord[i] & 0x7fff;
         p.perm[(int64_t)g * n + i] = (uint16_t)s;
         const int lab = i / p.m;
         p.lab8[(int64_t)g * p.ldl + s] = (uint8_t)(lab > 3 ? 3 : lab);
-        if (i > 0 && s_val[s] != s_val[ord[i - 1]]) uniq++;
+        if (marked) ties += ord[i] >> 15;
+        else if (i > 0 && s_val[s] == s_val[ord[i - 1] & 0x7fff]) ties++;
     }
-    if (uniq) atomicAdd(&s_uniq, uniq);
+    if (ties) atomicAdd(&s_ties, ties);
 
     double mean = block_sum(sum, red) / (double)n;
     double sxx = 0.0, sxc = 0.0;
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(CTASORT_THREADS, 2) k_gene_sort(GeneParams p)
     sxx = block_sum(sxx, red);
     sxc = block_sum(sxc, red);
     if (threadIdx.x == 0) {
-        int u = s_uniq;
+        int u = n - s_ties;
         p.nuniq[g] = u;
         double *ga = p.gene_aux + 4 * (int64_t)g;
         ga[0] = (u == 1) ? 0.0 : sxx; /* constant gene: sd is exactly 0 in R */
@@ -1670,7 +1676,7 @@ cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
 {
     if (p.G <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
-        k_gene_sort<<<p.G, ctasort_threads(p.n), sort_smem(p.n), st>>>(p);
+        k_gene_sort<<<p.G, ctab_threads(p.n), (size_t)((p.n + 1) & ~1) * 8 + ctab_smem(p.n), st>>>(p);
         return cudaGetLastError();
     }
     int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS; /* one gene per warp: G is small, favour parallelism */
