@@ -358,8 +358,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a CPU-side group for parking ranks: an NCCL barrier is a kernel that spins on the waiting ranks' GPUs
+        cpu_group = dist.new_group(backend="gloo")
     wl = make_workload(args.workload, rank, world)
     idx, n, G, P = wl["idx"], wl["n"], wl["G"], wl["P"]
     strong = bool(wl["w"].get("shard"))
@@ -634,7 +637,7 @@ def main():
         single = sess.analyze(wl["expr"], idx.row_ptr, idx.probe_idx, opts, full=True) if rank == 0 else None
         sess.close()
         torch.cuda.synchronize()
-        dist.barrier()
+        dist.barrier(group=cpu_group)    # the other ranks wait on the CPU: their GPUs must be idle for rank 0's measurement
         if rank == 0:
             try:
                 os.sched_setaffinity(0, range(os.cpu_count() or 1))   # one process, N GPUs: no NUMA binding any more
@@ -645,9 +648,10 @@ def main():
             ms_.set_methylation(wl["meth"])
             up_s = time.perf_counter() - t0
             calls = []
-            for i in range(1 + 5):   # the same call as the single-GPU e2e leg: two result tables into page-locked buffers
+            for i in range(1 + 6):   # the same call as the single-GPU e2e leg: two result tables into page-locked buffers,
+                rp_i, pi_i = variants[i & 1]   # and a different index on every call (rebuilt inside the call)
                 t0 = time.perf_counter()
-                ms_.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts, full=False, pinned_results=True)
+                ms_.analyze(wl["expr_pinned"], rp_i, pi_i, opts, full=False, pinned_results=True)
                 calls.append((time.perf_counter() - t0) * 1e3)
             multi = ms_.analyze(wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts)   # every table, for the comparison
             same = all(np.array_equal(getattr(single, k), getattr(multi, k), equal_nan=True)
@@ -660,7 +664,7 @@ def main():
                            "methylation_upload_s": round(up_s, 3), "single_gpu_call_ms": None,
                            "identical_to_single_gpu_tables": bool(same)}
             ms_.close()
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -65,6 +66,7 @@ inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 struct epx_session {
     int device = 0;
     int sm_count = 0;
+    int host_threads = 8;    /* worker threads of the index build; epx_multi_create divides the host's cores among its sessions */
     cudaStream_t stream = nullptr;
     /* methylation, probe-major */
     DevBuf<double> meth_own;
@@ -128,6 +130,7 @@ struct epx_multi {
     std::vector<std::vector<int32_t>> rows_of;
     bool sliced = false;
     std::vector<int64_t> pair_lo;   /* after epx_multi_analyze: device i owns pairs [pair_lo[i], pair_lo[i+1]) */
+    cudaEvent_t ev_expr = nullptr;  /* device 0: the expression matrix has arrived (the other devices copy it from there) */
 };
 
 /* contiguous gene ranges with (nearly) equal pair counts: cut[r] .. cut[r+1] is device r's range */
@@ -197,10 +200,13 @@ void epx_options_default(epx_options *opt)
     opt->test_meth_t = 0;
 }
 
+/* page-locked for EVERY device of the process (portable): with the default flag only the device that was current at
+ * the allocation sees it as pinned, and the other devices of an epx_multi handle copied their result rows into it at
+ * the pageable rate (3.5 ms more per call on 2 GPUs) */
 int epx_host_alloc(void **ptr, size_t bytes, char *err, size_t errlen)
 {
     if (!ptr) return fail(err, errlen, EPX_EINVAL, "ptr is NULL");
-    EPX_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    EPX_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
     return EPX_OK;
 }
 
@@ -490,7 +496,7 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     uint8_t *ref = s->ref_mark.data();
     const int64_t P = s->P;
     int nt = (int)std::thread::hardware_concurrency();
-    if (nt > 8) nt = 8;
+    if (nt > s->host_threads) nt = s->host_threads;
     if (nt < 1 || Np < 65536) nt = 1;
     std::vector<int64_t> cnt((size_t)nt + 1, 0), bad_at_t((size_t)nt, -1);
     std::vector<int> bad_code_t((size_t)nt, 0);
@@ -1029,6 +1035,24 @@ int epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *e
         if (rc) { epx_multi_destroy(m); return rc; }
         m->sess.push_back(s);
     }
+    /* one host thread per device drives its session at the same time: the index builds share the cores (their workers
+     * meet at spin barriers, so more workers than cores costs scheduling quanta: 2 devices x 8 workers on 16 cores made
+     * every call 3 ms longer) */
+    int per = (int)std::thread::hardware_concurrency() / n_devices - 1;
+    per = per < 1 ? 1 : (per > 8 ? 8 : per);
+    for (epx_session *s : m->sess) s->host_threads = per;
+    /* the expression matrix crosses PCIe once (to the first device); the others fetch it from there over NVLink */
+    if (n_devices > 1) {
+        for (int i = 0; i < n_devices; i++) {
+            if (cudaSetDevice(devices[i]) != cudaSuccess) continue;
+            for (int j = 0; j < n_devices; j++)
+                if (j != i && cudaDeviceEnablePeerAccess(devices[j], 0) != cudaSuccess) cudaGetLastError(); /* already on, or no path: the copy is staged */
+        }
+        if (cudaSetDevice(devices[0]) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_expr, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            m->ev_expr = nullptr;
+        }
+    }
     *out = m;
     return EPX_OK;
 }
@@ -1036,6 +1060,7 @@ int epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *e
 void epx_multi_destroy(epx_multi *m)
 {
     if (!m) return;
+    if (m->ev_expr && !m->sess.empty()) { cudaSetDevice(m->sess[0]->device); cudaEventDestroy(m->ev_expr); }
     for (epx_session *s : m->sess) epx_session_destroy(s);
     delete m;
 }
@@ -1106,6 +1131,7 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
     const int W = (int)m->sess.size();
     const std::vector<int64_t> cut = gene_cuts(row_ptr, n_genes, W);
     m->pair_lo.clear();
+    std::atomic<int> expr_ready{0}; /* 1: device 0 has queued its upload and recorded ev_expr; -1: it failed */
     int rc_all = for_each_device(m, [&](int i, char *e, size_t el) -> int {
         epx_session *s = m->sess[(size_t)i];
         const int64_t g0 = cut[(size_t)i], g1 = cut[(size_t)i + 1];
@@ -1140,7 +1166,45 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
             }
             pi = local.data();
         }
-        int rc = epx_analyze(s, expr, n_genes, n_samples, rp.data(), pi, opt, &r, e, el);
+        /* epx_analyze, with the expression matrix taken from device 0 by every other device: W uploads of the same 78 MB
+         * from one host buffer made a call on 8 GPUs slower than on one */
+        int rc;
+        const bool trace = getenv("EPX_TRACE") != nullptr; /* host-side phase times of every device thread, to stderr */
+        auto t_prev = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (!trace) return;
+            const auto t = std::chrono::steady_clock::now();
+            fprintf(stderr, "[epx_multi_analyze] device %d %-16s %8.3f ms\n", s->device, what,
+                    std::chrono::duration<double, std::milli>(t - t_prev).count());
+            t_prev = t;
+        };
+        if (i == 0 || !m->ev_expr) {
+            rc = set_expression_begin(s, expr, n_genes, n_samples, 0, e, el);
+            if (i == 0 && m->ev_expr) {
+                if (rc == EPX_OK && cudaEventRecord(m->ev_expr, s->stream) != cudaSuccess) rc = fail(e, el, EPX_ECUDA, "event record failed");
+                expr_ready.store(rc == EPX_OK ? 1 : -1, std::memory_order_release);
+            }
+        } else {
+            int st;
+            while ((st = expr_ready.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+            if (st < 0) return fail(e, el, EPX_ESTATE, "the expression upload on the first device failed");
+            if (cudaSetDevice(s->device) != cudaSuccess || cudaStreamWaitEvent(s->stream, m->ev_expr, 0) != cudaSuccess)
+                return fail(e, el, EPX_ECUDA, "cannot wait for the first device's expression upload: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = set_expression_begin(s, m->sess[0]->expr.p, n_genes, n_samples, 1, e, el);
+        }
+        if (rc) return rc;
+        lap("expression begin");
+        rc = epx_session_set_index(s, rp.data(), pi, n_genes, e, el);
+        if (rc) { cudaStreamSynchronize(s->stream); return rc; }
+        lap("index");
+        rc = set_expression_finish(s, n_genes, n_samples, e, el);
+        if (rc) return rc;
+        lap("expression there");
+        rc = epx_session_run(s, opt, nullptr, e, el);
+        if (rc) return rc;
+        lap("run (enqueue)");
+        rc = epx_session_fetch(s, &r, nullptr, e, el);
+        lap("fetch");
         if (rc == EPX_OK && i == 0) { memcpy(out->counts, r.counts, sizeof r.counts); out->ref_gene = r.ref_gene; }
         return rc;
     }, err, errlen);
