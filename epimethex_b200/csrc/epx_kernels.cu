@@ -29,7 +29,7 @@ __global__ void __maxnreg__(80) k_gene_sort(GeneParams p)
     extern __shared__ __align__(16) unsigned char smem[];
     const int g = blockIdx.x, n = p.n;
     double *s_val = (double *)smem;
-    unsigned *region = (unsigned *)(s_val + ((n + 1) & ~1)); /* bucket placement; holds the merge sort's buffers on a fallback */
+    unsigned *region = (unsigned *)(smem + ctab_row_bytes(n)); /* bucket placement; holds the merge sort's buffers on a fallback */
     __shared__ double red[40];
     __shared__ int s_ties;
 
@@ -43,10 +43,12 @@ __global__ void __maxnreg__(80) k_gene_sort(GeneParams p)
     }
     __syncthreads();
     /* value descending, ties by sample index: bucket placement (epx_ctabucket.cuh), else the merge sort */
-    const unsigned short *ord = cta_bucket_order<true>(s_val, n, region, p.one, nullptr);
+    const unsigned short *ord = cta_bucket_order<true>(s_val, x, n, region, p.one, nullptr);
     bool marked = ord != nullptr;
-    if (!ord) {
+    if (!ord) { /* the placement used the row's place in shared memory: stage it again for the merge sort */
         unsigned short *s_a = (unsigned short *)region, *s_b = s_a + ctasort_entries(n);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = x[i];
         __syncthreads();
         ord = cta_sort_row<true>(s_val, n, s_a, s_b, p.one);
     }
@@ -58,14 +60,14 @@ __global__ void __maxnreg__(80) k_gene_sort(GeneParams p)
         const int lab = i / p.m;
         p.lab8[(int64_t)g * p.ldl + s] = (uint8_t)(lab > 3 ? 3 : lab);
         if (marked) ties += ord[i] >> 15;
-        else if (i > 0 && s_val[s] == s_val[ord[i - 1] & 0x7fff]) ties++;
+        else if (i > 0 && x[s] == x[ord[i - 1] & 0x7fff]) ties++;
     }
     if (ties) atomicAdd(&s_ties, ties);
 
     double mean = block_sum(sum, red) / (double)n;
     double sxx = 0.0, sxc = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double d = s_val[i] - mean;
+        double d = x[i] - mean; /* from global memory (L2): the staged row is gone */
         p.xc[(int64_t)g * p.ldx + i] = d;
         sxx += d * d;
         sxc += d;
@@ -296,7 +298,7 @@ __global__ void __maxnreg__(80) k_probe_rank(RankParams p)
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = p.n;
     double *s_val = (double *)smem;
-    unsigned *region = (unsigned *)(s_val + ((n + 1) & ~1));
+    unsigned *region = (unsigned *)(smem + ctab_row_bytes(n));
     /* the row comes in as ONE bulk copy (cp.async.bulk + mbarrier) when it is 16-byte aligned: a per-thread loop of
      * loads and shared stores ran as ~35 dependent round trips to DRAM and took a quarter of the kernel */
     __shared__ __align__(8) uint64_t bar;
@@ -315,9 +317,17 @@ __global__ void __maxnreg__(80) k_probe_rank(RankParams p)
             for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
         }
         __syncthreads();
-        const unsigned short *ord = cta_bucket_order<false>(s_val, n, region, p.one, p.full_rows);
-        if (!ord) {
+        const unsigned short *ord = cta_bucket_order<false>(s_val, row, n, region, p.one, p.full_rows);
+        if (!ord) { /* the placement used the row's place in shared memory: stage it again for the merge sort */
             unsigned short *s_a = (unsigned short *)region, *s_b = s_a + ctasort_entries(n);
+            __syncthreads();
+            if (bulk) {
+                if (threadIdx.x == 0) { mbar_expect_tx(&bar, rowbytes); bulk_g2s(s_val, row, rowbytes, &bar); }
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+            } else {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) s_val[i] = __ldg(row + i);
+            }
             __syncthreads();
             /* n > 1024 here, so there is a last merge pass and it leaves the tie marks in place */
             ord = cta_sort_row<false, true>(s_val, n, s_a, s_b, p.one);
@@ -1676,7 +1686,7 @@ cudaError_t launch_gene_sort(const GeneParams &p, int sm_count, cudaStream_t st)
 {
     if (p.G <= 0) return cudaSuccess;
     if (p.n > MAX_WARP_SAMPLES) {
-        k_gene_sort<<<p.G, ctab_threads(p.n), (size_t)((p.n + 1) & ~1) * 8 + ctab_smem(p.n), st>>>(p);
+        k_gene_sort<<<p.G, ctab_threads(p.n), ctab_row_bytes(p.n) + ctab_smem(p.n), st>>>(p);
         return cudaGetLastError();
     }
     int grid = (p.G + SORT_WARPS - 1) / SORT_WARPS; /* one gene per warp: G is small, favour parallelism */
@@ -1756,7 +1766,7 @@ cudaError_t launch_probe_rank(const RankParams &p, int sm_count, cudaStream_t st
     if (p.n > MAX_WARP_SAMPLES) {
         {
             const int threads = ctab_threads(p.n);
-            const size_t smem = (size_t)((p.n + 1) & ~1) * 8 + ctab_smem(p.n);
+            const size_t smem = ctab_row_bytes(p.n) + ctab_smem(p.n);
             int per_sm = (int)((226 * 1024) / (smem + 1024));
             const int by_regs = 65536 / (80 * ((threads + 127) / 128 * 128)), by_threads = 2048 / threads; /* registers come in units of four warps */
             if (per_sm > by_regs) per_sm = by_regs;
