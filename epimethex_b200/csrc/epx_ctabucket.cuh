@@ -147,6 +147,8 @@ __device__ const unsigned short *cta_bucket_order(double *s_val, const double *_
     const double c0 = fma(-first, scale, 6755399441055744.0 + (double)((1u << CTAB_SH) - 64u));
 
     /* ---- counting pass: the two piles into their bitmaps, everything else into its bucket's counter ---- */
+    unsigned qf = (unsigned)__double2loint(fma(first, scale, c0)), ql = (unsigned)__double2loint(fma(last, scale, c0));
+    qf = min(qf, QMAX - 1u); ql = min(ql, QMAX - 1u);
     unsigned Q[CTAB_W]; /* per element: Q, bit 31 / 30: member of the first / last pile; 0xffffffff: no such element */
     /* n > 32 T - 1024 >= 16 T: the elements e < 16 of every thread exist */
 #pragma unroll
@@ -157,9 +159,12 @@ __device__ const unsigned short *cta_bucket_order(double *s_val, const double *_
             const double x = s_val[i];
             unsigned q = (unsigned)__double2loint(fma(x, scale, c0));
             q = min(q, QMAX - 1u); /* memory safety only: a q out of range means the row fails the check below */
-            if (x == first) { atomicOr(bm + (i >> 5), 1u << (i & 31)); q |= 0x80000000u; }
-            else if (x == last) { atomicOr(bm + T + (i >> 5), 1u << (i & 31)); q |= 0x40000000u; }
-            else atomicAdd(region + (q >> CTAB_SH), 1u);
+            bool pile = false;
+            if (q == qf || q == ql) { /* equal Q is necessary for membership; the values decide */
+                if (x == first) { atomicOr(bm + (i >> 5), 1u << (i & 31)); q |= 0x80000000u; pile = true; }
+                else if (x == last) { atomicOr(bm + T + (i >> 5), 1u << (i & 31)); q |= 0x40000000u; pile = true; }
+            }
+            if (!pile) atomicAdd(region + (q >> CTAB_SH), 1u);
             Q[e] = q;
         }
     }
