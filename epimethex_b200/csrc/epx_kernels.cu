@@ -1296,6 +1296,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
     __shared__ int ired[BIG_THREADS / 32];
     __shared__ int s_wtot[BIG_THREADS / 32][3];
     __shared__ double s_med[8];
+    __shared__ uint2 s_inc[4]; /* what a position of label 0 / 1 / 2 / none adds to the two packed count words of the walk */
     /* scalar results of up to TAIL_PAIRS finished pairs: their tails (Pearson p, tests, p-values, 17 result values --
      * serial work with dependent global loads) are done 32 at a time, one pair per lane of warp 0, instead of by one
      * thread per pair while the other 511 wait at the next barrier (12 % of the stall samples) */
@@ -1307,7 +1308,11 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
     const int t1 = (m - 1) / 2 + 1, t2 = m / 2 + 1;
     const int lane = tid & 31, warp = tid >> 5;
 
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init();
+        s_inc[0] = make_uint2(WALK_A0, WALK_B0); s_inc[1] = make_uint2(WALK_A1, WALK_B1);
+        s_inc[2] = make_uint2(WALK_A2, WALK_B2); s_inc[3] = make_uint2(0u, 0u);
+    }
     __syncthreads();
     uint32_t ph[2] = { 0, 0 };
     auto issue = [&](int j, int stage) { /* thread 0 only */
@@ -1446,38 +1451,65 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             if (TMODE) { ss0 = block_sum(b0, red); ss1 = block_sum(b1, red); ss2 = block_sum(b2, red); }
         }
 
-        /* sorted walk: thread t owns positions [t*chunk, (t+1)*chunk); label counts by warp scan + warp totals */
+        /* sorted walk, ONE pass: thread t owns positions [t*chunk, (t+1)*chunk). As in k_pair_stats2 the label counts run as
+         * two words of two biased 16-bit fields, ra = [cUP-cMID | cUP-cDOWN], rb = [cMID-cDOWN | cUP], advanced by the
+         * increment pair of each position's label (a 4-entry table) and folded into running packed maxima / minima at
+         * tie-run ends; the counts in front of the thread come from a scan afterwards (max(prefix + x) = prefix + max x),
+         * and only the threads whose positions hold a group's middle members look at their positions a second time.
+         * (Two passes with absolute counts -- count, scan, walk -- cost 66 instructions per position; this costs ~15.) */
         int chunk = (n + nt - 1) / nt;
         chunk += (chunk & 7) == 0 ? 1 : 0; /* lanes start `chunk` 16-bit entries apart: a multiple of 8 would share few banks */
         const int k0 = min(tid * chunk, n), k1 = min(k0 + chunk, n);
-        int c0 = 0, c1 = 0, c2 = 0;
-        for (int k = k0; k < k1; k++) {
-            const unsigned l = s_lab[s_ord[k] & 0x7fffu];
-            c0 += l == 0; c1 += l == 1; c2 += l == 2;
-        }
-        int i0 = c0, i1 = c1, i2 = c2; /* inclusive scan inside the warp */
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int a0 = __shfl_up_sync(FULL, i0, d), a1 = __shfl_up_sync(FULL, i1, d), a2 = __shfl_up_sync(FULL, i2, d);
-            if (lane >= d) { i0 += a0; i1 += a1; i2 += a2; }
-        }
-        __syncthreads(); /* s_wtot of the previous pair has been consumed */
-        if (lane == 31) { s_wtot[warp][0] = i0; s_wtot[warp][1] = i1; s_wtot[warp][2] = i2; }
-        __syncthreads();
-        int b0_ = 0, b1_ = 0, b2_ = 0;
-        for (int w = 0; w < warp; w++) { b0_ += s_wtot[w][0]; b1_ += s_wtot[w][1]; b2_ += s_wtot[w][2]; }
-        c0 = b0_ + i0 - c0; c1 = b1_ + i1 - c1; c2 = b2_ + i2 - c2; /* exclusive prefix of this thread */
-        int d01 = 0, d02 = 0, d12 = 0;
+        unsigned ra = WALK_BIAS, rb = WALK_BIAS, mxa = 0u, mna = 0xffffffffu, mxb = 0u, mnb = 0xffffffffu;
         for (int k = k0; k < k1; k++) {
             const unsigned short o = s_ord[k];
-            const int s = o & 0x7fffu;
-            const unsigned l = s_lab[s];
-            int c = -1;
-            if (l == 0) c = ++c0; else if (l == 1) c = ++c1; else if (l == 2) c = ++c2;
-            if (c == t1) s_med[l * 2] = s_row[s];
-            if (c == t2) s_med[l * 2 + 1] = s_row[s];
-            if (!TMODE && !(o & 0x8000u)) {
-                d01 = max(d01, abs(c0 - c1)); d02 = max(d02, abs(c0 - c2)); d12 = max(d12, abs(c1 - c2));
+            const uint2 inc = s_inc[s_lab[o & 0x7fffu]];
+            ra += inc.x; rb += inc.y;
+            if (!TMODE && !(o & 0x8000u)) { /* inside a tie run nothing is evaluated */
+                mxa = __vmaxu2(mxa, ra); mna = __vminu2(mna, ra);
+                mxb = __vmaxu2(mxb, rb); mnb = __vminu2(mnb, rb);
+            }
+        }
+        const unsigned da = ra - WALK_BIAS, db = rb - WALK_BIAS; /* this thread's totals (wrap-around sums of the fields) */
+        unsigned ia = da, ib = db;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned ta = __shfl_up_sync(FULL, ia, d), tb = __shfl_up_sync(FULL, ib, d);
+            if (lane >= d) { ia += ta; ib += tb; }
+        }
+        __syncthreads(); /* s_wtot of the previous pair has been consumed */
+        if (lane == 31) { s_wtot[warp][0] = (int)ia; s_wtot[warp][1] = (int)ib; }
+        __syncthreads();
+        unsigned wa = 0, wb = 0;
+        for (int w = 0; w < warp; w++) { wa += (unsigned)s_wtot[w][0]; wb += (unsigned)s_wtot[w][1]; }
+        ia += wa; ib += wb;
+        const unsigned ea = ia - da, eb = ib - db; /* counts in front of this thread */
+        int d01 = 0, d02 = 0, d12 = 0;
+        if (!TMODE && mxa != 0u) { /* the thread evaluated at least one position */
+            const unsigned xa = mxa + ea, na_ = mna + ea, xb = mxb + eb, nb = mnb + eb;
+            d01 = max((int)(xa >> 16) - 0x4000, 0x4000 - (int)(na_ >> 16));
+            d02 = max((int)(xa & 0xffffu) - 0x4000, 0x4000 - (int)(na_ & 0xffffu));
+            d12 = max((int)(xb >> 16) - 0x4000, 0x4000 - (int)(nb >> 16));
+        }
+        if (m >= 1 && k0 < k1) { /* medians: the t1-th and t2-th member of every group */
+            const unsigned eab = ea + WALK_BIAS, iab = ia + WALK_BIAS;
+            const int ce[3] = { (int)(eb & 0xffffu), (int)(eb & 0xffffu) - ((int)(eab >> 16) - 0x4000),
+                                (int)(eb & 0xffffu) - ((int)(eab & 0xffffu) - 0x4000) };
+            const int ci[3] = { (int)(ib & 0xffffu), (int)(ib & 0xffffu) - ((int)(iab >> 16) - 0x4000),
+                                (int)(ib & 0xffffu) - ((int)(iab & 0xffffu) - 0x4000) };
+#pragma unroll
+            for (int g = 0; g < 3; g++) {
+                if (ce[g] < t2 && t1 <= ci[g]) { /* at least one of the two lies in this thread's positions (rare) */
+                    int c = ce[g];
+                    for (int k = k0; k < k1; k++) {
+                        const int s = s_ord[k] & 0x7fffu;
+                        if (s_lab[s] == (unsigned)g) {
+                            ++c;
+                            if (c == t1) s_med[g * 2] = s_row[s];
+                            if (c == t2) s_med[g * 2 + 1] = s_row[s];
+                        }
+                    }
+                }
             }
         }
         if (!TMODE) { d01 = block_max_i(d01, ired); d02 = block_max_i(d02, ired); d12 = block_max_i(d12, ired); }
