@@ -1279,6 +1279,23 @@ __device__ __forceinline__ int block_max_i(int v, int *red)
     return r;
 }
 
+/* three sums over the block at once; every thread gets the results. red: >= 52 doubles of shared memory */
+__device__ __forceinline__ void block_sum3w(double &a, double &b, double &c, double *red)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    __syncthreads(); /* protect red[] from a previous use */
+    if (lane == 0) { red[w] = a; red[16 + w] = b; red[32 + w] = c; }
+    __syncthreads();
+    if (w == 0) {
+        double x = lane < nw ? red[lane] : 0.0, y = lane < nw ? red[16 + lane] : 0.0, z = lane < nw ? red[32 + lane] : 0.0;
+        x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+        if (lane == 0) { red[48] = x; red[49] = y; red[50] = z; }
+    }
+    __syncthreads();
+    a = red[48]; b = red[49]; c = red[50];
+}
+
 /* bytes of one stage: row (ld doubles) + order (ldo uint16) */
 __host__ __device__ inline size_t big_stage_bytes(int64_t ld, int64_t ldo) { return (size_t)ld * 8 + (size_t)ldo * 2; }
 
@@ -1292,8 +1309,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
     const uint32_t rowb = (uint32_t)p.ld * 8u, ordb = (uint32_t)p.ldo * 2u, stageb = rowb + ordb;
     uint8_t *s_lab = (uint8_t *)(smem + (size_t)STAGES * stageb);
     __shared__ __align__(8) uint64_t bar[2];
-    __shared__ double red[40];
-    __shared__ int ired[BIG_THREADS / 32];
+    __shared__ double red[64];
+    __shared__ int s_dmax[BIG_THREADS / 32][3];
     __shared__ int s_wtot[BIG_THREADS / 32][3];
     __shared__ double s_med[8];
     __shared__ uint2 s_inc[4]; /* what a position of label 0 / 1 / 2 / none adds to the two packed count words of the walk */
@@ -1423,7 +1440,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
                 else if (l == 2) { g2 += d; q2 = fma(d, d, q2); }
             }
         }
-        sd = block_sum(sd, red); sdd = block_sum(sdd, red); sxd = block_sum(sxd, red);
+        block_sum3w(sd, sdd, sxd, red); /* three sums behind one pair of barriers */
         double syy = sdd - sd * sd / dn_, sxy = sxd - (sd / dn_) * ga[2];
         double mg0 = 0, mg1 = 0, mg2 = 0, ss0 = 0, ss1 = 0, ss2 = 0;
         bool redo = sdd > 0.0 && syy < 1e-7 * sdd;
@@ -1512,7 +1529,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
                 }
             }
         }
-        if (!TMODE) { d01 = block_max_i(d01, ired); d02 = block_max_i(d02, ired); d12 = block_max_i(d12, ired); }
+        if (!TMODE) { /* per-warp maxima; thread 0 folds them when it files the pair's scalars (nobody else needs them) */
+            d01 = warp_max_i(d01); d02 = warp_max_i(d02); d12 = warp_max_i(d12);
+            if (lane == 0) { s_dmax[warp][0] = d01; s_dmax[warp][1] = d02; s_dmax[warp][2] = d12; }
+        }
         __syncthreads();
         const double medUP = (s_med[0] + s_med[1]) * 0.5, medMID = (s_med[2] + s_med[3]) * 0.5,
                      medDOWN = (s_med[4] + s_med[5]) * 0.5;
@@ -1544,6 +1564,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_pair_stats_cta(PairParams p)
             }
             t_i[npend][0] = j; t_i[npend][1] = gene;
             t_i[npend][2] = (guard[0] + 1) | ((guard[1] + 1) << 2) | ((guard[2] + 1) << 4);
+            if (!TMODE)
+                for (int w = 1; w < (nt >> 5); w++) { d01 = max(d01, s_dmax[w][0]); d02 = max(d02, s_dmax[w][1]); d12 = max(d12, s_dmax[w][2]); }
             t_i[npend][3] = d01; t_i[npend][4] = d02; t_i[npend][5] = d12;
         }
         if (++npend == TAIL_PAIRS) { flush_tails(npend); npend = 0; }
