@@ -790,6 +790,29 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(EPS >= 32 
             double sum = 0.0;
 #pragma unroll
             for (int e = 0; e < EPS; e++) { const int s = lane + 32 * e; if (s < n) sum += vals[s]; }
+            if constexpr (BUCKETS) {
+                /* order and labels go through shared memory (the sort's scratch is free): the labels are indexed by
+                 * SAMPLE, and 473 one-byte stores to random places of a global row cost a sector each; from shared
+                 * memory the label row leaves as one 16-byte store per lane and the order as coalesced 2-byte stores */
+                unsigned short *s16 = reinterpret_cast<unsigned short *>(s_bkt);
+                unsigned char *s8 = reinterpret_cast<unsigned char *>(s_bkt + N / 2);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < EPS; r++) {
+                    const int k = lane * EPS + r;
+                    if (k < n) {
+                        const int s = out[r] & 0x7fff;
+                        ties += (out[r] >> 15) & 1;
+                        s16[k] = (unsigned short)s;
+                        s8[s] = (unsigned char)((k >= m1) + (k >= m2) + (k >= m3)); /* = min(k / m, 3); m = 0 only for n < 3 (refused) */
+                    }
+                }
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) perm[i] = s16[i];
+                if (lane * 16 < (int)gp.ldl) /* the bytes behind the n-th label are never looked at */
+                    *reinterpret_cast<uint4 *>(lab8 + lane * 16) = *reinterpret_cast<const uint4 *>(s8 + lane * 16);
+                __syncwarp();
+            } else {
 #pragma unroll
             for (int r = 0; r < EPS; r++) {
                 const int k = lane * EPS + r;
@@ -799,6 +822,7 @@ __global__ void __launch_bounds__(rank_warps<EPS>() * 32) __maxnreg__(EPS >= 32 
                     perm[k] = (uint16_t)s;
                     lab8[s] = (uint8_t)((k >= m1) + (k >= m2) + (k >= m3)); /* = min(k / m, 3); m = 0 only for n < 3 (refused) */
                 }
+            }
             }
             ties = __reduce_add_sync(FULL, ties);
             const double mean = warp_sum(sum) / (double)n;
