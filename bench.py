@@ -454,6 +454,11 @@ def main():
     sampler.start()
     for _ in range(args.warmup):
         step()
+    # the collecting rank rotates: every rank must have collected once before the clock starts (NCCL sets up the
+    # send/recv connections of a (sender, collector) pair at their first use: ~1 s each, 131 ms per step over 50 steps
+    # when five of the eight collectors met theirs inside the timed region, r02T)
+    while world > 1 and not strong and step_no[0] < world:
+        step()
     finish()
     torch.cuda.synchronize()
     if world > 1:
