@@ -387,7 +387,7 @@ def main():
     # has landed.
     gather_plan = None
     gstream = torch.cuda.Stream() if world > 1 else None
-    step_no, last_root = [0], [0]
+    step_no, last_root, rotate = [0], [0], [True]
 
     def step():
         nonlocal gather_plan
@@ -439,7 +439,7 @@ def main():
                 # weak scaling = one cohort per GPU and step; the N tables of a step are collected on ONE rank, and that
                 # rank rotates with the step: with rank 0 collecting every step its inbound 7 x 41.8 MB per 1.45 ms
                 # step (~200 GB/s through NCCL send/recv) set the pace (N = 8: 85 % of 8 x one GPU, r02D)
-                root = step_no[0] % world
+                root = step_no[0] % world if rotate[0] else 0
                 step_no[0] += 1
                 last_root[0] = root
                 dist.gather(gene_t, gdst if rank == root else None, dst=root)
@@ -461,6 +461,29 @@ def main():
         step()
     finish()
     torch.cuda.synchronize()
+    collector = None
+    if world > 2 and not strong:
+        # untimed trial of the two ways to collect (2 x N steps): the rotating collector is the faster one where it has
+        # been measured, but a fabric on which it is not must not decide the figure (rank 0 collecting is the fallback)
+        trial = {}
+        for mode in (True, False):
+            rotate[0] = mode
+            dist.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(world):
+                step()
+            finish()
+            t1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            trial[mode] = float(tt.item()) / world
+        rotate[0] = trial[True] <= trial[False]
+        collector = {"rotating_ms_per_step": round(trial[True], 4), "rank0_ms_per_step": round(trial[False], 4),
+                     "chosen": "rotating (rank step mod N)" if rotate[0] else "rank 0"}
+    elif world == 2 and not strong:
+        collector = {"chosen": "rotating (rank step mod N)"}
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -715,6 +738,8 @@ def main():
             line["parity"] = parity
         if shards is not None:
             line["gathered_shards"] = shards
+        if collector:
+            line["collector"] = collector
         if modes:
             line["modes"] = modes
         if one_process:
