@@ -388,6 +388,13 @@ def main():
     gather_plan = None
     gstream = torch.cuda.Stream() if world > 1 else None
     step_no, last_root, rotate = [0], [0], [True]
+    # "lanes": one NCCL communicator + stream + table copies per collecting rank, so that the gathers of consecutive steps
+    # (different collectors) are in flight at the same time. One communicator serialises its collectives, and one gather
+    # lasts as long as its collector needs to take in N - 1 tables (1.6 ms at N = 8 whoever collects: measured, r02X).
+    lanes = {"on": False, "pg": [], "st": [], "pc": [], "gc": []}
+    if world > 1 and not strong:
+        lanes["pg"] = [dist.new_group(backend="nccl") for _ in range(world)]
+        lanes["st"] = [torch.cuda.Stream() for _ in range(world)]
 
     def step():
         nonlocal gather_plan
@@ -419,6 +426,23 @@ def main():
             gather_plan = (pair_t, pdst, gene_t, gdst, torch.cuda.Event(), torch.empty_like(pair_t))
         pair_t, pdst, gene_t, gdst, ev_gene, pair_copy = gather_plan
         sess.run_pairs(0, 1, stream)
+        if lanes["on"]:
+            ln = step_no[0] % world
+            step_no[0] += 1
+            last_root[0] = ln
+            if not lanes["pc"]:
+                lanes["pc"] = [torch.empty_like(pair_t) for _ in range(world)]
+                lanes["gc"] = [torch.empty_like(gene_t) for _ in range(world)]
+            ls = lanes["st"][ln]
+            tstream.wait_stream(ls)               # the lane's previous gather (N steps ago) has read its copies
+            lanes["pc"][ln].copy_(pair_t)
+            lanes["gc"][ln].copy_(gene_t)
+            ev_gene.record(tstream)               # the gene table is free for the next run_prepare
+            ls.wait_stream(tstream)
+            with torch.cuda.stream(ls):
+                dist.gather(lanes["gc"][ln], gdst if rank == ln else None, dst=ln, group=lanes["pg"][ln])
+                dist.gather(lanes["pc"][ln], pdst if rank == ln else None, dst=ln, group=lanes["pg"][ln])
+            return
         tstream.wait_stream(gstream)              # the previous gather has read the copy
         pair_copy.copy_(pair_t)
         pair_t = pair_copy
@@ -449,6 +473,8 @@ def main():
     def finish():
         if world > 1:
             tstream.wait_stream(gstream)
+            for ls in lanes["st"]:
+                tstream.wait_stream(ls)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -462,28 +488,32 @@ def main():
     finish()
     torch.cuda.synchronize()
     collector = None
-    if world > 2 and not strong:
-        # untimed trial of the two ways to collect (2 x N steps): the rotating collector is the faster one where it has
-        # been measured, but a fabric on which it is not must not decide the figure (rank 0 collecting is the fallback)
+    if world > 1 and not strong:
+        # untimed trial of the three ways to collect (N warm + N timed steps each); the fastest one is used for the
+        # measurement, so a fabric on which one of them misbehaves cannot decide the figure
         trial = {}
-        for mode in (True, False):
-            rotate[0] = mode
+        for mode in ("rank 0", "rotating (rank step mod N)", "rotating, one communicator per collector"):
+            rotate[0] = mode != "rank 0"
+            lanes["on"] = mode.endswith("collector")
+            for _ in range(world):
+                step()
+            finish()
+            torch.cuda.synchronize()
             dist.barrier()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
-            for _ in range(world):
+            for _ in range(2 * world):
                 step()
             finish()
             t1.record()
             torch.cuda.synchronize()
             tt = torch.tensor([t0.elapsed_time(t1)], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            trial[mode] = float(tt.item()) / world
-        rotate[0] = trial[True] <= trial[False]
-        collector = {"rotating_ms_per_step": round(trial[True], 4), "rank0_ms_per_step": round(trial[False], 4),
-                     "chosen": "rotating (rank step mod N)" if rotate[0] else "rank 0"}
-    elif world == 2 and not strong:
-        collector = {"chosen": "rotating (rank step mod N)"}
+            trial[mode] = float(tt.item()) / (2 * world)
+        best = min(trial, key=lambda k: trial[k])
+        rotate[0] = best != "rank 0"
+        lanes["on"] = best.endswith("collector")
+        collector = {"trial_ms_per_step": {k: round(v, 4) for k, v in trial.items()}, "chosen": best}
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
