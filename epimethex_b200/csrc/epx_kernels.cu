@@ -1674,7 +1674,6 @@ cudaError_t launch_check_finite(const double *a, int64_t rows, int64_t n, int64_
 }
 
 
-static size_t sort_smem(int n) { return (size_t)((n + 1) & ~1) * 8 + ctasort_smem(n); }
 
 template <typename F> static cudaError_t allow_max_dynamic_smem(F *func)
 {

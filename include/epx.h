@@ -184,7 +184,10 @@ int  epx_session_result_device_ptr(epx_session *s, int which, void **ptr, int64_
  * only the rows its genes reference) and the whole expression matrix (the
  * gene-level kernels run everywhere, so the bin.var reference gene needs no exchange) and computes its own pairs,
  * which are copied straight into the caller's result tables (the destination is host memory, so no device-to-device
- * gather is needed in this mode; the one-process-per-GPU mode of bench.py gathers over NCCL instead). */
+ * gather is needed in this mode; the one-process-per-GPU mode of bench.py gathers over NCCL instead). The expression
+ * matrix goes over PCIe to the first device only; the others copy it from there (peer copies behind an event). Result
+ * tables in page-locked memory should come from epx_host_alloc (portable: pinned for every device). With EPX_TRACE set
+ * in the environment, epx_multi_analyze prints the host-side phase times of every device thread to stderr. */
 typedef struct epx_multi epx_multi;
 int  epx_multi_create(const int *devices, int n_devices, epx_multi **out, char *err, size_t errlen);
 void epx_multi_destroy(epx_multi *m);
