@@ -1,12 +1,22 @@
 /*
- * epx_warpsort.cuh — one warp orders one row (n <= 32*EPS values) entirely in registers.
+ * epx_warpsort.cuh — one warp orders one row (n <= 32*EPS values) entirely in registers and its own shared memory.
  *
- * The row's doubles are mapped to order-preserving 64-bit keys, the bits all keys share are stripped,
- * and the leading (31 - IDXB) remaining bits ("coarse key") are packed above the sample index, below a pad
- * flag, into ONE 32-bit word per element.  A direction-free bitonic network then sorts the words with one VIMNMX per
- * compare-exchange half: strides below EPS stay inside a thread, larger strides are one SHFL each.
- * Only rows in which two neighbours of the sorted order share a coarse key (exact ties, or values closer
- * than ~2^-22 of the row's key range) take the exact path: an odd-even transposition on the full keys,
+ * Two paths, same result (ascending by (value, sample index), tie marks):
+ *
+ * order_bucket (round 2; rows of 257..512 values, and the two halves of 513..1024-value rows): every value is dropped
+ * near its final position by a counting pass over a linear map of the row's range (shared-memory atomics), a
+ * 16-value network inside each thread and one merge across the thread boundaries settle what shares a bucket, a
+ * check decides whether that was enough, and a row that fails takes the full network below. See the comment at
+ * order_bucket.
+ *
+ * order (round 1; shorter rows, chunks of the merge sort, the fallback): the row's doubles are mapped to
+ * order-preserving 64-bit keys, the bits all keys share are stripped, and the leading (31 - IDXB) remaining bits
+ * ("coarse key") are packed above the sample index, below a pad flag, into ONE 32-bit word per element.  A
+ * direction-free bitonic network then sorts the words with one VIMNMX per compare-exchange half: strides below EPS
+ * stay inside a thread, larger strides are one SHFL each.
+ *
+ * Either way only rows in which two neighbours of the sorted order share a coarse key (exact ties, or values closer
+ * than ~2^-22 of the row's range) take the exact path of finish(): an odd-even transposition on the full values,
  * restricted to those neighbours, which also yields the tie marks.  The result is exact for any input.
  */
 #pragma once

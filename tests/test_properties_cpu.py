@@ -65,3 +65,35 @@ def test_guard_matches_sd_of_recycled_differences(a, b):
     L = max(a.size, b.size)
     d = np.array([a[i % a.size] - b[i % b.size] for i in range(L)])
     assert oracle.guard(a, b) == (0 if np.all(d == d[0]) else 1)
+
+
+def test_sixty_comparator_network_of_the_rank_kernel_sorts_every_zero_one_input():
+    """The 16 words a thread holds after the bucket placement are ordered by the 60-comparator network written out in
+    epx_warpsort.cuh (sort16_thread). Zero-one principle: a comparator network that sorts all 2^16 zero-one inputs
+    sorts everything. The comparators are read from the shipped header, not from a copy."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "epimethex_b200", "csrc",
+                            "epx_warpsort.cuh")).read()
+    body = src[src.index("static void sort16_thread"):src.index("#undef EPX_CE")]
+    ces = [(int(a), int(b)) for a, b in re.findall(r"EPX_CE\((\d+), (\d+)\)", body)]
+    assert len(ces) == 60 and all(0 <= a < b < 16 for a, b in ces)
+    x = ((np.arange(1 << 16)[:, None] >> np.arange(16)[None, :]) & 1).astype(np.int8)
+    for a, b in ces:
+        lo, hi = np.minimum(x[:, a], x[:, b]), np.maximum(x[:, a], x[:, b])
+        x[:, a], x[:, b] = lo, hi
+    assert np.all(x[:, :-1] <= x[:, 1:])
+
+
+def test_slot_number_in_the_long_row_word_names_the_slot_of_arrival():
+    """epx_ctabucket.cuh keeps the low six bits of a value's slot of arrival in its word; after the short network a
+    value sits fewer than 32 slots away, and p0 = k - 32 + ((lid - (k - 32)) mod 64) must give the slot back, also at the
+    start of the row where k - 32 is negative (the kernel computes in unsigned arithmetic)."""
+    for k in list(range(0, 70)) + [8999, 16383]:
+        for delta in range(-31, 32):
+            p0 = k + delta
+            if p0 < 0:
+                continue
+            lid = p0 & 63
+            got = (k - 32) + (((lid - ((k - 32) & 0xffffffff)) & 0xffffffff) & 63)
+            assert got == p0, (k, delta, got)
