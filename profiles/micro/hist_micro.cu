@@ -1,4 +1,5 @@
 // Microbenchmark (B200): cost of the warp-level histogram primitives a bucket sort would need.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o hist_micro hist_micro.cu ; results on B200: profiles/r02m_hist_micro.txt
 // Each warp owns 512 u32 counters in shared memory and issues 16 operations per "row" on pseudo-random buckets.
 // Prints ns per row per SM-resident warp set and derived cycles per warp-instruction per SM.
 #include <cstdio>
