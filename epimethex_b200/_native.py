@@ -26,7 +26,7 @@ EXPORTS = [
     "epx_session_set_methylation_cols", "epx_session_set_methylation_device", "epx_session_set_expression",
     "epx_session_set_index", "epx_session_run", "epx_session_run_prepare", "epx_session_run_pairs",
     "epx_session_pairs_chunk", "epx_session_wait", "epx_session_fetch", "epx_session_timing",
-    "epx_session_result_device_ptr", "epx_analyze", "epx_multi_create", "epx_multi_destroy",
+    "epx_session_result_device_ptr", "epx_analyze", "epx_analyze_host", "epx_multi_create", "epx_multi_destroy",
     "epx_multi_set_methylation_rows", "epx_multi_set_methylation_cols", "epx_multi_set_methylation_sliced",
     "epx_multi_analyze", "epx_multi_groups", "epx_session_run_groups", "epx_session_fetch_groups",
     "epx_write_csv", "epx_format_real15",
@@ -110,6 +110,7 @@ def lib():
     L.epx_session_timing.argtypes = [vp, C.POINTER(Timing)] + e
     L.epx_session_result_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)] + e
     L.epx_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
+    L.epx_analyze_host.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
     L.epx_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)] + e
     L.epx_multi_destroy.argtypes = [vp]
     L.epx_multi_destroy.restype = None
@@ -399,6 +400,33 @@ class Session:
         b = _errbuf()
         _check(lib().epx_analyze(self._h, expr.ctypes.data, expr.shape[0], expr.shape[1], row_ptr.ctypes.data,
                                  probe_idx.ctypes.data, C.byref(opt), C.byref(r), b, len(b)), b)
+        res.counts, res.ref_gene = tuple(r.counts), r.ref_gene
+        res.timing = self.timing()
+        return res
+
+    def analyze_host(self, meth_rows, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True,
+                     pinned_results: bool = False) -> Result:
+        """One blocking epx_analyze_host call: the methylation matrix stays in host memory ([P, n] probe-major float64,
+        any row stride) and only the rows the index names are uploaded -- fetched by the device itself when the matrix
+        is page-locked (pinned_empty), else the whole matrix through the staged upload. The session then holds a
+        partial matrix: the next call is analyze_host again, or set_methylation."""
+        rows = np.asarray(meth_rows)
+        if rows.dtype != np.float64 or rows.ndim != 2 or rows.strides[1] != 8:
+            rows = np.ascontiguousarray(rows, np.float64)
+        ld = rows.strides[0] // 8 if rows.shape[0] > 1 else rows.shape[1]
+        expr = np.ascontiguousarray(expr, np.float64)
+        row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        probe_idx = np.ascontiguousarray(probe_idx, np.int32)
+        if rows.shape[1] != expr.shape[1]:
+            raise ValueError(f"sample counts differ: methylation {rows.shape[1]}, expression {expr.shape[1]}")
+        self.n_genes, self.n_samples = expr.shape
+        self.n_pairs = int(row_ptr[-1])
+        res, r = self._alloc_result(full, pinned_results)
+        opt = options if options is not None else make_options()
+        b = _errbuf()
+        _check(lib().epx_analyze_host(self._h, rows.ctypes.data, rows.shape[0], ld, expr.ctypes.data, expr.shape[0],
+                                      expr.shape[1], row_ptr.ctypes.data, probe_idx.ctypes.data, C.byref(opt),
+                                      C.byref(r), b, len(b)), b)
         res.counts, res.ref_gene = tuple(r.counts), r.ref_gene
         res.timing = self.timing()
         return res

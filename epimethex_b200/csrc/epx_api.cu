@@ -72,6 +72,7 @@ struct epx_session {
     DevBuf<double> meth_own;
     const double *meth = nullptr;
     int64_t P = 0, n_meth = 0, ld = 0;
+    bool meth_partial = false; /* epx_analyze_host: only the rows the current index names are on the device */
     /* expression */
     DevBuf<double> expr;
     int64_t G = 0, n = 0;
@@ -304,7 +305,7 @@ int epx_session_set_methylation_rows(epx_session *s, const double *rows, int64_t
     const int64_t dld = round_up(n_samples, 4); /* 32-byte aligned rows */
     EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
     /* a failed upload leaves no usable matrix behind */
-    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    s->meth = nullptr; s->meth_partial = false; s->prepared = false; s->ran = false; s->n_groups = -1;
     EPX_CUDA(arm_finite_check(s, s->stream));
     if (ld == dld) {
         EPX_CUDA(cudaMemcpyAsync(s->meth_own.p, rows, (size_t)(n_probes * dld) * 8, cudaMemcpyHostToDevice, s->stream));
@@ -364,7 +365,7 @@ int epx_session_set_methylation_cols(epx_session *s, const double *const *cols, 
     if (chunk > n_samples) chunk = (int)n_samples;
     DevBuf<double> stage;
     EPX_CUDA(stage.reserve((size_t)chunk * (size_t)n_probes));
-    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    s->meth = nullptr; s->meth_partial = false; s->prepared = false; s->ran = false; s->n_groups = -1;
     EPX_CUDA(arm_finite_check(s, s->stream));
     for (int64_t s0 = 0; s0 < n_samples; s0 += chunk) {
         const int ns = (int)((n_samples - s0) < chunk ? (n_samples - s0) : chunk);
@@ -399,7 +400,7 @@ int epx_session_set_methylation_device(epx_session *s, const double *d_rows, int
         return fail(err, errlen, EPX_EINVAL, "device methylation rows must be 16-byte aligned with an even leading dimension (bulk copies)");
     EPX_CUDA(cudaSetDevice(s->device));
     s->meth_own.release();
-    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    s->meth = nullptr; s->meth_partial = false; s->prepared = false; s->ran = false; s->n_groups = -1;
     EPX_CUDA(arm_finite_check(s, s->stream));
     EPX_CUDA(launch_check_finite(d_rows, n_probes, n_samples, ld, s->first_bad.p, s->stream));
     EPX_CUDA(cudaStreamSynchronize(s->stream));
@@ -450,11 +451,12 @@ int epx_session_set_expression(epx_session *s, const double *expr, int64_t n_gen
     return set_expression_finish(s, n_genes, n_samples, err, errlen);
 }
 
-int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
-                          char *err, size_t errlen)
+/* host_call: epx_analyze_host builds the index BEFORE the rows it names are fetched (s->P is set, s->meth not yet) */
+static int set_index_impl(epx_session *s, const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
+                          bool host_call, char *err, size_t errlen)
 {
     if (!s || !row_ptr || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad index arguments");
-    if (!s->meth) return fail(err, errlen, EPX_ESTATE, "set the methylation matrix before the index");
+    if (!s->meth && !host_call) return fail(err, errlen, EPX_ESTATE, "set the methylation matrix before the index");
     if (row_ptr[0] != 0) return fail(err, errlen, EPX_EINVAL, "row_ptr[0] must be 0");
     const int64_t Np = row_ptr[n_genes];
     if (Np < 0 || Np > 0x7fffffff) return fail(err, errlen, EPX_EINVAL, "pair count %lld out of range", (long long)Np);
@@ -465,6 +467,10 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
         memcmp(s->h_row_ptr.data(), row_ptr, ((size_t)n_genes + 1) * sizeof(int64_t)) == 0 &&
         (Np == 0 || memcmp(s->h_probe_idx, probe_idx, (size_t)Np * sizeof(int32_t)) == 0))
         return EPX_OK;
+    if (s->meth_partial && !host_call)
+        return fail(err, errlen, EPX_ESTATE,
+                    "the session holds only the methylation rows of the last epx_analyze_host index: upload the matrix "
+                    "(epx_session_set_methylation_*) before another index, or call epx_analyze_host again");
     EPX_CUDA(cudaSetDevice(s->device));
 
     /* Host bookkeeping of a new index. The reference is called once per gene range (README.md:90), so this runs on
@@ -591,6 +597,12 @@ int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t 
     s->prepared = false;
     s->Np = Np; s->U = (int64_t)n_uniq; s->n_items = (int64_t)n_items; s->G_index = n_genes;
     return EPX_OK;
+}
+
+int epx_session_set_index(epx_session *s, const int64_t *row_ptr, const int32_t *probe_idx, int64_t n_genes,
+                          char *err, size_t errlen)
+{
+    return set_index_impl(s, row_ptr, probe_idx, n_genes, false, err, errlen);
 }
 
 /* Tables that depend on the sample count alone, built once per n on the host with the same epx_math.h code the
@@ -1017,6 +1029,77 @@ int epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_s
     rc = epx_session_run(s, opt, nullptr, err, errlen);
     if (rc) return rc;
     return epx_session_fetch(s, out, nullptr, err, errlen);
+}
+
+/* The caller's matrix as the device sees it, when the device can read it in place: page-locked host memory
+ * (epx_host_alloc, cudaHostAlloc, cudaHostRegister) -- or device memory, which the same kernel reads just as well.
+ * NULL for pageable memory. Both ends of the matrix must lie in the same mapping. */
+static const double *rows_readable_by_device(const double *rows, int64_t n_probes, int64_t n_samples, int64_t ld)
+{
+    const double *last = rows + (n_probes - 1) * ld + (n_samples - 1);
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, rows) != cudaSuccess || cudaPointerGetAttributes(&a1, last) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if ((a0.type != cudaMemoryTypeHost && a0.type != cudaMemoryTypeDevice) || a1.type != a0.type) return nullptr;
+    if (!a0.devicePointer || !a1.devicePointer) return nullptr;
+    if ((const char *)a1.devicePointer - (const char *)a0.devicePointer != (const char *)last - (const char *)rows) return nullptr;
+    return (const double *)a0.devicePointer;
+}
+
+int epx_analyze_host(epx_session *s, const double *meth_rows, int64_t n_probes, int64_t ld, const double *expr,
+                     int64_t n_genes, int64_t n_samples, const int64_t *row_ptr, const int32_t *probe_idx,
+                     const epx_options *opt, epx_result *out, char *err, size_t errlen)
+{
+    if (!s || !meth_rows || n_probes < 1 || ld < n_samples) return fail(err, errlen, EPX_EINVAL, "bad methylation arguments");
+    int rc = check_samples(s, n_samples, err, errlen);
+    if (rc) return rc;
+    EPX_CUDA(cudaSetDevice(s->device));
+    const double *src = getenv("EPX_NO_ZEROCOPY") ? nullptr : rows_readable_by_device(meth_rows, n_probes, n_samples, ld);
+    if (!src) {
+        /* pageable memory: the device cannot fetch rows by itself; whole matrix through the staged upload */
+        rc = epx_session_set_methylation_rows(s, meth_rows, n_probes, n_samples, ld, err, errlen);
+        if (rc) return rc;
+        return epx_analyze(s, expr, n_genes, n_samples, row_ptr, probe_idx, opt, out, err, errlen);
+    }
+    const bool trace = getenv("EPX_TRACE") != nullptr; /* host-side phase times, to stderr */
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    const int64_t dld = round_up(n_samples, 4);
+    /* no usable matrix until the rows have arrived and passed the finite check */
+    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
+    if (s->index_P != n_probes) s->G_index = -1; /* as in set_methylation_*: the index depends on the row count only */
+    s->P = n_probes; s->n_meth = n_samples; s->ld = dld; s->meth_partial = true;
+    /* the expression matrix is on its way to the device while the host builds the index */
+    rc = set_expression_begin(s, expr, n_genes, n_samples, 0, err, errlen);
+    if (rc) return rc;
+    rc = set_index_impl(s, row_ptr, probe_idx, n_genes, true, err, errlen);
+    if (rc) { cudaStreamSynchronize(s->stream); return rc; }
+    rc = set_expression_finish(s, n_genes, n_samples, err, errlen);
+    if (rc) return rc;
+    const double t_index = ms_since(t_start);
+    /* the rows the index names (s->uniq_probe, ascending), straight from the caller's memory into their places */
+    const auto t_rows = std::chrono::steady_clock::now();
+    EPX_CUDA(arm_finite_check(s, s->stream));
+    EPX_CUDA(launch_gather_host_rows(src, ld, s->uniq_probe.p, s->U, n_samples, s->meth_own.p, dld, s->first_bad.p, s->stream));
+    EPX_CUDA(cudaStreamSynchronize(s->stream));
+    rc = finite_check_result(s, "methylation", "probe", n_samples, err, errlen);
+    if (rc) return rc;
+    const double t_fetch = ms_since(t_rows);
+    s->meth = s->meth_own.p;
+    const auto t_run = std::chrono::steady_clock::now();
+    rc = epx_session_run(s, opt, nullptr, err, errlen);
+    if (rc) return rc;
+    rc = epx_session_fetch(s, out, nullptr, err, errlen);
+    if (trace)
+        fprintf(stderr, "epx_analyze_host: expression upload + index %.2f ms, %lld rows of %lld fetched in %.2f ms (%.1f GB/s), "
+                        "kernels + tables back %.2f ms\n", t_index, (long long)s->U, (long long)n_probes, t_fetch,
+                (double)s->U * (double)n_samples * 8.0 / (t_fetch * 1e6), ms_since(t_run));
+    return rc;
 }
 
 

@@ -171,6 +171,10 @@ cudaError_t launch_transpose_cols(const double *src, double *dst, int64_t P, int
 /* dst[r*ld + j] = src[r*n + j]: re-space contiguous rows to the padded leading dimension (row0 = first row's number) */
 cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, int64_t row0,
                                 unsigned long long *first_bad, cudaStream_t st);
+/* dst[p*ld + j] = src[p*lds + j] for the rows p = uniq[0..U) only; src is HOST memory the device can read in place
+ * (page-locked), fetched over PCIe by the kernel itself (epx_analyze_host) */
+cudaError_t launch_gather_host_rows(const double *src, int64_t lds, const int32_t *uniq, int64_t U, int64_t n, double *dst,
+                                    int64_t ld, unsigned long long *first_bad, cudaStream_t st);
 /* finite test alone, for matrices that need no re-spacing */
 cudaError_t launch_check_finite(const double *a, int64_t rows, int64_t n, int64_t ld, unsigned long long *first_bad,
                                 cudaStream_t st);

@@ -1655,7 +1655,52 @@ __global__ void __launch_bounds__(256) k_check_finite(const double *__restrict__
     }
 }
 
+/* Rows of a page-locked HOST matrix fetched over PCIe by the kernel itself -- only the rows the index names
+ * (uniq[0..U), ascending) -- into their places in the padded device matrix: the upload, the subset() of
+ * R/EpimethexAnalysis.R:281-282 (methylation rows of the annotated probes of the gene range) and the re-spacing in one
+ * pass. A warp takes a row; every load instruction of the warp covers one 256-byte block of host memory that starts
+ * on a 128-byte boundary (whole read requests on the bus but for the two ends of the row: rows of 473 doubles start
+ * at any multiple of 8 bytes), eight loads in flight per lane. Lanes in front of the row or behind it load nothing. */
+__global__ void __launch_bounds__(256) k_gather_host_rows(const double *__restrict__ src, int64_t lds,
+                                                          const int32_t *__restrict__ uniq, int64_t U, int n,
+                                                          double *__restrict__ dst, int64_t ld,
+                                                          unsigned long long *first_bad)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < U; u += nw) {
+        const int64_t p = uniq[u];
+        const double *s = src + p * lds;
+        double *d = dst + p * ld;
+        const int lead = (int)(((uintptr_t)s & 127) >> 3); /* doubles between the 128-byte boundary below the row and the row */
+        for (int j0 = -lead; j0 < n; j0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int j = j0 + k * 32 + lane;
+                v[k] = (j >= 0 && j < n) ? __ldcs(s + j) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int j = j0 + k * 32 + lane;
+                if (j >= 0 && j < n) {
+                    d[j] = v[k];
+                    note_nonfinite(v[k], (unsigned long long)(p * n + j), first_bad);
+                }
+            }
+        }
+    }
+}
+
 /* ============================================================ launchers */
+
+cudaError_t launch_gather_host_rows(const double *src, int64_t lds, const int32_t *uniq, int64_t U, int64_t n, double *dst,
+                                    int64_t ld, unsigned long long *first_bad, cudaStream_t st)
+{
+    if (U <= 0) return cudaSuccess;
+    k_gather_host_rows<<<148 * 8, 256, 0, st>>>(src, lds, uniq, U, (int)n, dst, ld, first_bad);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_respace_rows(const double *src, double *dst, int64_t rows, int64_t n, int64_t ld, int64_t row0,
                                 unsigned long long *first_bad, cudaStream_t st)

@@ -18,6 +18,7 @@
  *                                   R/Functions.R:2-22,26-80,85-132,192-220
  *   epx_session_fetch               the `.combine = cbind` fold of foreach (R/EpimethexAnalysis.R:352)
  *   epx_analyze                     all of the above in one blocking call with host buffers
+ *   epx_analyze_host                the same plus R/EpimethexAnalysis.R:278-282 (only the annotated probes' rows are uploaded)
  *
  * Error convention: every function returns 0 on success or a negative EPX_E* code and, when `err` is
  * non-NULL, writes a NUL-terminated message into err[0..errlen).  The library never calls into R, never
@@ -249,6 +250,24 @@ int  epx_format_real15(double x, char *buf, size_t buflen);
 int  epx_analyze(epx_session *s, const double *expr, int64_t n_genes, int64_t n_samples,
                  const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
                  epx_result *out, char *err, size_t errlen);
+
+/* The same with the methylation matrix still in HOST memory (probe-major rows as in epx_session_set_methylation_rows):
+ * only the rows the index names cross the bus. Replaces, on top of epx_analyze, the methylation filter of
+ * R/EpimethexAnalysis.R:278-282 (`subset(dfMethylation, sample %in% dfAnnotations$cg)`: the reference keeps the rows of
+ * the annotated probes of the gene range and nothing else) together with the upload: when `meth_rows` is page-locked
+ * (epx_host_alloc, cudaHostAlloc, cudaHostRegister) a kernel fetches exactly those rows over PCIe from the caller's
+ * memory into the session's device matrix -- a 1,000-gene range of the SKCM shape moves ~5 % of the matrix, the whole
+ * genome 75 % (the probes no gene names stay behind). Pageable `meth_rows`: the device cannot read them in place, the
+ * call is epx_session_set_methylation_rows + epx_analyze (same tables). NaN / infinite values are refused (EPX_EINVAL)
+ * in the rows the index names; other rows are never looked at, as in the reference, where they are dropped before any
+ * arithmetic. Afterwards the session holds a PARTIAL matrix: epx_session_run* / run_groups / fetch work on this index,
+ * epx_session_set_index / epx_analyze with another index answer EPX_ESTATE until a whole matrix is uploaded
+ * (epx_session_set_methylation_*) -- or call epx_analyze_host again, which is the intended use: one call per gene
+ * range (README.md:90), nothing kept in between but the allocations. */
+int  epx_analyze_host(epx_session *s, const double *meth_rows, int64_t n_probes, int64_t ld,
+                      const double *expr, int64_t n_genes, int64_t n_samples,
+                      const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
+                      epx_result *out, char *err, size_t errlen);
 
 #ifdef __cplusplus
 }
