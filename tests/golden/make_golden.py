@@ -6,7 +6,8 @@
                         of the path (numpy / fractions / big integers / mpmath, written from the R sources; imports
                         neither oracle/ nor libepx): exact KS (n = 99), asymptotic KS (n = 474), the n mod 3 extension
                         (n = 473), 3-decimal rounded betas (ties: exact falls back to asymptotic), both methylation tests,
-                        both expression tests, and the pooled CG_of_a_genes rows.
+                        both expression tests, and the pooled CG_of_a_genes rows; four more at 600 / 1,000 / 1,500 / 1,501
+                        samples, where the CUDA path runs other kernels (the statistics are the same).
 
 R is not installable in the build environment, so NONE of this is R output (parity unpinned); it is the strongest pin
 available without R: tests/test_golden_cpu.py holds the oracle to these tables and tests/test_gpu_golden.py the CUDA
@@ -34,6 +35,11 @@ CASES = {
     "n99_ties3": dict(G=40, n=99, P=170, decimals=3),
     "n474_ties3": dict(G=40, n=474, P=170, decimals=3),
     "n30_tiny_ties2": dict(G=24, n=30, P=90, decimals=2),
+    # longer rows (the CUDA path changes kernels at 513 and 1025 samples; the statistics do not change with n)
+    "n600_ties2": dict(G=24, n=600, P=100, decimals=2),          # two-halves rank kernel, long tie runs
+    "n1000_epic": dict(G=30, n=1000, P=130, decimals=None),      # BASELINE configs[3] sample count, n mod 3 = 1
+    "n1500_long": dict(G=24, n=1500, P=100, decimals=None),      # CTA-per-row kernels
+    "n1501_long_ties3": dict(G=24, n=1501, P=100, decimals=3),   # the same with ties and the n mod 3 extension
 }
 
 
