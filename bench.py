@@ -771,6 +771,30 @@ def main():
                            "ms_per_call": round(call_ms, 3), "pairs_per_s": Np / (call_ms * 1e-3), "calls_ms": [round(v, 2) for v in calls[1:]],
                            "methylation_upload_s": round(up_s, 3), "single_gpu_call_ms": None,
                            "identical_to_single_gpu_tables": bool(same)}
+            # the same whole-genome call with the matrix still in host memory: every device fetches, over its own PCIe
+            # link, the rows its gene range names (epx_multi_analyze_host) -- end to end for ONE cohort on N GPUs
+            if wl["pinned"] and not args.no_analyze_host:
+                try:
+                    hcalls = []
+                    for i in range(1 + 5):
+                        rp_i, pi_i = variants[i & 1]
+                        t0 = time.perf_counter()
+                        ms_.analyze_host(wl["meth"], wl["expr_pinned"], rp_i, pi_i, opts, full=False, pinned_results=True)
+                        hcalls.append((time.perf_counter() - t0) * 1e3)
+                    mh = ms_.analyze_host(wl["meth"], wl["expr_pinned"], idx.row_ptr, idx.probe_idx, opts)
+                    same_h = all(np.array_equal(getattr(single, k), getattr(mh, k), equal_nan=True)
+                                 for k in ("pair", "pair_stat", "gene")) and all(
+                        np.array_equal(getattr(single, k), getattr(mh, k)) for k in ("ks_dnum", "pair_na", "gene_na", "perm"))
+                    h_ms = float(np.median(hcalls[1:]))
+                    one_process["analyze_host"] = {
+                        "what": "epx_multi_analyze_host: the same call with the methylation matrix in page-locked host memory, "
+                                "every device fetches the rows of its own gene range (end to end, nothing resident)",
+                        "ms_per_call": round(h_ms, 3), "pairs_per_s": Np / (h_ms * 1e-3), "calls_ms": [round(v, 2) for v in hcalls[1:]],
+                        "single_gpu_call_ms": round(host_t, 3) if host_t == host_t else None,
+                        "identical_to_single_gpu_tables": bool(same_h)}
+                    del mh
+                except _native.EpxError as ex:
+                    one_process["analyze_host"] = {"error": str(ex)}
             ms_.close()
         dist.barrier(group=cpu_group)
 

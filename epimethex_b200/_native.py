@@ -28,7 +28,7 @@ EXPORTS = [
     "epx_session_pairs_chunk", "epx_session_wait", "epx_session_fetch", "epx_session_timing",
     "epx_session_result_device_ptr", "epx_analyze", "epx_analyze_host", "epx_multi_create", "epx_multi_destroy",
     "epx_multi_set_methylation_rows", "epx_multi_set_methylation_cols", "epx_multi_set_methylation_sliced",
-    "epx_multi_analyze", "epx_multi_groups", "epx_session_run_groups", "epx_session_fetch_groups",
+    "epx_multi_analyze", "epx_multi_analyze_host", "epx_multi_groups", "epx_session_run_groups", "epx_session_fetch_groups",
     "epx_write_csv", "epx_format_real15",
 ]
 
@@ -119,6 +119,7 @@ def lib():
     L.epx_multi_groups.argtypes = [vp, vp, vp, i64, C.POINTER(_GroupResult)] + e
     L.epx_multi_set_methylation_sliced.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64] + e
     L.epx_multi_analyze.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
+    L.epx_multi_analyze_host.argtypes = [vp, vp, i64, i64, vp, i64, i64, vp, vp, C.POINTER(Options), C.POINTER(_Result)] + e
     L.epx_session_run_groups.argtypes = [vp, vp, vp, i64, vp] + e
     L.epx_session_fetch_groups.argtypes = [vp, C.POINTER(_GroupResult), vp] + e
     L.epx_write_csv.argtypes = [C.c_char_p, i64, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), vp, vp,
@@ -493,8 +494,14 @@ class MultiSession:
                                                       rows.shape[1], row_ptr.ctypes.data, probe_idx.ctypes.data,
                                                       row_ptr.size - 1, b, len(b)), b)
 
+    def analyze_host(self, meth_rows, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True,
+                     pinned_results: bool = False) -> Result:
+        """One blocking epx_multi_analyze_host call: the matrix stays in (page-locked) host memory, every device fetches
+        the rows its own gene range names."""
+        return self.analyze(expr, row_ptr, probe_idx, options, full, pinned_results, meth_rows=meth_rows)
+
     def analyze(self, expr, row_ptr, probe_idx, options: Options | None = None, full: bool = True,
-                pinned_results: bool = False) -> Result:
+                pinned_results: bool = False, meth_rows=None) -> Result:
         """One blocking epx_multi_analyze call. full / pinned_results as in Session.analyze: the two result tables only,
         written by every device straight into page-locked buffers this object keeps (copy what you keep)."""
         expr = np.ascontiguousarray(expr, np.float64)
@@ -528,7 +535,18 @@ class MultiSession:
                 r.gene_ks_dnum, r.perm = res.gene_ks_dnum.ctypes.data, res.perm.ctypes.data
         opt = options if options is not None else make_options()
         b = _errbuf()
-        _check(lib().epx_multi_analyze(self._h, expr.ctypes.data, G, n, row_ptr.ctypes.data, probe_idx.ctypes.data,
-                                       C.byref(opt), C.byref(r), b, len(b)), b)
+        if meth_rows is None:
+            _check(lib().epx_multi_analyze(self._h, expr.ctypes.data, G, n, row_ptr.ctypes.data, probe_idx.ctypes.data,
+                                           C.byref(opt), C.byref(r), b, len(b)), b)
+        else:
+            rows = np.asarray(meth_rows)
+            if rows.dtype != np.float64 or rows.ndim != 2 or rows.strides[1] != 8:
+                rows = np.ascontiguousarray(rows, np.float64)
+            if rows.shape[1] != n:
+                raise ValueError(f"sample counts differ: methylation {rows.shape[1]}, expression {n}")
+            ld = rows.strides[0] // 8 if rows.shape[0] > 1 else rows.shape[1]
+            _check(lib().epx_multi_analyze_host(self._h, rows.ctypes.data, rows.shape[0], ld, expr.ctypes.data, G, n,
+                                                row_ptr.ctypes.data, probe_idx.ctypes.data, C.byref(opt), C.byref(r),
+                                                b, len(b)), b)
         res.counts, res.ref_gene = tuple(r.counts), r.ref_gene
         return res

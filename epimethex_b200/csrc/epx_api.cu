@@ -1048,6 +1048,32 @@ static const double *rows_readable_by_device(const double *rows, int64_t n_probe
     return (const double *)a0.devicePointer;
 }
 
+/* epx_analyze_host / epx_multi_analyze_host, first half: the session gets a device matrix of the caller's shape with no
+ * valid row in it yet (the index is built against its row count before the rows it names are fetched) */
+static int host_rows_begin(epx_session *s, int64_t n_probes, int64_t n_samples, char *err, size_t errlen)
+{
+    const int64_t dld = round_up(n_samples, 4);
+    /* no usable matrix until the rows have arrived and passed the finite check */
+    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
+    EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
+    if (s->index_P != n_probes) s->G_index = -1; /* as in set_methylation_*: the index depends on the row count only */
+    s->P = n_probes; s->n_meth = n_samples; s->ld = dld; s->meth_partial = true;
+    return EPX_OK;
+}
+
+/* second half, after the index: the rows it names (s->uniq_probe, ascending), straight from the caller's memory into
+ * their places, checked for NaN / infinity; blocking */
+static int host_rows_fetch(epx_session *s, const double *src, int64_t ld, char *err, size_t errlen)
+{
+    EPX_CUDA(arm_finite_check(s, s->stream));
+    EPX_CUDA(launch_gather_host_rows(src, ld, s->uniq_probe.p, s->U, s->n_meth, s->meth_own.p, s->ld, s->first_bad.p, s->stream));
+    EPX_CUDA(cudaStreamSynchronize(s->stream));
+    int rc = finite_check_result(s, "methylation", "probe", s->n_meth, err, errlen);
+    if (rc) return rc;
+    s->meth = s->meth_own.p;
+    return EPX_OK;
+}
+
 int epx_analyze_host(epx_session *s, const double *meth_rows, int64_t n_probes, int64_t ld, const double *expr,
                      int64_t n_genes, int64_t n_samples, const int64_t *row_ptr, const int32_t *probe_idx,
                      const epx_options *opt, epx_result *out, char *err, size_t errlen)
@@ -1068,12 +1094,8 @@ int epx_analyze_host(epx_session *s, const double *meth_rows, int64_t n_probes, 
     auto ms_since = [&](std::chrono::steady_clock::time_point t) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
     };
-    const int64_t dld = round_up(n_samples, 4);
-    /* no usable matrix until the rows have arrived and passed the finite check */
-    s->meth = nullptr; s->prepared = false; s->ran = false; s->n_groups = -1;
-    EPX_CUDA(s->meth_own.reserve((size_t)(n_probes * dld)));
-    if (s->index_P != n_probes) s->G_index = -1; /* as in set_methylation_*: the index depends on the row count only */
-    s->P = n_probes; s->n_meth = n_samples; s->ld = dld; s->meth_partial = true;
+    rc = host_rows_begin(s, n_probes, n_samples, err, errlen);
+    if (rc) return rc;
     /* the expression matrix is on its way to the device while the host builds the index */
     rc = set_expression_begin(s, expr, n_genes, n_samples, 0, err, errlen);
     if (rc) return rc;
@@ -1082,15 +1104,10 @@ int epx_analyze_host(epx_session *s, const double *meth_rows, int64_t n_probes, 
     rc = set_expression_finish(s, n_genes, n_samples, err, errlen);
     if (rc) return rc;
     const double t_index = ms_since(t_start);
-    /* the rows the index names (s->uniq_probe, ascending), straight from the caller's memory into their places */
     const auto t_rows = std::chrono::steady_clock::now();
-    EPX_CUDA(arm_finite_check(s, s->stream));
-    EPX_CUDA(launch_gather_host_rows(src, ld, s->uniq_probe.p, s->U, n_samples, s->meth_own.p, dld, s->first_bad.p, s->stream));
-    EPX_CUDA(cudaStreamSynchronize(s->stream));
-    rc = finite_check_result(s, "methylation", "probe", n_samples, err, errlen);
+    rc = host_rows_fetch(s, src, ld, err, errlen);
     if (rc) return rc;
     const double t_fetch = ms_since(t_rows);
-    s->meth = s->meth_own.p;
     const auto t_run = std::chrono::steady_clock::now();
     rc = epx_session_run(s, opt, nullptr, err, errlen);
     if (rc) return rc;
@@ -1207,8 +1224,11 @@ int epx_multi_set_methylation_sliced(epx_multi *m, const double *rows, int64_t n
     return EPX_OK;
 }
 
-int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t n_samples, const int64_t *row_ptr,
-                      const int32_t *probe_idx, const epx_options *opt, epx_result *out, char *err, size_t errlen)
+/* epx_multi_analyze (meth_rows == NULL: every device holds its matrix already) and epx_multi_analyze_host (meth_rows =
+ * the caller's page-locked matrix: every device fetches the rows ITS gene range names, after its index is built) */
+static int multi_analyze_impl(epx_multi *m, const double *meth_rows, int64_t n_probes, int64_t ld, const double *expr,
+                              int64_t n_genes, int64_t n_samples, const int64_t *row_ptr, const int32_t *probe_idx,
+                              const epx_options *opt, epx_result *out, char *err, size_t errlen)
 {
     if (!m || !expr || !row_ptr || !out || n_genes < 1) return fail(err, errlen, EPX_EINVAL, "bad arguments");
     const int W = (int)m->sess.size();
@@ -1217,6 +1237,14 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
     std::atomic<int> expr_ready{0}; /* 1: device 0 has queued its upload and recorded ev_expr; -1: it failed */
     int rc_all = for_each_device(m, [&](int i, char *e, size_t el) -> int {
         epx_session *s = m->sess[(size_t)i];
+        if (meth_rows) {
+            int rb = cudaSetDevice(s->device) == cudaSuccess ? host_rows_begin(s, n_probes, n_samples, e, el)
+                                                             : fail(e, el, EPX_ECUDA, "cudaSetDevice(%d) failed", s->device);
+            if (rb) {
+                if (i == 0 && m->ev_expr) expr_ready.store(-1, std::memory_order_release); /* the other devices wait for this one's upload */
+                return rb;
+            }
+        }
         const int64_t g0 = cut[(size_t)i], g1 = cut[(size_t)i + 1];
         const int64_t lo = row_ptr[g0], hi = row_ptr[g1];
         std::vector<int64_t> rp((size_t)n_genes + 1);
@@ -1241,10 +1269,12 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
             for (int64_t k = 0; k < hi - lo; k++) {
                 if (pi[k] < 0) { local[(size_t)k] = -1; continue; }
                 auto it = std::lower_bound(u.begin(), u.end(), pi[k]);
-                if (it == u.end() || *it != pi[k])
+                if (it == u.end() || *it != pi[k]) {
+                    if (i == 0 && m->ev_expr) expr_ready.store(-1, std::memory_order_release); /* the other devices wait for this one's upload */
                     return fail(e, el, EPX_ESTATE, "pair %lld needs methylation row %d, which is not in this device's slice "
                                 "(the index differs from the one passed to epx_multi_set_methylation_sliced)",
                                 (long long)(lo + k), pi[k]);
+                }
                 local[(size_t)k] = (int32_t)(it - u.begin());
             }
             pi = local.data();
@@ -1277,12 +1307,19 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
         }
         if (rc) return rc;
         lap("expression begin");
-        rc = epx_session_set_index(s, rp.data(), pi, n_genes, e, el);
+        rc = set_index_impl(s, rp.data(), pi, n_genes, meth_rows != nullptr, e, el);
         if (rc) { cudaStreamSynchronize(s->stream); return rc; }
         lap("index");
         rc = set_expression_finish(s, n_genes, n_samples, e, el);
         if (rc) return rc;
         lap("expression there");
+        if (meth_rows) {
+            const double *src = rows_readable_by_device(meth_rows, n_probes, n_samples, ld); /* as THIS device sees it */
+            if (!src) return fail(e, el, EPX_EINVAL, "the methylation matrix is not page-locked for this device (use epx_host_alloc: portable)");
+            rc = host_rows_fetch(s, src, ld, e, el);
+            if (rc) return rc;
+            lap("rows fetched");
+        }
         rc = epx_session_run(s, opt, nullptr, e, el);
         if (rc) return rc;
         lap("run (enqueue)");
@@ -1294,6 +1331,31 @@ int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t
     if (rc_all == EPX_OK)
         for (int i = 0; i <= W; i++) m->pair_lo.push_back(row_ptr[cut[(size_t)i]]);
     return rc_all;
+}
+
+int epx_multi_analyze(epx_multi *m, const double *expr, int64_t n_genes, int64_t n_samples, const int64_t *row_ptr,
+                      const int32_t *probe_idx, const epx_options *opt, epx_result *out, char *err, size_t errlen)
+{
+    return multi_analyze_impl(m, nullptr, 0, 0, expr, n_genes, n_samples, row_ptr, probe_idx, opt, out, err, errlen);
+}
+
+int epx_multi_analyze_host(epx_multi *m, const double *meth_rows, int64_t n_probes, int64_t ld, const double *expr,
+                           int64_t n_genes, int64_t n_samples, const int64_t *row_ptr, const int32_t *probe_idx,
+                           const epx_options *opt, epx_result *out, char *err, size_t errlen)
+{
+    if (!m || m->sess.empty() || !meth_rows || n_probes < 1 || ld < n_samples) return fail(err, errlen, EPX_EINVAL, "bad methylation arguments");
+    int rc = check_samples(m->sess[0], n_samples, err, errlen);
+    if (rc) return rc;
+    EPX_CUDA(cudaSetDevice(m->sess[0]->device));
+    if (getenv("EPX_NO_ZEROCOPY") || !rows_readable_by_device(meth_rows, n_probes, n_samples, ld)) {
+        /* pageable memory: replicas of the whole matrix through the staged upload, then the resident-matrix call */
+        rc = epx_multi_set_methylation_rows(m, meth_rows, n_probes, n_samples, ld, err, errlen);
+        if (rc) return rc;
+        return epx_multi_analyze(m, expr, n_genes, n_samples, row_ptr, probe_idx, opt, out, err, errlen);
+    }
+    m->sliced = false;      /* every device indexes its (partial) matrix by the caller's row numbers */
+    m->rows_of.clear();
+    return multi_analyze_impl(m, meth_rows, n_probes, ld, expr, n_genes, n_samples, row_ptr, probe_idx, opt, out, err, errlen);
 }
 
 int epx_multi_groups(epx_multi *m, const int64_t *group_ptr, const int32_t *group_pairs, int64_t n_groups,

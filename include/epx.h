@@ -268,6 +268,16 @@ int  epx_analyze_host(epx_session *s, const double *meth_rows, int64_t n_probes,
                       const double *expr, int64_t n_genes, int64_t n_samples,
                       const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
                       epx_result *out, char *err, size_t errlen);
+/* The same on several GPUs from one process (epx_multi_analyze with the matrix still in host memory): the genes are cut
+ * into ranges of equal pair counts as in epx_multi_analyze, and every device fetches, over its own PCIe link, only the
+ * rows ITS range names -- the whole job moves about one copy of the named rows, spread over the links. `meth_rows` must
+ * be page-locked for every device (epx_host_alloc is portable); pageable memory: replicas through
+ * epx_multi_set_methylation_rows, then epx_multi_analyze. EPX_NO_ZEROCOPY in the environment forces the pageable path
+ * of both calls. */
+int  epx_multi_analyze_host(epx_multi *m, const double *meth_rows, int64_t n_probes, int64_t ld,
+                            const double *expr, int64_t n_genes, int64_t n_samples,
+                            const int64_t *row_ptr, const int32_t *probe_idx, const epx_options *opt,
+                            epx_result *out, char *err, size_t errlen);
 
 #ifdef __cplusplus
 }

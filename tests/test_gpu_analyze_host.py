@@ -171,3 +171,37 @@ def test_empty_index_and_bad_arguments():
         with pytest.raises(ValueError):
             s.analyze_host(yp[:, :20], x, idx.row_ptr, idx.probe_idx)   # sample counts differ
         assert_parity(s.analyze_host(yp, x, idx.row_ptr, idx.probe_idx), run_oracle(x, y, idx), "after the errors")
+
+
+def test_several_devices_one_process_each_fetches_the_rows_of_its_gene_range():
+    """epx_multi_analyze_host. On a one-GPU box the sessions share device 0 -- the gene cuts, the per-device indices and
+    the row fetch are the same code."""
+    from epimethex_b200.annotation import build_groups
+    nd = min(_native.device_count(), 4)
+    devices = list(range(nd)) if nd >= 2 else [0, 0, 0]
+    x, y, idx = _synth(300, 99, 5000, missing_every=37)
+    x2, _, idx2 = _synth(300, 99, 5000, first=0, last=150)
+    assert (idx.probe_idx < 0).any()
+    yp = _pinned(y)
+    gi = build_groups(idx, "gene")
+    with _native.Session(0) as s:
+        s.set_methylation(y)
+        one = s.analyze(x, idx.row_ptr, idx.probe_idx)
+        one_groups = s.analyze_groups(gi.group_ptr, gi.group_pairs)
+        one2 = s.analyze(x2, idx2.row_ptr, idx2.probe_idx)
+    with _native.MultiSession(devices) as ms:
+        for _ in range(2):      # twice: the sessions and their allocations are reused
+            _same(ms.analyze_host(yp, x, idx.row_ptr, idx.probe_idx), one, "multi analyze_host")
+        got = ms.analyze_groups(gi.group_ptr, gi.group_pairs)
+        assert np.array_equal(got.group, one_groups.group, equal_nan=True) and np.array_equal(got.group_dnum, one_groups.group_dnum)
+        # every device holds the rows of ITS range of THIS index only: the resident-matrix call refuses another index
+        with pytest.raises(_native.EpxError, match="EPX_ESTATE"):
+            ms.analyze(x2, idx2.row_ptr, idx2.probe_idx)
+        _same(ms.analyze_host(yp, x2, idx2.row_ptr, idx2.probe_idx), one2, "multi analyze_host, next range")
+        # pageable matrix: replicas through the staged upload, after which any index works
+        _same(ms.analyze_host(y, x, idx.row_ptr, idx.probe_idx), one, "multi analyze_host, pageable")
+        _same(ms.analyze(x2, idx2.row_ptr, idx2.probe_idx), one2, "replicas resident")
+        # a NaN in a named row is refused by the device that fetches it
+        yp[int(idx.probe_idx[idx.probe_idx >= 0][-1]), 3] = np.nan
+        with pytest.raises(_native.EpxError, match="EPX_EINVAL"):
+            ms.analyze_host(yp, x, idx.row_ptr, idx.probe_idx)
