@@ -40,6 +40,16 @@ def test_no_gpu_is_an_error_not_a_fallback():
         _native.Session(0)
 
 
+def test_one_shot_calls_refuse_null_handles_before_touching_a_device():
+    """epx_analyze / epx_analyze_host / epx_multi_analyze(_host): argument checks come first, with a message, on any box"""
+    L = _native.lib()
+    for name, nargs in (("epx_analyze", 8), ("epx_analyze_host", 11), ("epx_multi_analyze", 8), ("epx_multi_analyze_host", 11)):
+        b = C.create_string_buffer(256)
+        args = [None if t is C.c_void_p or hasattr(t, "contents") else 0 for t in getattr(L, name).argtypes[:nargs]]
+        assert getattr(L, name)(*args, b, len(b)) == -1, name
+        assert b.value, f"{name}: no message"
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "epimethex_b200")
     for dirpath, _, files in os.walk(pkg):
